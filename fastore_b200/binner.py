@@ -1,0 +1,119 @@
+"""Python mirror of the reference interface for the hot path, over the C ABI.
+
+Reference: `categorizer.Categorize(reads, dnaBins); packer.PackToBins(dnaBins, binBins)`
+(BinModule.cpp:130-133).  Here: `GpuBinner(params).bin_chunks([chunk, ...]) -> [BinBlock, ...]`.
+All compute happens in libfastore_b200.so on the GPU; a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+
+
+class FastoreError(RuntimeError):
+    """Mirrors the reference's `Exception` (Exception.h:20-40): carries the library's message."""
+
+
+@dataclass
+class BinBlock:
+    """One BinaryBinBlock (BinBlockData.h:62-180): four packed streams + per-bin descriptors."""
+    meta: np.ndarray
+    dna: np.ndarray
+    qua: np.ndarray
+    head: np.ndarray
+    bins: np.ndarray            # BIN_DESC_DTYPE, ascending signature, N-bin last
+    raw_dna_size: int
+    raw_head_size: int
+    n_records: int
+    read_signature: np.ndarray | None = None
+    read_info: np.ndarray | None = None
+
+
+class GpuBinner:
+    def __init__(self, params: N.FsbParams, device: int = 0, stream: int | None = None, per_read: bool = False,
+                 profile: bool = False):
+        self._lib = N.cuda_lib()
+        self._ctx = C.c_void_p()
+        self.params = params
+        rc = self._lib.fsb_create(C.byref(params), device, C.c_void_p(stream) if stream else None, C.byref(self._ctx))
+        if rc != N.FSB_OK:
+            msg = self._lib.fsb_last_error(None)
+            raise FastoreError(f"fsb_create failed ({rc}): {msg.decode() if msg else ''}")
+        if per_read:
+            self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_PER_READ, 1))
+        if profile:
+            self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_PROFILE, 1))
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.fsb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != N.FSB_OK:
+            msg = self._lib.fsb_last_error(self._ctx)
+            raise FastoreError(f"fastore_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    # -- the path ---------------------------------------------------------------------------------
+    @staticmethod
+    def _chunk_array(chunks):
+        arr = (N.FsbChunk * len(chunks))()
+        for i, ch in enumerate(chunks):
+            arr[i] = ch
+        return arr
+
+    def bin_chunks(self, chunks) -> list[BinBlock]:
+        """Host buffers in, host blocks out (H2D + kernels + D2H), one BinBlock per chunk."""
+        arr = self._chunk_array(chunks)
+        blocks = (N.FsbBlock * len(chunks))()
+        self._check(self._lib.fsb_bin_chunks(self._ctx, arr, len(chunks), blocks))
+        return [self._to_block(b) for b in blocks]
+
+    def stage(self, chunks):
+        self._n_staged = len(chunks)
+        self._check(self._lib.fsb_stage(self._ctx, self._chunk_array(chunks), len(chunks)))
+
+    def run(self):
+        self._check(self._lib.fsb_run(self._ctx))
+
+    def sync(self):
+        self._check(self._lib.fsb_sync(self._ctx))
+
+    def fetch(self, copy=True):
+        blocks = (N.FsbBlock * self._n_staged)()
+        self._check(self._lib.fsb_fetch(self._ctx, blocks, self._n_staged))
+        return [self._to_block(b) for b in blocks] if copy else blocks
+
+    def stage_times(self):
+        ms = (C.c_float * 4)()
+        runs = C.c_uint32()
+        self._check(self._lib.fsb_stage_times(self._ctx, ms, 4, C.byref(runs)))
+        return {n: float(ms[i]) for i, n in enumerate(N.FSB_STAGE_NAMES)}, int(runs.value)
+
+    def stats(self) -> dict:
+        s = N.FsbStats()
+        self._check(self._lib.fsb_get_stats(self._ctx, C.byref(s)))
+        return {f: int(getattr(s, f)) for f, _ in N.FsbStats._fields_}
+
+    @staticmethod
+    def _to_block(b) -> BinBlock:
+        d = N.block_to_dict(b)
+        return BinBlock(d["meta"], d["dna"], d["qua"], d["head"], d["bins"], d["raw_dna_size"], d["raw_head_size"],
+                        d["n_records"], d["read_signature"], d["read_info"])

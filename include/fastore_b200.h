@@ -1,0 +1,217 @@
+/*
+ * fastore_b200.h -- C ABI of the B200-native fastore_bin categorise + scatter path.
+ *
+ * This is the drop-in boundary.  One call takes parsed FASTQ chunks (the chunk text as cut by the
+ * host chunk cutter plus a compact record table produced by the host parser) and returns, per
+ * chunk, what the reference produces with
+ *
+ *     FastqCategorizerSE/PE::Categorize(records, bins)      (FastqCategorizer.h:68-69, .cpp:169-363)
+ *     FastqRecordsPackerSE/PE::PackToBins(bins, binBlock)   (FastqPacker.h:127-128, .cpp:417-491)
+ *
+ * i.e. the content of one BinaryBinBlock (BinBlockData.h:62-180): four MSB-first bit streams
+ * (meta / dna / qua / head), byte-aligned per bin, bins in ascending signature order with the
+ * N-bin last, in-bin order = chunk parse order, plus one BinaryBinDescriptor per bin.
+ * The block is consumed unchanged by BinFileWriter::WriteNextBlock (BinFile.cpp:85-222).
+ *
+ * Plain C, plain pointers and sizes.  No CUDA or torch types cross this boundary (the optional
+ * stream handle is an opaque void*).  There is no CPU fallback: every entry point that computes
+ * fails with FSB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FASTORE_B200_H
+#define FASTORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSB_VERSION 1
+
+/* status codes (reference: `throw Exception(msg)`, Exception.h:20-40; no exceptions cross the ABI) */
+enum {
+    FSB_OK = 0,
+    FSB_ERR_PARAM = 1,      /* invalid parameter / unsupported configuration */
+    FSB_ERR_INPUT = 2,      /* record table violates the contract (symbols, lengths, offsets) */
+    FSB_ERR_CUDA = 3,       /* CUDA runtime failure or no usable device */
+    FSB_ERR_NOMEM = 4,      /* host or device allocation failure */
+    FSB_ERR_STATE = 5       /* call sequence error (e.g. fetch before run) */
+};
+
+/* quality modes: QualityCompressionParams::CompressionMethod (Quality.h:29-35) */
+enum { FSB_QUA_NONE = 0, FSB_QUA_BINARY = 1, FSB_QUA_8BIN = 2, FSB_QUA_QVZ = 3 };
+
+/* per-read flags: FastqRecord::RecordFlags (FastqRecord.h:34-38), stored in read_info bits 16.. */
+#define FSB_INFO_POS_MASK     0x0000FFFFu   /* minimPos in the stored orientation            */
+#define FSB_INFO_REVERSE      0x00010000u   /* FlagReadIsReverse                             */
+#define FSB_INFO_SWAPPED      0x00020000u   /* FlagIsPairSwapped (PE only)                   */
+#define FSB_INFO_PLAIN_A      0x00040000u   /* stored mate A has no 'N' (isDnaPlain)         */
+#define FSB_INFO_PLAIN_B      0x00080000u   /* stored mate B has no 'N' (PE only)            */
+
+/*
+ * Binning parameters: the subset of BinModuleConfig (Params.h:167-193) the path reads.
+ *   signature_len              MinimizerParameters::signatureLen      (-p, 1..15)
+ *   skip_zone_len              MinimizerParameters::skipZoneLen       (-s)
+ *   signature_mask_cutoff_bits MinimizerParameters::signatureMaskCutoffBits (no CLI flag, 0)
+ *   paired_end                 ArchiveType::readType == READ_PE       (-z)
+ *   quality_method             QualityCompressionParams::method       (-q0..3)
+ *   quality_offset             ArchiveType::qualityOffset             (33, or 64 with -I)
+ *   binary_threshold           QualityCompressionParams::binaryThreshold (-w, default 20)
+ *   reads_have_headers         ArchiveType::readsHaveHeaders          (-H)
+ *   dna_symbol_order           MinimizerParameters::dnaSymbolOrder    (only "ACGTN" is accepted)
+ */
+typedef struct fsb_params {
+    uint8_t signature_len;
+    uint8_t skip_zone_len;
+    uint8_t signature_mask_cutoff_bits;
+    uint8_t paired_end;
+    uint8_t quality_method;
+    uint8_t quality_offset;
+    uint8_t binary_threshold;
+    uint8_t reads_have_headers;
+    char    dna_symbol_order[5];
+    uint8_t reserved[3];
+} fsb_params;
+
+/*
+ * One parsed FASTQ record = what SingleFastqRecordParser::ReadNextRecord (FastqParser.cpp:118-165)
+ * leaves in a FastqRecord (FastqRecord.h:41-49), as byte offsets into the chunk text instead of
+ * pointers.  head_off points at the '@'; head_len is 0 when headers are not kept.
+ */
+typedef struct fsb_record {
+    uint32_t head_off;
+    uint32_t seq_off;
+    uint32_t qua_off;
+    uint16_t seq_len;
+    uint8_t  head_len;
+    uint8_t  reserved;
+} fsb_record;
+
+/*
+ * One input chunk (FastqChunk / FastqChunkCollectionSE,PE: FastqRecord.h:336-391).
+ * SE uses index 0 only.  PE: text[0]/records[0] are mate 1, text[1]/records[1] mate 2, record i
+ * of both tables forms pair i; the two mates of a pair must have equal length (the reference
+ * ASSERTs this, FastqRecord.h:87,192) and only mate 1's header is kept (FastqPacker.cpp:854).
+ */
+typedef struct fsb_chunk {
+    const uint8_t*    text[2];
+    uint64_t          text_size[2];
+    const fsb_record* records[2];
+    uint64_t          n_records;
+} fsb_chunk;
+
+/* BinaryBinDescriptor (BinBlockData.h:27-55) + the bin's signature (the map key). */
+typedef struct fsb_bin_descriptor {
+    uint64_t signature;      /* 0 .. 4^k ; 4^k is the N-bin */
+    uint64_t meta_size;
+    uint64_t dna_size;
+    uint64_t qua_size;
+    uint64_t head_size;
+    uint64_t records_count;
+    uint64_t raw_dna_size;
+    uint64_t raw_head_size;
+} fsb_bin_descriptor;
+
+/*
+ * One output block = BinaryBinBlock with blockType == MultiSignatureType (BinBlockData.h:62-180).
+ * All pointers are library-owned pinned host memory, valid until the next fsb_fetch /
+ * fsb_bin_chunks / fsb_destroy on the same context.  read_signature / read_info are per record in
+ * chunk parse order (signature, minimPos | flags); they are NULL unless per-read output was
+ * enabled with fsb_set_option(ctx, FSB_OPT_PER_READ, 1).
+ */
+typedef struct fsb_block {
+    const uint8_t* meta;
+    const uint8_t* dna;
+    const uint8_t* qua;
+    const uint8_t* head;
+    uint64_t meta_size;
+    uint64_t dna_size;
+    uint64_t qua_size;
+    uint64_t head_size;
+    uint64_t raw_dna_size;
+    uint64_t raw_head_size;
+    const fsb_bin_descriptor* bins;   /* ascending signature, N-bin last */
+    uint64_t n_bins;
+    uint64_t n_records;
+    const uint32_t* read_signature;
+    const uint32_t* read_info;
+} fsb_block;
+
+typedef struct fsb_ctx fsb_ctx;
+
+/* options for fsb_set_option */
+enum {
+    FSB_OPT_PER_READ = 1,    /* also return per-read signature/info arrays (parity Mode B)        */
+    FSB_OPT_PROFILE = 2,     /* record CUDA events around every pipeline stage of fsb_run         */
+    FSB_OPT_VALIDATE = 3     /* device-side input validation (symbols / quality range), default 1 */
+};
+
+/* pipeline stages reported by fsb_stage_times (order of execution inside fsb_run) */
+enum {
+    FSB_STAGE_SIGNATURE = 0, /* K1: per-read minimizer signature, both strands                    */
+    FSB_STAGE_SORT = 1,      /* K2/K3: histogram + scan + stable rank (radix passes)              */
+    FSB_STAGE_LAYOUT = 2,    /* bin boundaries, per-bin length stats, bit-offset scans            */
+    FSB_STAGE_PACK = 3,      /* K4: bit-pack + scatter into the four streams                      */
+    FSB_STAGE_COUNT = 4
+};
+
+typedef struct fsb_stats {
+    uint64_t kernel_launches;      /* kernels of this library launched since creation              */
+    uint64_t h2d_bytes;            /* bytes copied host->device since creation                     */
+    uint64_t d2h_bytes;            /* bytes copied device->host since creation                     */
+    uint64_t records;              /* records binned since creation                                */
+    uint64_t algorithmic_bytes;    /* input bytes consumed + output bytes produced    */
+} fsb_stats;
+
+/*
+ * Create a context bound to one GPU.  `cuda_stream` may be NULL (the context creates its own
+ * stream) or a cudaStream_t the caller owns; all work of the context is enqueued on that stream.
+ * One context per GPU worker; calls on one context must be serialised by the caller, different
+ * contexts are independent (reference: one BinEncoder operator per thread, BinOperator.cpp:71).
+ */
+int  fsb_create(const fsb_params* params, int device, void* cuda_stream, fsb_ctx** out_ctx);
+void fsb_destroy(fsb_ctx* ctx);
+
+/* Message of the last error on this context; with ctx == NULL, of the last failed fsb_create. */
+const char* fsb_last_error(const fsb_ctx* ctx);
+
+int fsb_set_option(fsb_ctx* ctx, int option, int64_t value);
+
+/*
+ * Categorise + pack `n_chunks` chunks held in host memory: host->device copies, kernels,
+ * device->host copies, synchronous.  blocks[i] describes chunk i.  This is the call that replaces
+ * the Categorize + PackToBins pair at BinModule.cpp:130-133 / :379-382 and
+ * BinOperator.cpp:97+205 / :375+472.
+ */
+int fsb_bin_chunks(fsb_ctx* ctx, const fsb_chunk* chunks, uint32_t n_chunks, fsb_block* blocks);
+
+/*
+ * The same work split into its three phases, for callers that keep input resident or overlap
+ * transfers with compute:
+ *   fsb_stage  enqueue host->device copies of the chunks (text + record tables);
+ *   fsb_run    enqueue the kernels over the staged chunks (may be repeated on the same staging);
+ *   fsb_fetch  enqueue device->host copies of the result, wait, fill `blocks`.
+ * fsb_sync waits for everything enqueued on the context's stream.
+ */
+int fsb_stage(fsb_ctx* ctx, const fsb_chunk* chunks, uint32_t n_chunks);
+int fsb_run(fsb_ctx* ctx);
+int fsb_fetch(fsb_ctx* ctx, fsb_block* blocks, uint32_t n_blocks);
+int fsb_sync(fsb_ctx* ctx);
+
+/* Accumulated per-stage device time in milliseconds since the last call (needs FSB_OPT_PROFILE). */
+int fsb_stage_times(fsb_ctx* ctx, float* ms, uint32_t n_stages, uint32_t* n_runs);
+
+int fsb_get_stats(const fsb_ctx* ctx, fsb_stats* out);
+
+/* Pinned host memory for chunk text / record tables (optional; pageable memory also works). */
+void* fsb_host_alloc(size_t bytes);
+void  fsb_host_free(void* p);
+
+/* Number of usable sm_100 devices (0 when there is none; never falls back to the CPU). */
+int fsb_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTORE_B200_H */
