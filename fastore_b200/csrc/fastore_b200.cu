@@ -1,0 +1,626 @@
+// fastore_b200.cu -- the C ABI of include/fastore_b200.h: context, staging, the kernel pipeline
+// (K1 signature -> stable radix sort -> layout scans -> K4 pack) and result fetch.
+//
+// Host-side structure mirrors what the reference does per chunk in its -t1 loop
+// (BinModule.cpp:124-167): Categorize(reads, bins); PackToBins(bins, block).  Several chunks may be
+// processed by one pass of the pipeline ("batch"): bins are keyed by (chunk, signature), so every
+// chunk still yields exactly its own BinaryBinBlock, byte for byte.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fastore_b200.h"
+#include "scan_sort.cuh"
+#include "signature.cuh"
+#include "layout.cuh"
+#include "pack.cuh"
+
+using namespace fsb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr size_t kTextPad = 64;           // slack around every chunk text: aligned vector loads may over-read
+constexpr uint32_t kMaxChunksPerBatch = 256;
+constexpr int kMaxPendingProfiles = 256;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+} // namespace
+
+struct fsb_ctx
+{
+    fsb_params params{};
+    DeviceParams dp{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    bool per_read = false, profile = false, validate = true;
+
+    // ---- staged batch -------------------------------------------------------------------------
+    bool staged = false, ran = false;
+    uint32_t n_chunks = 0;
+    uint64_t n_records = 0;
+    std::vector<uint64_t> chunk_first_rec;       // n_chunks + 1
+    std::vector<uint64_t> chunk_text_base[2];
+    uint64_t total_bases = 0, total_head = 0;
+    uint64_t nb_max = 0;
+    uint64_t algorithmic_in = 0;
+    size_t out_cap[4] = {0, 0, 0, 0};
+    int sort_passes = 0;
+
+    DevBuf d_text[2], d_rec[2], d_chunk_meta;
+    DevBuf d_keys[2], d_vals[2], d_info, d_sig, d_counts, d_counts_scan, d_scan_tmp;
+    DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head;
+    DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4], d_desc, d_summary, d_out[4];
+    PinBuf h_summary, h_out[4], h_desc, h_sig, h_info;
+    uint32_t* sorted_keys = nullptr;
+    uint32_t* sorted_vals = nullptr;
+
+    // ---- profiling -----------------------------------------------------------------------------
+    std::vector<cudaEvent_t> events;             // kMaxPendingProfiles * (FSB_STAGE_COUNT + 1)
+    int pending_profiles = 0;
+    float stage_ms[FSB_STAGE_COUNT] = {0, 0, 0, 0};
+    uint32_t stage_runs = 0;
+
+    fsb_stats stats{};
+};
+
+namespace {
+
+int fail(fsb_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? FSB_ERR_NOMEM : FSB_ERR_CUDA,            \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+
+uint32_t bits_for(uint32_t v) { uint32_t b = 0; while ((1ull << b) <= v) ++b; return b; }   // bits to represent v
+
+int resolve_profiles(fsb_ctx* c)
+{
+    if (c->pending_profiles == 0) return FSB_OK;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < c->pending_profiles; ++r)
+    {
+        cudaEvent_t* ev = &c->events[(size_t)r * (FSB_STAGE_COUNT + 1)];
+        for (int s = 0; s < FSB_STAGE_COUNT; ++s)
+        {
+            float ms = 0;
+            CUDA_TRY(c, cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+            c->stage_ms[s] += ms;
+        }
+        c->stage_runs++;
+    }
+    c->pending_profiles = 0;
+    return FSB_OK;
+}
+
+} // namespace
+
+extern "C" int fsb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    int ok = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+extern "C" const char* fsb_last_error(const fsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fsb_ctx** out)
+{
+    if (!p || !out) return fail(nullptr, FSB_ERR_PARAM, "fsb_create: null argument");
+    *out = nullptr;
+    // MinimizerParameters (Params.h:22-96): k <= 15 because TotalMinimizersCount() is 1 << 2k in an int (:55-58);
+    // k >= 3 because the AAA/AAC test shifts by 2k-6 (FastqCategorizer.cpp:56)
+    if (p->signature_len < 3 || p->signature_len > 15) return fail(nullptr, FSB_ERR_PARAM, "signature_len must be in [3, 15]");
+    if (p->signature_mask_cutoff_bits >= 2 * p->signature_len) return fail(nullptr, FSB_ERR_PARAM, "signature_mask_cutoff_bits too large");
+    if (std::memcmp(p->dna_symbol_order, "ACGTN", 5) != 0) return fail(nullptr, FSB_ERR_PARAM, "only dna_symbol_order \"ACGTN\" is supported");
+    if (p->quality_method > FSB_QUA_QVZ) return fail(nullptr, FSB_ERR_PARAM, "quality_method must be 0..3");
+    if (p->quality_method == FSB_QUA_BINARY && p->binary_threshold >= 64) return fail(nullptr, FSB_ERR_PARAM, "binary_threshold must be < 64");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, FSB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, FSB_ERR_PARAM, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, FSB_ERR_CUDA, "device is not sm_100 (kernels are built for sm_100a only)");
+
+    fsb_ctx* c = new (std::nothrow) fsb_ctx();
+    if (!c) return fail(nullptr, FSB_ERR_NOMEM, "out of host memory");
+    c->params = *p;
+    c->device = device;
+    DeviceParams& d = c->dp;
+    d.k = p->signature_len; d.s = p->skip_zone_len;
+    d.cutoff_mask = (1u << p->signature_mask_cutoff_bits) - 1;
+    d.nbin = 1u << (2 * d.k); d.kmer_mask = d.nbin - 1;
+    d.paired = p->paired_end ? 1 : 0;
+    d.qua_method = p->quality_method; d.qua_offset = p->quality_offset; d.qua_threshold = p->binary_threshold;
+    static const uint32_t bpb[4] = {6, 1, 3, 6};                 // QualityCompressionParams::BitsPerBase (Quality.h:58-64)
+    d.qua_bits = bpb[p->quality_method];
+    d.has_headers = p->reads_have_headers ? 1 : 0;
+    d.key_bits = 2 * d.k + 1;
+
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail(nullptr, FSB_ERR_CUDA, "cudaSetDevice failed"); }
+    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else
+    {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(nullptr, FSB_ERR_CUDA, "cudaStreamCreate failed"); }
+        c->own_stream = true;
+    }
+    *out = c;
+    return FSB_OK;
+}
+
+extern "C" void fsb_destroy(fsb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& e : c->events) cudaEventDestroy(e);
+    DevBuf* dev[] = {&c->d_text[0], &c->d_text[1], &c->d_rec[0], &c->d_rec[1], &c->d_chunk_meta, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0],
+                     &c->d_vals[1], &c->d_info, &c->d_sig, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags, &c->d_flags_excl,
+                     &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
+                     &c->d_bits[2], &c->d_bits[3], &c->d_P[0], &c->d_P[1], &c->d_P[2], &c->d_P[3], &c->d_bytes[0], &c->d_bytes[1],
+                     &c->d_bytes[2], &c->d_bytes[3], &c->d_BO[0], &c->d_BO[1], &c->d_BO[2], &c->d_BO[3], &c->d_desc, &c->d_summary,
+                     &c->d_out[0], &c->d_out[1], &c->d_out[2], &c->d_out[3]};
+    for (DevBuf* b : dev) b->release();
+    PinBuf* pin[] = {&c->h_summary, &c->h_out[0], &c->h_out[1], &c->h_out[2], &c->h_out[3], &c->h_desc, &c->h_sig, &c->h_info};
+    for (PinBuf* b : pin) b->release();
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int fsb_set_option(fsb_ctx* c, int option, int64_t value)
+{
+    if (!c) return FSB_ERR_PARAM;
+    switch (option)
+    {
+    case FSB_OPT_PER_READ: c->per_read = value != 0; return FSB_OK;
+    case FSB_OPT_PROFILE: c->profile = value != 0; return FSB_OK;
+    case FSB_OPT_VALIDATE: c->validate = value != 0; return FSB_OK;
+    }
+    return fail(c, FSB_ERR_PARAM, "unknown option");
+}
+
+extern "C" void* fsb_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void fsb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int fsb_sync(fsb_ctx* c)
+{
+    if (!c) return FSB_ERR_PARAM;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return FSB_OK;
+}
+
+extern "C" int fsb_get_stats(const fsb_ctx* c, fsb_stats* out)
+{
+    if (!c || !out) return FSB_ERR_PARAM;
+    *out = c->stats;
+    return FSB_OK;
+}
+
+extern "C" int fsb_stage_times(fsb_ctx* c, float* ms, uint32_t n_stages, uint32_t* n_runs)
+{
+    if (!c || !ms) return FSB_ERR_PARAM;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = resolve_profiles(c);
+    if (rc != FSB_OK) return rc;
+    for (uint32_t s = 0; s < n_stages; ++s) ms[s] = s < FSB_STAGE_COUNT ? c->stage_ms[s] : 0.f;
+    if (n_runs) *n_runs = c->stage_runs;
+    for (int s = 0; s < FSB_STAGE_COUNT; ++s) c->stage_ms[s] = 0;
+    c->stage_runs = 0;
+    return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fsb_stage: validate the record tables' framing on the host (offsets inside the chunk, lengths,
+// PE mate-length equality - the things the reference only ASSERTs: FastqRecord.h:87,
+// FastqParser.cpp:130) and enqueue the host->device copies.
+extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
+{
+    if (!c || (!chunks && n_chunks)) return FSB_ERR_PARAM;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->staged = false; c->ran = false;
+    const int nfiles = c->dp.paired ? 2 : 1;
+    const uint32_t max_chunks = std::min<uint64_t>(kMaxChunksPerBatch, 1ull << (32 - c->dp.key_bits));
+    if (n_chunks == 0) return fail(c, FSB_ERR_PARAM, "fsb_stage: no chunks");
+    if (n_chunks > max_chunks) return fail(c, FSB_ERR_PARAM, "fsb_stage: too many chunks in one batch for this signature length (max " + std::to_string(max_chunks) + ")");
+
+    c->n_chunks = n_chunks;
+    c->chunk_first_rec.assign(n_chunks + 1, 0);
+    size_t text_bytes[2] = {kTextPad, kTextPad};
+    for (int m = 0; m < 2; ++m) c->chunk_text_base[m].assign(n_chunks, 0);
+    uint64_t n = 0, bases = 0, heads = 0;
+    for (uint32_t ci = 0; ci < n_chunks; ++ci)
+    {
+        const fsb_chunk& ch = chunks[ci];
+        c->chunk_first_rec[ci] = n;
+        for (int m = 0; m < nfiles; ++m)
+        {
+            if (ch.n_records && (!ch.text[m] || !ch.records[m])) return fail(c, FSB_ERR_PARAM, "fsb_stage: null text/records");
+            if (ch.text_size[m] >= 0xFFFFFFFFull) return fail(c, FSB_ERR_INPUT, "fsb_stage: chunk text must be < 4 GiB (32-bit record offsets)");
+            c->chunk_text_base[m][ci] = text_bytes[m];
+            text_bytes[m] = align_up(text_bytes[m] + ch.text_size[m] + kTextPad, 256);
+        }
+        if (c->validate)
+        {
+            const fsb_record* r0 = ch.records[0];
+            const fsb_record* r1 = nfiles == 2 ? ch.records[1] : nullptr;
+            for (uint64_t i = 0; i < ch.n_records; ++i)
+            {
+                const fsb_record& a = r0[i];
+                bool ok = a.seq_len >= 1 && a.seq_len <= 255 && (uint64_t)a.seq_off + a.seq_len <= ch.text_size[0] &&
+                          (uint64_t)a.qua_off + a.seq_len <= ch.text_size[0] && (uint64_t)a.head_off + a.head_len <= ch.text_size[0];
+                bases += a.seq_len;
+                heads += a.head_len;
+                if (r1)
+                {
+                    const fsb_record& b = r1[i];
+                    ok = ok && b.seq_len == a.seq_len && (uint64_t)b.seq_off + b.seq_len <= ch.text_size[1] &&
+                         (uint64_t)b.qua_off + b.seq_len <= ch.text_size[1];
+                    bases += b.seq_len;
+                }
+                if (!ok) return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(i) + " of chunk " + std::to_string(ci) +
+                                                           " violates the input contract (length 1..255, offsets inside the chunk, equal PE mate lengths)");
+            }
+        }
+        else
+        {
+            // bounds only: a record has at least 2L + 6 bytes of text; headers are at most the text
+            for (int m = 0; m < nfiles; ++m) bases += ch.text_size[m] / 2;
+            heads += ch.text_size[0];
+        }
+        n += ch.n_records;
+    }
+    c->chunk_first_rec[n_chunks] = n;
+    if (n >= 0xFFFFFFFFull) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^32-2 records in one batch");
+    c->n_records = n;
+    c->total_bases = bases; c->total_head = heads;
+    c->nb_max = std::min<uint64_t>(n, (uint64_t)n_chunks * ((uint64_t)c->dp.nbin + 1));
+    c->sort_passes = (int)((c->dp.key_bits + bits_for(n_chunks - 1) + 7) / 8);
+
+    // ---- device input buffers + copies ----------------------------------------------------------
+    uint64_t h2d = 0;
+    for (int m = 0; m < nfiles; ++m)
+    {
+        CUDA_TRY(c, c->d_text[m].ensure(text_bytes[m] + kTextPad));
+        CUDA_TRY(c, c->d_rec[m].ensure((n + 1) * sizeof(fsb_record)));
+        for (uint32_t ci = 0; ci < n_chunks; ++ci)
+        {
+            const fsb_chunk& ch = chunks[ci];
+            if (ch.text_size[m])
+                CUDA_TRY(c, cudaMemcpyAsync(c->d_text[m].as<uint8_t>() + c->chunk_text_base[m][ci], ch.text[m], ch.text_size[m], cudaMemcpyHostToDevice, c->stream));
+            if (ch.n_records)
+                CUDA_TRY(c, cudaMemcpyAsync(c->d_rec[m].as<fsb_record>() + c->chunk_first_rec[ci], ch.records[m], ch.n_records * sizeof(fsb_record),
+                                            cudaMemcpyHostToDevice, c->stream));
+            h2d += ch.text_size[m] + ch.n_records * sizeof(fsb_record);
+        }
+    }
+    // chunk tables: [first_rec (n_chunks+1)] [text_base0 (n_chunks)] [text_base1 (n_chunks)]
+    {
+        std::vector<uint64_t> meta;
+        meta.insert(meta.end(), c->chunk_first_rec.begin(), c->chunk_first_rec.end());
+        meta.insert(meta.end(), c->chunk_text_base[0].begin(), c->chunk_text_base[0].end());
+        meta.insert(meta.end(), c->chunk_text_base[1].begin(), c->chunk_text_base[1].end());
+        CUDA_TRY(c, c->d_chunk_meta.ensure(meta.size() * sizeof(uint64_t)));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // `meta` (and pageable user buffers) must outlive the copies
+        h2d += meta.size() * sizeof(uint64_t);
+    }
+    c->stats.h2d_bytes += h2d;
+
+    // ---- intermediate + output buffers (grow-only) -----------------------------------------------
+    const uint64_t nsort_blocks = (n + kSortTile - 1) / kSortTile;
+    const uint64_t ncounts = (uint64_t)kRadix * std::max<uint64_t>(nsort_blocks, 1);
+    for (int i = 0; i < 2; ++i)
+    {
+        CUDA_TRY(c, c->d_keys[i].ensure((n + 1) * 4));
+        CUDA_TRY(c, c->d_vals[i].ensure((n + 1) * 4));
+    }
+    CUDA_TRY(c, c->d_info.ensure((n + 1) * 4));
+    CUDA_TRY(c, c->d_sig.ensure((n + 1) * 4));
+    CUDA_TRY(c, c->d_counts.ensure((ncounts + 1) * 4));
+    CUDA_TRY(c, c->d_counts_scan.ensure((ncounts + 1) * 4));
+    const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(n, ncounts), c->nb_max) + 1;
+    CUDA_TRY(c, c->d_scan_tmp.ensure((scan_num_tiles(max_scan_n) + 2) * 8));
+    CUDA_TRY(c, c->d_flags.ensure((n + 1) * 4));
+    CUDA_TRY(c, c->d_flags_excl.ensure((n + 2) * 4));
+    CUDA_TRY(c, c->d_bin_of.ensure((n + 1) * 4));
+    CUDA_TRY(c, c->d_bin_start.ensure((c->nb_max + 2) * 4));
+    CUDA_TRY(c, c->d_bin_min.ensure((c->nb_max + 1) * 4));
+    CUDA_TRY(c, c->d_bin_max.ensure((c->nb_max + 1) * 4));
+    CUDA_TRY(c, c->d_raw_dna.ensure((c->nb_max + 1) * 8));
+    CUDA_TRY(c, c->d_raw_head.ensure((c->nb_max + 1) * 8));
+    for (int s = 0; s < 4; ++s)
+    {
+        CUDA_TRY(c, c->d_bits[s].ensure((n + 1) * 4));
+        CUDA_TRY(c, c->d_P[s].ensure((n + 2) * 8));
+        CUDA_TRY(c, c->d_bytes[s].ensure((c->nb_max + 1) * 8));
+        CUDA_TRY(c, c->d_BO[s].ensure((c->nb_max + 2) * 8));
+    }
+    CUDA_TRY(c, c->d_desc.ensure((c->nb_max + 1) * sizeof(fsb_bin_descriptor)));
+    CUDA_TRY(c, c->d_summary.ensure((size_t)n_chunks * sizeof(ChunkSummary)));
+    // upper bounds of the stream sizes (exact sizes are only known on the device after the layout scans)
+    const uint64_t pad_bytes = c->nb_max + 64;                              // < 1 byte of padding per bin and stream
+    c->out_cap[0] = align_up((28 * n + 17 * c->nb_max) / 8 + pad_bytes, 64);
+    c->out_cap[1] = align_up(3 * bases / 8 + pad_bytes, 64);
+    c->out_cap[2] = align_up((uint64_t)c->dp.qua_bits * bases / 8 + pad_bytes, 64);
+    c->out_cap[3] = align_up(c->dp.has_headers ? (8 * n + 7 * heads) / 8 + pad_bytes : 64, 64);
+    for (int s = 0; s < 4; ++s) CUDA_TRY(c, c->d_out[s].ensure(c->out_cap[s]));
+
+    // SURVEY 8(d) algorithmic input bytes: every sequence, quality and kept header byte once
+    c->algorithmic_in = 2 * bases + (c->dp.has_headers ? heads : 0);
+    c->staged = true;
+    return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int fsb_run(fsb_ctx* c)
+{
+    if (!c) return FSB_ERR_PARAM;
+    if (!c->staged) return fail(c, FSB_ERR_STATE, "fsb_run: nothing staged");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint64_t n = c->n_records;
+    const DeviceParams& P = c->dp;
+    uint64_t launches = 0;
+
+    cudaEvent_t* ev = nullptr;
+    if (c->profile)
+    {
+        if (c->pending_profiles == kMaxPendingProfiles) { int rc = resolve_profiles(c); if (rc != FSB_OK) return rc; }
+        const size_t need = (size_t)(c->pending_profiles + 1) * (FSB_STAGE_COUNT + 1);
+        while (c->events.size() < need) { cudaEvent_t e; CUDA_TRY(c, cudaEventCreate(&e)); c->events.push_back(e); }
+        ev = &c->events[(size_t)c->pending_profiles * (FSB_STAGE_COUNT + 1)];
+        CUDA_TRY(c, cudaEventRecord(ev[0], st));
+    }
+
+    BatchView B{};
+    const uint64_t* meta = c->d_chunk_meta.as<uint64_t>();
+    B.text[0] = c->d_text[0].as<uint8_t>(); B.text[1] = c->d_text[1].as<uint8_t>();
+    B.rec[0] = c->d_rec[0].as<fsb_record>(); B.rec[1] = c->d_rec[1].as<fsb_record>();
+    B.chunk_first_rec = meta;
+    B.chunk_text_base[0] = meta + (c->n_chunks + 1);
+    B.chunk_text_base[1] = meta + (c->n_chunks + 1) + c->n_chunks;
+    B.n_chunks = c->n_chunks; B.n_records = n;
+
+    const unsigned tpb = 256;
+    const unsigned grid_n = (unsigned)std::max<uint64_t>(1, (n + tpb - 1) / tpb);
+
+    // ---- K1: signatures ---------------------------------------------------------------------------
+    if (n)
+    {
+        const uint64_t warps_needed = n;
+        const unsigned blocks = (unsigned)std::min<uint64_t>((warps_needed + 7) / 8, 148ull * 32);
+        signature_kernel<<<blocks, 256, 0, st>>>(B, P, c->d_keys[0].as<uint32_t>(), c->d_info.as<uint32_t>(),
+                                                   c->per_read ? c->d_sig.as<uint32_t>() : nullptr);
+        launches++;
+    }
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[1], st));
+
+    // ---- K2/K3: stable radix sort of (chunk:signature, record index) ----------------------------------
+    int cur = 0;
+    if (n)
+    {
+        const uint32_t nblocks = (uint32_t)((n + kSortTile - 1) / kSortTile);
+        const uint64_t ncounts = (uint64_t)kRadix * nblocks;
+        for (int pass = 0; pass < c->sort_passes; ++pass)
+        {
+            const int shift = 8 * pass;
+            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), n, shift, c->d_counts.as<uint32_t>(), nblocks);
+            launches++;
+            launches += exclusive_scan<uint32_t, uint32_t>(c->d_counts.as<uint32_t>(), ncounts, c->d_counts_scan.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
+            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), pass == 0 ? nullptr : c->d_vals[cur].as<uint32_t>(), n, shift,
+                                                            c->d_counts_scan.as<uint32_t>(), nblocks, c->d_keys[cur ^ 1].as<uint32_t>(),
+                                                            c->d_vals[cur ^ 1].as<uint32_t>());
+            launches++;
+            cur ^= 1;
+        }
+    }
+    c->sorted_keys = c->d_keys[cur].as<uint32_t>();
+    c->sorted_vals = c->d_vals[cur].as<uint32_t>();
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[2], st));
+
+    // ---- layout --------------------------------------------------------------------------------------
+    SortedView S{c->sorted_keys, c->sorted_vals, c->d_info.as<uint32_t>()};
+    BinArrays A{c->d_bin_of.as<uint32_t>(), c->d_bin_start.as<uint32_t>(), c->d_bin_min.as<uint32_t>(), c->d_bin_max.as<uint32_t>(),
+                c->d_raw_dna.as<unsigned long long>(), c->d_raw_head.as<unsigned long long>()};
+    StreamScans SC{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
+    BinOffsets BO{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
+    const uint32_t* nb_ptr = c->d_flags_excl.as<uint32_t>() + n;
+    {
+        const uint64_t nbm = c->nb_max;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_min.p, 0xFF, (nbm + 1) * 4, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_max.p, 0, (nbm + 1) * 4, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_dna.p, 0, (nbm + 1) * 8, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_head.p, 0, (nbm + 1) * 8, st));
+        if (n)
+        {
+            bin_flags_kernel<<<grid_n, tpb, 0, st>>>(c->sorted_keys, n, c->d_flags.as<uint32_t>());
+            launches++;
+        }
+        launches += exclusive_scan<uint32_t, uint32_t>(c->d_flags.as<uint32_t>(), n, c->d_flags_excl.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
+        if (n)
+        {
+            bin_stats_kernel<<<grid_n, tpb, 0, st>>>(B, P, S, c->d_flags.as<uint32_t>(), c->d_flags_excl.as<uint32_t>(), A);
+            read_bits_kernel<<<grid_n, tpb, 0, st>>>(B, P, S, A, c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(),
+                                                      c->d_bits[3].as<uint32_t>());
+            launches += 2;
+        }
+        for (int s = 0; s < 4; ++s)
+            launches += exclusive_scan<uint32_t, uint64_t>(c->d_bits[s].as<uint32_t>(), n, c->d_P[s].as<uint64_t>(), c->d_scan_tmp.as<uint64_t>(), st);
+        if (nbm)
+        {
+            const unsigned grid_b = (unsigned)((nbm + tpb - 1) / tpb);
+            bin_sizes_kernel<<<grid_b, tpb, 0, st>>>(P, n, nb_ptr, nbm, c->sorted_keys, A, SC, c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(),
+                                                      c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>(), c->d_desc.as<fsb_bin_descriptor>());
+            launches++;
+        }
+        for (int s = 0; s < 4; ++s)
+            launches += exclusive_scan<uint64_t, uint64_t>(c->d_bytes[s].as<uint64_t>(), nbm, c->d_BO[s].as<uint64_t>(), c->d_scan_tmp.as<uint64_t>(), st);
+        chunk_summary_kernel<<<c->n_chunks, 128, 0, st>>>(B, nb_ptr, A.bin_of, BO, c->d_desc.as<fsb_bin_descriptor>(), c->d_summary.as<ChunkSummary>());
+        launches++;
+    }
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[3], st));
+
+    // ---- K4: pack ------------------------------------------------------------------------------------
+    for (int s = 0; s < 4; ++s) CUDA_TRY(c, cudaMemsetAsync(c->d_out[s].p, 0, c->out_cap[s], st));
+    if (n)
+    {
+        PackArgs pa{B, P, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}}};
+        const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, 148ull * 32);
+        pack_kernel<<<blocks, 256, 0, st>>>(pa);
+        launches++;
+    }
+    if (ev)
+    {
+        CUDA_TRY(c, cudaEventRecord(ev[4], st));
+        c->pending_profiles++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->stats.kernel_launches += launches;
+    c->stats.records += n;
+    c->ran = true;
+    return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int fsb_fetch(fsb_ctx* c, fsb_block* blocks, uint32_t n_blocks)
+{
+    if (!c || !blocks) return FSB_ERR_PARAM;
+    if (!c->ran) return fail(c, FSB_ERR_STATE, "fsb_fetch: fsb_run has not been called on the staged batch");
+    if (n_blocks != c->n_chunks) return fail(c, FSB_ERR_PARAM, "fsb_fetch: n_blocks must equal the number of staged chunks");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint64_t n = c->n_records;
+    uint64_t d2h = 0;
+
+    CUDA_TRY(c, c->h_summary.ensure((size_t)c->n_chunks * sizeof(ChunkSummary)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_summary.p, c->d_summary.p, (size_t)c->n_chunks * sizeof(ChunkSummary), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    d2h += (size_t)c->n_chunks * sizeof(ChunkSummary);
+    const ChunkSummary* sum = c->h_summary.as<ChunkSummary>();
+    const ChunkSummary& last = sum[c->n_chunks - 1];
+    uint64_t total[4], nb = last.first_bin + last.n_bins;
+    for (int s = 0; s < 4; ++s)
+    {
+        total[s] = last.off[s] + last.size[s];
+        if (total[s] > c->out_cap[s]) return fail(c, FSB_ERR_STATE, "internal error: stream size exceeds its bound");
+        CUDA_TRY(c, c->h_out[s].ensure(total[s] + 64));
+        if (total[s]) CUDA_TRY(c, cudaMemcpyAsync(c->h_out[s].p, c->d_out[s].p, total[s], cudaMemcpyDeviceToHost, st));
+        d2h += total[s];
+    }
+    CUDA_TRY(c, c->h_desc.ensure((nb + 1) * sizeof(fsb_bin_descriptor)));
+    if (nb) CUDA_TRY(c, cudaMemcpyAsync(c->h_desc.p, c->d_desc.p, nb * sizeof(fsb_bin_descriptor), cudaMemcpyDeviceToHost, st));
+    d2h += nb * sizeof(fsb_bin_descriptor);
+    if (c->per_read)
+    {
+        CUDA_TRY(c, c->h_sig.ensure((n + 1) * 4));
+        CUDA_TRY(c, c->h_info.ensure((n + 1) * 4));
+        if (n)
+        {
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_sig.p, c->d_sig.p, n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_info.p, c->d_info.p, n * 4, cudaMemcpyDeviceToHost, st));
+        }
+        d2h += 8 * n;
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->stats.d2h_bytes += d2h;
+
+    uint64_t alg_out = 0;
+    for (uint32_t ci = 0; ci < c->n_chunks; ++ci)
+    {
+        const ChunkSummary& s = sum[ci];
+        fsb_block& b = blocks[ci];
+        std::memset(&b, 0, sizeof(b));
+        b.meta = c->h_out[0].as<uint8_t>() + s.off[0]; b.meta_size = s.size[0];
+        b.dna = c->h_out[1].as<uint8_t>() + s.off[1];  b.dna_size = s.size[1];
+        b.qua = c->h_out[2].as<uint8_t>() + s.off[2];  b.qua_size = s.size[2];
+        b.head = c->h_out[3].as<uint8_t>() + s.off[3]; b.head_size = s.size[3];
+        b.raw_dna_size = s.raw_dna; b.raw_head_size = s.raw_head;
+        b.bins = c->h_desc.as<fsb_bin_descriptor>() + s.first_bin;
+        b.n_bins = s.n_bins;
+        b.n_records = c->chunk_first_rec[ci + 1] - c->chunk_first_rec[ci];
+        if (c->per_read)
+        {
+            b.read_signature = c->h_sig.as<uint32_t>() + c->chunk_first_rec[ci];
+            b.read_info = c->h_info.as<uint32_t>() + c->chunk_first_rec[ci];
+        }
+        alg_out += s.size[0] + s.size[1] + s.size[2] + s.size[3];
+    }
+    c->stats.algorithmic_bytes += c->algorithmic_in + alg_out;
+    return FSB_OK;
+}
+
+extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks, fsb_block* blocks)
+{
+    int rc = fsb_stage(c, chunks, n_chunks);
+    if (rc != FSB_OK) return rc;
+    rc = fsb_run(c);
+    if (rc != FSB_OK) return rc;
+    return fsb_fetch(c, blocks, n_chunks);
+}

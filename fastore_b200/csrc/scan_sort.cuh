@@ -1,0 +1,223 @@
+// scan_sort.cuh -- device-wide exclusive scan and stable LSD radix sort, hand-written for sm_100a.
+//
+// These are the "histogram, prefix-sum and scatter" pieces of the path: the reference builds
+// std::map<uint32, FastqRecordsPtrBin> by push_back in parse order (FastqCategorizer.cpp:247,357),
+// i.e. a *stable* grouping of records by signature.  On the device that is a stable sort of
+// (key = chunk:signature, value = record index): per-block digit histograms in shared memory,
+// a device-wide exclusive scan over the digit-major count table, and a rank-and-scatter pass that
+// keeps equal keys in input order.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fsb {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;                       // items per thread
+constexpr int kScanTile = kScanThreads * kScanItems; // 4096 items per block
+
+// ---- block-wide exclusive scan of one value per thread (256 threads) ----------------------------
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_scan(T v)
+{
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        T o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= (unsigned)d) v += o;
+    }
+    return v;
+}
+
+// returns the exclusive prefix of `v` over the block; `total` receives the block sum (all threads)
+template <typename T, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan(T v, T& total, T* smem /* THREADS/32 + 1 entries */)
+{
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T inc = warp_inclusive_scan(v);
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        T w = (lane < THREADS / 32) ? smem[lane] : T(0);
+        T winc = warp_inclusive_scan(w);
+        if (lane < THREADS / 32) smem[lane] = winc - w;     // exclusive warp offsets
+        if (lane == THREADS / 32 - 1) smem[THREADS / 32] = winc;
+    }
+    __syncthreads();
+    const T res = smem[warp] + inc - v;
+    total = smem[THREADS / 32];
+    __syncthreads();
+    return res;
+}
+
+// ---- three-phase device-wide exclusive scan ------------------------------------------------------
+// phase A: per-tile sums; phase B: one block scans the tile sums; phase C: per-tile scan + offset.
+// IN may be narrower than OUT (u32 counts -> u64 bit offsets).  out[n] (one past the end) receives
+// the grand total, so callers can read segment ends without a special case.
+template <typename IN, typename OUT>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const IN* __restrict__ in, uint64_t n, OUT* __restrict__ tile_sums)
+{
+    __shared__ OUT sm[kScanThreads / 32 + 1];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+    OUT s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const uint64_t idx = base + (uint64_t)i * kScanThreads + threadIdx.x;
+        if (idx < n) s += (OUT)in[idx];
+    }
+    OUT total;
+    block_exclusive_scan<OUT, kScanThreads>(s, total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(1024) scan_small(OUT* __restrict__ data, uint64_t n)
+{
+    // single block, in-place exclusive scan of `n` values (tile sums); data[n] <- total
+    __shared__ OUT sm[1024 / 32 + 1];
+    OUT carry = 0;
+    for (uint64_t base = 0; base < n; base += 1024)
+    {
+        const uint64_t idx = base + threadIdx.x;
+        const OUT v = idx < n ? data[idx] : OUT(0);
+        OUT total;
+        const OUT ex = block_exclusive_scan<OUT, 1024>(v, total, sm);
+        if (idx < n) data[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) data[n] = carry;
+}
+
+template <typename IN, typename OUT>
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const IN* __restrict__ in, uint64_t n, const OUT* __restrict__ tile_offsets,
+                                                            OUT* __restrict__ out)
+{
+    __shared__ OUT sm[kScanThreads / 32 + 1];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    OUT v[kScanItems];
+    OUT s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const uint64_t idx = base + i;
+        v[i] = idx < n ? (OUT)in[idx] : OUT(0);
+        s += v[i];
+    }
+    OUT total;
+    OUT ex = block_exclusive_scan<OUT, kScanThreads>(s, total, sm) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const uint64_t idx = base + i;
+        if (idx < n) out[idx] = ex;
+        ex += v[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) out[n] = tile_offsets[gridDim.x];
+}
+
+inline uint64_t scan_num_tiles(uint64_t n) { return (n + kScanTile - 1) / kScanTile; }
+
+// out must hold n + 1 entries; tmp must hold scan_num_tiles(n) + 1 entries.  3 launches.
+template <typename IN, typename OUT>
+inline int exclusive_scan(const IN* in, uint64_t n, OUT* out, OUT* tmp, cudaStream_t st)
+{
+    if (n == 0)
+    {
+        cudaMemsetAsync(out, 0, sizeof(OUT), st);
+        return 0;
+    }
+    const uint64_t tiles = scan_num_tiles(n);
+    scan_tile_sums<IN, OUT><<<(unsigned)tiles, kScanThreads, 0, st>>>(in, n, tmp);
+    scan_small<OUT><<<1, 1024, 0, st>>>(tmp, tiles);
+    scan_apply<IN, OUT><<<(unsigned)tiles, kScanThreads, 0, st>>>(in, n, tmp, out);
+    return 3;
+}
+
+// ---- stable LSD radix sort, 8-bit digits ---------------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortStrips = 16;                          // 32-key strips per warp
+constexpr int kSortTile = kSortThreads * kSortStrips;    // 4096 keys per block
+constexpr int kRadix = 256;
+
+// counts[digit * nblocks + block]
+__global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* __restrict__ keys, uint64_t n, int shift,
+                                                                uint32_t* __restrict__ counts, uint32_t nblocks)
+{
+    __shared__ uint32_t hist[kRadix];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+#pragma unroll 4
+    for (int i = 0; i < kSortStrips; ++i)
+    {
+        const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
+        const bool in = idx < n;
+        const uint32_t d = in ? ((keys[idx] >> shift) & 0xFFu) : 0xFFFFFFFFu;
+        // warp-aggregated shared atomics: bins are heavily skewed (minimizers are minima)
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        if (in && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    counts[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+// offsets: exclusive scan of counts (same layout).  vals_in == nullptr means "identity" (first pass).
+__global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                              uint64_t n, int shift, const uint32_t* __restrict__ offsets, uint32_t nblocks,
+                                                              uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
+{
+    __shared__ uint32_t warp_hist[kSortThreads / 32][kRadix];   // 8 KB
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (kSortThreads / 32) * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+
+    // each warp owns a contiguous run of kSortStrips * 32 keys (keeps the order stable)
+    const uint64_t wbase = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (kSortStrips * 32);
+    uint32_t key[kSortStrips];
+    uint32_t rank[kSortStrips];
+#pragma unroll
+    for (int i = 0; i < kSortStrips; ++i)
+    {
+        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
+        const bool in = idx < n;
+        key[i] = in ? keys_in[idx] : 0xFFFFFFFFu;
+        const uint32_t d = in ? ((key[i] >> shift) & 0xFFu) : 0xFFFFFFFFu;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        const uint32_t before = in ? warp_hist[warp][d] : 0;
+        rank[i] = before + __popc(peers & ((1u << lane) - 1));
+        __syncwarp();
+        if (in && (__ffs(peers) - 1) == (int)lane) warp_hist[warp][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // digit = threadIdx.x: turn per-warp counts into global bases
+    {
+        uint32_t run = offsets[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; ++w)
+        {
+            const uint32_t c = warp_hist[w][threadIdx.x];
+            warp_hist[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortStrips; ++i)
+    {
+        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
+        if (idx < n)
+        {
+            const uint32_t d = (key[i] >> shift) & 0xFFu;
+            const uint32_t dst = warp_hist[warp][d] + rank[i];
+            keys_out[dst] = key[i];
+            vals_out[dst] = vals_in ? vals_in[idx] : (uint32_t)idx;
+        }
+    }
+}
+
+} // namespace fsb

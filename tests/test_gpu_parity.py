@@ -1,0 +1,95 @@
+"""GPU parity (driver runs these with -m gpu on a B200): the CUDA path, called through the C ABI,
+must equal the CPU checkers bit for bit -- streams, descriptors, per-read (signature, pos, flags)."""
+import numpy as np
+import pytest
+
+import oracle_helpers as O
+from cases import CASES, make_case
+from fastore_b200 import _native as N
+from fastore_b200 import synth
+from fastore_b200.binner import GpuBinner, FastoreError
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_block_dict(blk):
+    return {"meta": blk.meta, "dna": blk.dna, "qua": blk.qua, "head": blk.head, "bins": blk.bins,
+            "raw_dna_size": blk.raw_dna_size, "raw_head_size": blk.raw_head_size, "n_records": blk.n_records,
+            "read_signature": blk.read_signature, "read_info": blk.read_info}
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_case_matches_oracle(name):
+    params, chunk, keep = make_case(name)
+    want = O.bin_chunk("orc", params, chunk)
+    with GpuBinner(params, per_read=True) as g:
+        got = gpu_block_dict(g.bin_chunks([chunk])[0])
+    O.assert_blocks_equal(got, want, f"{name} (gpu vs port)")
+    if O.have_reference():
+        O.assert_blocks_equal(got, O.bin_chunk("ref", params, chunk), f"{name} (gpu vs compiled reference)")
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_multi_chunk_batch(paired):
+    """Several chunks in one pass of the pipeline: every chunk must still yield exactly its own block."""
+    params = N.make_params(signature_len=8, skip_zone_len=0, paired_end=paired)
+    keep, chunks = [], []
+    for ci, (n, L) in enumerate([(5000, 100), (1, 100), (7000, 151), (3000, 36), (4097, 100)]):
+        cfg = synth.synth_config(n, L, paired=paired, seed=900 + ci, first_index=ci * 100000, nrich=0.05, lowcomplex=0.05, alln=0.01, tie=0.02)
+        t = synth.generate(cfg, threads=2)
+        keep.append(t)
+        chunks.append(N.make_chunk(t[0], t[2], t[1], t[3]))
+    with GpuBinner(params, per_read=True) as g:
+        got = g.bin_chunks(chunks)
+        # the same context again with a different batch shape (buffers are reused)
+        got2 = g.bin_chunks(chunks[::-1])
+    for ci, ch in enumerate(chunks):
+        want = O.bin_chunk("orc", params, ch)
+        O.assert_blocks_equal(gpu_block_dict(got[ci]), want, f"chunk {ci}")
+        O.assert_blocks_equal(gpu_block_dict(got2[len(chunks) - 1 - ci]), want, f"chunk {ci} (reversed batch)")
+
+
+def test_stage_run_fetch_repeatable():
+    params, chunk, keep = make_case("c2_pe150_lossless")
+    want = O.bin_chunk("orc", params, chunk)
+    with GpuBinner(params, per_read=True, profile=True) as g:
+        g.stage([chunk])
+        for _ in range(3):
+            g.run()
+        got = gpu_block_dict(g.fetch()[0])
+        times, runs = g.stage_times()
+        st = g.stats()
+    O.assert_blocks_equal(got, want, "resident re-run")
+    assert runs == 3 and all(v > 0 for v in times.values())
+    assert st["kernel_launches"] > 0 and st["records"] == 3 * chunk.n_records
+
+
+def test_input_contract_errors():
+    params, chunk, keep = make_case("pe_three_records")
+    t1, t2, r1, r2 = keep
+    bad = r2.copy()
+    bad["seq_len"][1] -= 1            # unequal mates: the reference only ASSERTs (FastqRecord.h:87)
+    with GpuBinner(params) as g:
+        with pytest.raises(FastoreError):
+            g.bin_chunks([N.make_chunk(t1, r1, t2, bad)])
+        bad2 = r1.copy()
+        bad2["seq_off"][2] = t1.size    # offset outside the chunk
+        with pytest.raises(FastoreError):
+            g.bin_chunks([N.make_chunk(t1, bad2, t2, r2)])
+        # the context is still usable afterwards
+        blk = g.bin_chunks([chunk])[0]
+        assert blk.n_records == 3
+
+
+def test_parser_table_equals_generator_table_on_gpu_path():
+    """host parser -> C ABI: the table the parser builds drives the device exactly like the generator's."""
+    cfg = synth.synth_config(3000, 100, paired=False, seed=33, header_comments=True)
+    t1, _, r1, _ = synth.generate(cfg)
+    recs, st = synth.parse_chunk(t1, keep_headers=True, keep_comments=False)
+    params = N.make_params(signature_len=8, skip_zone_len=0)
+    chunk = N.make_chunk(t1, recs)
+    want = O.bin_chunk("orc", params, chunk)
+    with GpuBinner(params, per_read=True) as g:
+        got = gpu_block_dict(g.bin_chunks([chunk])[0])
+    O.assert_blocks_equal(got, want, "-C headers")
+    assert int(recs["head_len"].max()) < int(r1["head_len"].min())
