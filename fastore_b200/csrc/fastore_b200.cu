@@ -16,6 +16,7 @@
 
 #include "../../include/fastore_b200.h"
 #include "scan_sort.cuh"
+#include "stage.cuh"
 #include "signature.cuh"
 #include "layout.cuh"
 #include "pack.cuh"
@@ -92,7 +93,9 @@ struct fsb_ctx
     size_t out_cap[4] = {0, 0, 0, 0};
     int sort_passes = 0;
 
-    DevBuf d_text[2], d_rec[2], d_chunk_meta;
+    DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats;
+    PinBuf h_stage_stats;
+    uint32_t min_len = 0, max_len = 0, max_head = 0;
     DevBuf d_keys[2], d_vals[2], d_info, d_sig, d_counts, d_counts_scan, d_scan_tmp;
     DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head;
     DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4], d_desc, d_summary, d_out[4];
@@ -126,6 +129,31 @@ int fail(fsb_ctx* c, int code, const std::string& msg)
     } while (0)
 
 uint32_t bits_for(uint32_t v) { uint32_t b = 0; while ((1ull << b) <= v) ++b; return b; }   // bits to represent v
+
+BatchView batch_view(const fsb_ctx* c)
+{
+    BatchView B{};
+    const uint64_t* meta = c->d_chunk_meta.as<uint64_t>();
+    B.text[0] = c->d_text[0].as<uint8_t>(); B.text[1] = c->d_text[1].as<uint8_t>();
+    B.rec[0] = c->d_rec[0].as<fsb_record>(); B.rec[1] = c->d_rec[1].as<fsb_record>();
+    B.chunk_first_rec = meta;
+    B.chunk_text_base[0] = meta + (c->n_chunks + 1);
+    B.chunk_text_base[1] = meta + (c->n_chunks + 1) + c->n_chunks;
+    B.n_chunks = c->n_chunks; B.n_records = c->n_records;
+    return B;
+}
+
+template <int NW>
+cudaError_t launch_signature(const BatchView& B, const DeviceParams& P, uint32_t* keys, uint32_t* info, uint32_t* sig, cudaStream_t st)
+{
+    const size_t smem = sig_smem_bytes<NW>();
+    cudaError_t e = cudaFuncSetAttribute(signature_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
+    const unsigned blocks = (unsigned)((n_mates + kSigWarps * 32 - 1) / (kSigWarps * 32));
+    signature_kernel<NW><<<blocks, kSigWarps * 32, smem, st>>>(B, P, keys, info, sig);
+    return cudaGetLastError();
+}
 
 int resolve_profiles(fsb_ctx* c)
 {
@@ -187,16 +215,7 @@ extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fs
     if (!c) return fail(nullptr, FSB_ERR_NOMEM, "out of host memory");
     c->params = *p;
     c->device = device;
-    DeviceParams& d = c->dp;
-    d.k = p->signature_len; d.s = p->skip_zone_len;
-    d.cutoff_mask = (1u << p->signature_mask_cutoff_bits) - 1;
-    d.nbin = 1u << (2 * d.k); d.kmer_mask = d.nbin - 1;
-    d.paired = p->paired_end ? 1 : 0;
-    d.qua_method = p->quality_method; d.qua_offset = p->quality_offset; d.qua_threshold = p->binary_threshold;
-    static const uint32_t bpb[4] = {6, 1, 3, 6};                 // QualityCompressionParams::BitsPerBase (Quality.h:58-64)
-    d.qua_bits = bpb[p->quality_method];
-    d.has_headers = p->reads_have_headers ? 1 : 0;
-    d.key_bits = 2 * d.k + 1;
+    c->dp = make_device_params(*p);
 
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail(nullptr, FSB_ERR_CUDA, "cudaSetDevice failed"); }
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
@@ -215,14 +234,14 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& e : c->events) cudaEventDestroy(e);
-    DevBuf* dev[] = {&c->d_text[0], &c->d_text[1], &c->d_rec[0], &c->d_rec[1], &c->d_chunk_meta, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0],
+    DevBuf* dev[] = {&c->d_text[0], &c->d_text[1], &c->d_rec[0], &c->d_rec[1], &c->d_chunk_meta, &c->d_stage_stats, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0],
                      &c->d_vals[1], &c->d_info, &c->d_sig, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags, &c->d_flags_excl,
                      &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
                      &c->d_bits[2], &c->d_bits[3], &c->d_P[0], &c->d_P[1], &c->d_P[2], &c->d_P[3], &c->d_bytes[0], &c->d_bytes[1],
                      &c->d_bytes[2], &c->d_bytes[3], &c->d_BO[0], &c->d_BO[1], &c->d_BO[2], &c->d_BO[3], &c->d_desc, &c->d_summary,
                      &c->d_out[0], &c->d_out[1], &c->d_out[2], &c->d_out[3]};
     for (DevBuf* b : dev) b->release();
-    PinBuf* pin[] = {&c->h_summary, &c->h_out[0], &c->h_out[1], &c->h_out[2], &c->h_out[3], &c->h_desc, &c->h_sig, &c->h_info};
+    PinBuf* pin[] = {&c->h_stage_stats, &c->h_summary, &c->h_out[0], &c->h_out[1], &c->h_out[2], &c->h_out[3], &c->h_desc, &c->h_sig, &c->h_info};
     for (PinBuf* b : pin) b->release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -277,9 +296,9 @@ extern "C" int fsb_stage_times(fsb_ctx* c, float* ms, uint32_t n_stages, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// fsb_stage: validate the record tables' framing on the host (offsets inside the chunk, lengths,
-// PE mate-length equality - the things the reference only ASSERTs: FastqRecord.h:87,
-// FastqParser.cpp:130) and enqueue the host->device copies.
+// fsb_stage: enqueue the host->device copies, then check the record tables on the device (offsets
+// inside the chunk, lengths, PE mate-length equality - the things the reference only ASSERTs:
+// FastqRecord.h:87, FastqParser.cpp:130) and collect the batch statistics that size the buffers.
 extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
 {
     if (!c || (!chunks && n_chunks)) return FSB_ERR_PARAM;
@@ -294,7 +313,7 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
     c->chunk_first_rec.assign(n_chunks + 1, 0);
     size_t text_bytes[2] = {kTextPad, kTextPad};
     for (int m = 0; m < 2; ++m) c->chunk_text_base[m].assign(n_chunks, 0);
-    uint64_t n = 0, bases = 0, heads = 0;
+    uint64_t n = 0;
     for (uint32_t ci = 0; ci < n_chunks; ++ci)
     {
         const fsb_chunk& ch = chunks[ci];
@@ -306,40 +325,11 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
             c->chunk_text_base[m][ci] = text_bytes[m];
             text_bytes[m] = align_up(text_bytes[m] + ch.text_size[m] + kTextPad, 256);
         }
-        if (c->validate)
-        {
-            const fsb_record* r0 = ch.records[0];
-            const fsb_record* r1 = nfiles == 2 ? ch.records[1] : nullptr;
-            for (uint64_t i = 0; i < ch.n_records; ++i)
-            {
-                const fsb_record& a = r0[i];
-                bool ok = a.seq_len >= 1 && a.seq_len <= 255 && (uint64_t)a.seq_off + a.seq_len <= ch.text_size[0] &&
-                          (uint64_t)a.qua_off + a.seq_len <= ch.text_size[0] && (uint64_t)a.head_off + a.head_len <= ch.text_size[0];
-                bases += a.seq_len;
-                heads += a.head_len;
-                if (r1)
-                {
-                    const fsb_record& b = r1[i];
-                    ok = ok && b.seq_len == a.seq_len && (uint64_t)b.seq_off + b.seq_len <= ch.text_size[1] &&
-                         (uint64_t)b.qua_off + b.seq_len <= ch.text_size[1];
-                    bases += b.seq_len;
-                }
-                if (!ok) return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(i) + " of chunk " + std::to_string(ci) +
-                                                           " violates the input contract (length 1..255, offsets inside the chunk, equal PE mate lengths)");
-            }
-        }
-        else
-        {
-            // bounds only: a record has at least 2L + 6 bytes of text; headers are at most the text
-            for (int m = 0; m < nfiles; ++m) bases += ch.text_size[m] / 2;
-            heads += ch.text_size[0];
-        }
         n += ch.n_records;
     }
     c->chunk_first_rec[n_chunks] = n;
     if (n >= 0xFFFFFFFFull) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^32-2 records in one batch");
     c->n_records = n;
-    c->total_bases = bases; c->total_head = heads;
     c->nb_max = std::min<uint64_t>(n, (uint64_t)n_chunks * ((uint64_t)c->dp.nbin + 1));
     c->sort_passes = (int)((c->dp.key_bits + bits_for(n_chunks - 1) + 7) / 8);
 
@@ -360,18 +350,52 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
             h2d += ch.text_size[m] + ch.n_records * sizeof(fsb_record);
         }
     }
-    // chunk tables: [first_rec (n_chunks+1)] [text_base0 (n_chunks)] [text_base1 (n_chunks)]
+    // chunk tables: [first_rec (n_chunks+1)] [text_base0] [text_base1] [text_size0] [text_size1]  (n_chunks each)
+    StageStats stats{};
     {
         std::vector<uint64_t> meta;
         meta.insert(meta.end(), c->chunk_first_rec.begin(), c->chunk_first_rec.end());
         meta.insert(meta.end(), c->chunk_text_base[0].begin(), c->chunk_text_base[0].end());
         meta.insert(meta.end(), c->chunk_text_base[1].begin(), c->chunk_text_base[1].end());
+        for (int m = 0; m < 2; ++m)
+            for (uint32_t ci = 0; ci < n_chunks; ++ci) meta.push_back(chunks[ci].text_size[m]);
         CUDA_TRY(c, c->d_chunk_meta.ensure(meta.size() * sizeof(uint64_t)));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // `meta` (and pageable user buffers) must outlive the copies
         h2d += meta.size() * sizeof(uint64_t);
+
+        CUDA_TRY(c, c->d_stage_stats.ensure(sizeof(StageStats)));
+        CUDA_TRY(c, c->h_stage_stats.ensure(sizeof(StageStats)));
+        StageStats init{};
+        init.first_bad = ~0ull; init.min_len = 0xFFFFFFFFu;
+        *c->h_stage_stats.as<StageStats>() = init;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_stage_stats.p, c->h_stage_stats.p, sizeof(StageStats), cudaMemcpyHostToDevice, c->stream));
+        if (n)
+        {
+            const BatchView B = batch_view(c);
+            const uint64_t* m64 = c->d_chunk_meta.as<uint64_t>();
+            const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
+            stage_stats_kernel<<<blocks, 256, 0, c->stream>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1),
+                                                              c->d_stage_stats.as<StageStats>());
+            c->stats.kernel_launches++;
+        }
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // the H2D of the init block must finish before the D2H reuses the pinned block
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_stage_stats.p, c->d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // `meta` (and pageable user buffers) must outlive the copies
+        stats = *c->h_stage_stats.as<StageStats>();
     }
     c->stats.h2d_bytes += h2d;
+    if (stats.n_bad)
+    {
+        // never run the kernels on tables that point outside the staged text
+        uint32_t ci = 0;
+        while (ci + 1 < n_chunks && c->chunk_first_rec[ci + 1] <= stats.first_bad) ++ci;
+        return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(stats.first_bad - c->chunk_first_rec[ci]) + " of chunk " + std::to_string(ci) +
+                                          " violates the input contract (length 1..255, offsets inside the chunk, equal PE mate lengths); " +
+                                          std::to_string(stats.n_bad) + " such record(s)");
+    }
+    const uint64_t bases = stats.bases, heads = stats.heads;
+    c->total_bases = bases; c->total_head = heads;
+    c->min_len = n ? stats.min_len : 0; c->max_len = stats.max_len; c->max_head = stats.max_head;
 
     // ---- intermediate + output buffers (grow-only) -----------------------------------------------
     const uint64_t nsort_blocks = (n + kSortTile - 1) / kSortTile;
@@ -439,14 +463,7 @@ extern "C" int fsb_run(fsb_ctx* c)
         CUDA_TRY(c, cudaEventRecord(ev[0], st));
     }
 
-    BatchView B{};
-    const uint64_t* meta = c->d_chunk_meta.as<uint64_t>();
-    B.text[0] = c->d_text[0].as<uint8_t>(); B.text[1] = c->d_text[1].as<uint8_t>();
-    B.rec[0] = c->d_rec[0].as<fsb_record>(); B.rec[1] = c->d_rec[1].as<fsb_record>();
-    B.chunk_first_rec = meta;
-    B.chunk_text_base[0] = meta + (c->n_chunks + 1);
-    B.chunk_text_base[1] = meta + (c->n_chunks + 1) + c->n_chunks;
-    B.n_chunks = c->n_chunks; B.n_records = n;
+    const BatchView B = batch_view(c);
 
     const unsigned tpb = 256;
     const unsigned grid_n = (unsigned)std::max<uint64_t>(1, (n + tpb - 1) / tpb);
@@ -454,10 +471,22 @@ extern "C" int fsb_run(fsb_ctx* c)
     // ---- K1: signatures ---------------------------------------------------------------------------
     if (n)
     {
-        const uint64_t warps_needed = n;
-        const unsigned blocks = (unsigned)std::min<uint64_t>((warps_needed + 7) / 8, 148ull * 32);
-        signature_kernel<<<blocks, 256, 0, st>>>(B, P, c->d_keys[0].as<uint32_t>(), c->d_info.as<uint32_t>(),
-                                                   c->per_read ? c->d_sig.as<uint32_t>() : nullptr);
+        uint32_t* keys = c->d_keys[0].as<uint32_t>();
+        uint32_t* info = c->d_info.as<uint32_t>();
+        uint32_t* sig = c->per_read ? c->d_sig.as<uint32_t>() : nullptr;
+        cudaError_t e = cudaSuccess;
+        switch ((c->max_len + 31) / 32)              // words of 32 bases per mate
+        {
+        case 0: case 1: e = launch_signature<1>(B, P, keys, info, sig, st); break;
+        case 2: e = launch_signature<2>(B, P, keys, info, sig, st); break;
+        case 3: e = launch_signature<3>(B, P, keys, info, sig, st); break;
+        case 4: e = launch_signature<4>(B, P, keys, info, sig, st); break;
+        case 5: e = launch_signature<5>(B, P, keys, info, sig, st); break;
+        case 6: e = launch_signature<6>(B, P, keys, info, sig, st); break;
+        case 7: e = launch_signature<7>(B, P, keys, info, sig, st); break;
+        default: e = launch_signature<8>(B, P, keys, info, sig, st); break;
+        }
+        CUDA_TRY(c, e);
         launches++;
     }
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[1], st));

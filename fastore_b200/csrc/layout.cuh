@@ -34,7 +34,7 @@ struct BinArrays
     unsigned long long* bin_raw_head;  // [nb_max]
 };
 
-__device__ __forceinline__ uint32_t bit_length_u32(uint32_t x) { return 32u - __clz(x); }     // Utils.h:235-243 for x < 2^31
+
 
 // flags[i] = 1 where a new (chunk, signature) bin starts
 __global__ void bin_flags_kernel(const uint32_t* __restrict__ skeys, uint64_t n, uint32_t* __restrict__ flags)

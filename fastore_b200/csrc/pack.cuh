@@ -19,7 +19,7 @@ struct OutStreams
     uint32_t* w[4];          // meta, dna, qua, head as 32-bit words (zero-initialised)
 };
 
-__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
 
 // OR `nbits` (<= 32) bits of `value` into the stream at absolute bit offset `off`
 __device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t off, uint32_t value, uint32_t nbits)

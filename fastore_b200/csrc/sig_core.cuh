@@ -1,0 +1,213 @@
+// sig_core.cuh -- per-thread minimizer search of one mate, bit-parallel over the whole read.
+//
+// Replaces FastqCategorizerBase::FindMinimizer on both strands of one mate
+// (FastqCategorizer.cpp:79-106), ComputeMinimizer (:138-152), the validBinSignatures table
+// (:34-76) and FastqRecord::ComputeRC (FastqRecord.h:80-111).
+//
+// One thread owns one mate.  The read is held as three bit planes of 32*NW positions (hi and lo
+// bit of the 2-bit base code A,C,G,T = 0..3, and an 'N' plane), so every test the reference makes
+// per k-mer becomes a handful of word operations for all positions at once:
+//
+//   * validBinSignatures[m]: m is invalid iff its top three symbols are AAA / AAC, or an "AA" sits
+//     at symbols (t, t+1) for some t in [1, k-2], or one of its low cutoff bits is set.  With
+//     AA[p] = isA[p] & isA[p+1]: the k-mer at p is invalid iff AA hits [p+1, p+k-2] (sliding OR)
+//     or AA[p] and base[p+2] is A or C.  The reverse-strand k-mer at the same forward position is
+//     the reverse complement, so the same rules read TT instead of AA from the other end.
+//   * k-mers containing 'N' (ComputeMinimizer returns 4^k): sliding OR of the N plane over k.
+//   * scan windows: forward i in [0, L-k-s)  (:88); reverse strand position q = L-k-p in the same
+//     range, i.e. forward p in (s, L-k].
+//   * the minimum itself is a radix descent over the candidate set: for each of the 2k key bits,
+//     most significant first, keep the candidates whose bit is 0 if there are any.  What survives
+//     all share the smallest k-mer; "first minimum wins" (strict <, :93) picks the lowest forward
+//     position on the forward strand and the highest on the reverse strand (lowest q).
+//   * N filter (:102): popcount of the N plane >= L/3 -> (4^k, 0).
+#pragma once
+
+#include "core.cuh"
+
+namespace fsb {
+
+struct StrandMin { uint32_t sig; uint32_t pos; };
+
+// multipliers that gather one bit per byte of two masked words into the top byte of the product:
+// bits 8b+beta of w0 and 8b+beta+4 of (w1 << 4) land at 24+b and 28+b; every cross term falls
+// below bit 24 or above bit 31 on a position of its own, so nothing carries into the result.
+constexpr uint32_t kGatherBit1 = (1u << 23) | (1u << 16) | (1u << 9) | (1u << 2);
+constexpr uint32_t kGatherBit2 = (1u << 22) | (1u << 15) | (1u << 8) | (1u << 1);
+constexpr uint32_t kGatherBit3 = (1u << 21) | (1u << 14) | (1u << 7) | (1u << 0);
+
+// ASCII bases -> bit planes.  `w` points at the 4-byte-aligned word holding base 0 (8*NW + 1
+// words readable), `bshift` = 8 * (address of base 0 & 3).  Planes beyond the read length hold
+// whatever follows the read in the text; callers mask with the length.
+//   hi plane = ASCII bit 2 (A 0x41, C 0x43 -> 0;  G 0x47, T 0x54 -> 1)
+//   lo plane = ASCII bit 1 ^ bit 2 (A 0, C 1, G 1^1 = 0, T 0^1 = 1)
+//   N  plane = ASCII bit 3 ('N' = 0x4E is the only symbol of the alphabet with it)
+template <int NW>
+FSB_HD void ascii_to_planes(const uint32_t* w, uint32_t bshift, BV<NW>& H, BV<NW>& Lo, BV<NW>& Nm)
+{
+    uint32_t prev = w[0];
+#pragma unroll
+    for (int j = 0; j < NW; ++j)
+    {
+        uint32_t h = 0, b1 = 0, n = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            const uint32_t a = w[8 * j + 2 * q + 1], b = w[8 * j + 2 * q + 2];
+            const uint32_t w0 = funnel_r(prev, a, bshift);      // bases 32j + 8q .. +3
+            const uint32_t w1 = funnel_r(a, b, bshift);         // bases 32j + 8q + 4 .. +7
+            prev = b;
+            const uint32_t s = w1 << 4;
+            const uint32_t xh = (w0 & 0x04040404u) | (s & 0x40404040u);
+            const uint32_t x1 = (w0 & 0x02020202u) | (s & 0x20202020u);
+            const uint32_t xn = (w0 & 0x08080808u) | (s & 0x80808080u);
+            h |= ((xh * kGatherBit2) >> 24) << (8 * q);
+            b1 |= ((x1 * kGatherBit1) >> 24) << (8 * q);
+            n |= ((xn * kGatherBit3) >> 24) << (8 * q);
+        }
+        H.w[j] = h; Lo.w[j] = b1 ^ h; Nm.w[j] = n;
+    }
+}
+
+// Candidate positions of both strands (forward coordinates): in the scan window, no 'N' in the
+// k-mer, signature valid.
+template <int NW>
+FSB_HD void candidate_masks(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, const DeviceParams& P,
+                            BV<NW>& Cf, BV<NW>& Cr)
+{
+    const uint32_t k = P.k;
+    BV<NW> isA, isT;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { isA.w[j] = ~(H.w[j] | Lo.w[j]); isT.w[j] = H.w[j] & Lo.w[j]; }
+    const BV<NW> AA = bv_and(isA, bv_shr(isA, 1));
+    const BV<NW> TT = bv_and(isT, bv_shr(isT, 1));
+    const BV<NW> Nw = bv_slide_or(Nm, k);
+
+    // forward strand: AA at any of p+1 .. p+k-2, or AA at p followed by A/C
+    BV<NW> badF = bv_or(bv_shr(bv_slide_or(AA, k - 2), 1), bv_andn(AA, bv_shr(H, 2)));
+    // reverse strand: rc symbols (t, t+1) are bases (p+k-1-t, p+k-2-t): TT at any of p .. p+k-3, or
+    // TT at p+k-2 (rc symbols 0,1 = AA) preceded by T/G at p+k-3 (rc symbol 2 = A/C)
+    BV<NW> badR = bv_or(bv_slide_or(TT, k - 2), bv_and(bv_shr(TT, k - 2), bv_shr(H, k - 3)));
+    // signatureMaskCutoffBits (FastqCategorizer.cpp:49-53): the low c bits of the k-mer must be 0.
+    // Bit b of the k-mer is the lo (even b) / hi (odd b) bit of the symbol b/2 places from its end.
+    for (uint32_t b = 0; b < P.cutoff_bits; ++b)
+    {
+        const BV<NW>& plane = (b & 1u) ? H : Lo;
+        badF = bv_or(badF, bv_shr(plane, k - 1 - (b >> 1)));
+        const BV<NW> sh = bv_shr(plane, b >> 1);                // rc symbol = 3 - base: the bit is complemented
+#pragma unroll
+        for (int j = 0; j < NW; ++j) badR.w[j] |= ~sh.w[j];
+    }
+    const int32_t lim = (int32_t)L - (int32_t)k - (int32_t)P.s;  // FindMinimizer scans i < L - k - s
+    Cf = bv_andn(bv_andn(bv_range<NW>(0, lim), badF), Nw);
+    Cr = bv_andn(bv_andn(bv_range<NW>((int32_t)P.s + 1, (int32_t)L - (int32_t)k + 1), badR), Nw);
+}
+
+// Radix descent, forward strand.  D tracks the candidates shifted onto the symbol under test.
+template <int NW>
+FSB_HD StrandMin descend_forward(BV<NW> D, const BV<NW>& H, const BV<NW>& Lo, const DeviceParams& P)
+{
+    uint32_t m = 0;
+    for (uint32_t d = 0; d < P.k; ++d)
+    {
+        if (d) D = bv_shl(D, 1);
+        BV<NW> T = bv_andn(D, H);
+        bool any = bv_any(T);
+        D = bv_select(any, T, D);
+        m = 2 * m + (any ? 0u : 1u);
+        T = bv_andn(D, Lo);
+        any = bv_any(T);
+        D = bv_select(any, T, D);
+        m = 2 * m + (any ? 0u : 1u);
+    }
+    StrandMin r;
+    r.sig = m;
+    r.pos = bv_lowest(D) - (P.k - 1);
+    return r;
+}
+
+// Radix descent, reverse strand: symbol d of the rc k-mer at forward position p is the complement
+// of base p+k-1-d.  The first minimum in reverse-strand order is the highest forward position.
+template <int NW>
+FSB_HD StrandMin descend_reverse(const BV<NW>& C, const BV<NW>& H, const BV<NW>& Lo, uint32_t L, const DeviceParams& P)
+{
+    BV<NW> D = bv_shl(C, P.k - 1);
+    uint32_t m = 0;
+    for (uint32_t d = 0; d < P.k; ++d)
+    {
+        if (d) D = bv_shr(D, 1);
+        BV<NW> T = bv_and(D, H);
+        bool any = bv_any(T);
+        D = bv_select(any, T, D);
+        m = 2 * m + (any ? 0u : 1u);
+        T = bv_and(D, Lo);
+        any = bv_any(T);
+        D = bv_select(any, T, D);
+        m = 2 * m + (any ? 0u : 1u);
+    }
+    StrandMin r;
+    r.sig = m;
+    r.pos = L - P.k - bv_highest(D);
+    return r;
+}
+
+// FM(x) and FM(rc(x)) of one mate, plus its N count.  L <= 32 * NW.
+template <int NW>
+FSB_HD void mate_minimizers(const uint32_t* words, uint32_t bshift, uint32_t L, const DeviceParams& P,
+                            StrandMin& fwd, StrandMin& rev, uint32_t& nN)
+{
+    BV<NW> H, Lo, Nm;
+    ascii_to_planes<NW>(words, bshift, H, Lo, Nm);
+    Nm = bv_and(Nm, bv_range<NW>(0, (int32_t)L));
+    nN = bv_popc(Nm);
+    BV<NW> Cf, Cr;
+    candidate_masks<NW>(H, Lo, Nm, L, P, Cf, Cr);
+    const bool tooManyN = nN >= L / 3;                           // FastqCategorizer.cpp:102
+    fwd.sig = P.nbin; fwd.pos = 0;
+    rev.sig = P.nbin; rev.pos = 0;
+    if (!tooManyN)
+    {
+        if (bv_any(Cf)) fwd = descend_forward<NW>(Cf, H, Lo, P);
+        if (bv_any(Cr)) rev = descend_reverse<NW>(Cr, H, Lo, L, P);
+    }
+}
+
+// FastqCategorizerSE::DistributeToBins (FastqCategorizer.cpp:212-245): forward wins ties.
+FSB_HD void select_se(const StrandMin& f, const StrandMin& r, uint32_t nN, const DeviceParams& P, uint32_t& sig, uint32_t& info)
+{
+    const bool reverse = !(f.sig <= r.sig);
+    sig = reverse ? r.sig : f.sig;
+    uint32_t pos = reverse ? r.pos : f.pos, flags = 0;
+    if (sig != P.nbin) flags |= reverse ? FSB_INFO_REVERSE : 0u; else pos = 0;
+    if (nN == 0) flags |= FSB_INFO_PLAIN_A;
+    info = pos | flags;
+}
+
+// FastqCategorizerPE::DistributeToBins (:289-336): strict < everywhere, so ties go to mate 2 over
+// mate 1 and to the reverse strand over the forward one.  f1 = FM(m1), f2 = FM(m2),
+// r1 = FM(rc(m2)) ("minRev_1": first half of the reversed pair), r2 = FM(rc(m1)).
+FSB_HD void select_pe(const StrandMin& f1, const StrandMin& f2, const StrandMin& r1, const StrandMin& r2, uint32_t nN1, uint32_t nN2,
+                      const DeviceParams& P, uint32_t& sig, uint32_t& info)
+{
+    const bool isF1 = f1.sig < f2.sig;
+    const StrandMin F = isF1 ? f1 : f2;
+    const bool isR1 = r1.sig < r2.sig;
+    const StrandMin R = isR1 ? r1 : r2;
+    bool isRev, first;
+    uint32_t pos, flags = 0;
+    if (F.sig < R.sig) { sig = F.sig; pos = F.pos; isRev = false; first = isF1; }
+    else { sig = R.sig; pos = R.pos; isRev = true; first = isR1; }
+    bool a_is_m2 = false;
+    if (sig != P.nbin)
+    {
+        if (isRev) flags |= FSB_INFO_REVERSE;
+        if (!first) flags |= FSB_INFO_SWAPPED;
+        a_is_m2 = isRev != !first;          // reversed pair is [rc(m2) | rc(m1)]; a swap exchanges the halves
+    }
+    else pos = 0;
+    if ((a_is_m2 ? nN2 : nN1) == 0) flags |= FSB_INFO_PLAIN_A;
+    if ((a_is_m2 ? nN1 : nN2) == 0) flags |= FSB_INFO_PLAIN_B;
+    info = pos | flags;
+}
+
+} // namespace fsb

@@ -1,0 +1,44 @@
+"""The per-thread routines of the CUDA kernels (csrc/*_core.cuh) are plain integer code that also
+compiles for the host.  tests/emul/emul.cpp runs them "thread" by "thread" over a chunk; here their
+output must equal the oracle's.  This checks kernel logic in the CPU tier; the product never runs
+this code on the host (the GPU parity tests call the real kernels through the C ABI)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_helpers as O
+from cases import CASES, make_case
+from fastore_b200 import _native as N
+
+ROOT = Path(__file__).resolve().parent.parent
+EMUL_SRC = ROOT / "tests" / "emul" / "emul.cpp"
+EMUL_LIB = ROOT / "tests" / "emul" / "_build" / "libemul.so"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    deps = [EMUL_SRC] + list((ROOT / "fastore_b200" / "csrc").glob("*.cuh")) + [ROOT / "include" / "fastore_b200.h"]
+    if not EMUL_LIB.exists() or any(d.stat().st_mtime > EMUL_LIB.stat().st_mtime for d in deps):
+        EMUL_LIB.parent.mkdir(exist_ok=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-x", "c++", str(EMUL_SRC), "-o", str(EMUL_LIB)], check=True)
+    lib = C.CDLL(str(EMUL_LIB))
+    lib.emul_signatures.restype = C.c_int
+    lib.emul_signatures.argtypes = [C.POINTER(N.FsbParams), C.POINTER(N.FsbChunk), C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_signature_core_matches_oracle(emul, name):
+    params, chunk, keep = make_case(name)
+    want = O.bin_chunk("orc", params, chunk)
+    n = int(chunk.n_records)
+    sig = np.zeros(n, dtype=np.uint32)
+    info = np.zeros(n, dtype=np.uint32)
+    assert emul.emul_signatures(C.byref(params), C.byref(chunk), N.np_ptr(sig), N.np_ptr(info)) == N.FSB_OK
+    bad = np.nonzero(sig != want["read_signature"])[0]
+    assert bad.size == 0, f"{name}: signature of read {bad[0]}: {sig[bad[0]]:#x} vs {want['read_signature'][bad[0]]:#x} ({bad.size} differ)"
+    bad = np.nonzero(info != want["read_info"])[0]
+    assert bad.size == 0, f"{name}: info of read {bad[0]}: {info[bad[0]]:#x} vs {want['read_info'][bad[0]]:#x} ({bad.size} differ)"
