@@ -155,6 +155,20 @@ cudaError_t launch_signature(const BatchView& B, const DeviceParams& P, uint32_t
     return cudaGetLastError();
 }
 
+template <int NW>
+cudaError_t launch_pack(const PackArgs& pa, uint32_t max_len, uint32_t max_head, cudaStream_t st)
+{
+    // largest tile whose shared memory still lets three blocks share an SM; smaller tiles for long reads
+    uint32_t T = pa.P.paired ? 64u : 128u;
+    PackTilePlan pl = make_pack_plan<NW>(pa.P, T, max_len, max_head);
+    while (pl.total_bytes > 74u * 1024u && T > 16u) { T >>= 1; pl = make_pack_plan<NW>(pa.P, T, max_len, max_head); }
+    cudaError_t e = cudaFuncSetAttribute(pack_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((pa.B.n_records + T - 1) / T);
+    pack_kernel<NW><<<blocks, pl.threads, pl.total_bytes, st>>>(pa, pl);
+    return cudaGetLastError();
+}
+
 int resolve_profiles(fsb_ctx* c)
 {
     if (c->pending_profiles == 0) return FSB_OK;
@@ -560,9 +574,20 @@ extern "C" int fsb_run(fsb_ctx* c)
     for (int s = 0; s < 4; ++s) CUDA_TRY(c, cudaMemsetAsync(c->d_out[s].p, 0, c->out_cap[s], st));
     if (n)
     {
-        PackArgs pa{B, P, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}}};
-        const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, 148ull * 32);
-        pack_kernel<<<blocks, 256, 0, st>>>(pa);
+        PackArgs pa{B, P, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}}, nb_ptr};
+        cudaError_t e = cudaSuccess;
+        switch ((c->max_len + 31) / 32)
+        {
+        case 0: case 1: e = launch_pack<1>(pa, c->max_len, c->max_head, st); break;
+        case 2: e = launch_pack<2>(pa, c->max_len, c->max_head, st); break;
+        case 3: e = launch_pack<3>(pa, c->max_len, c->max_head, st); break;
+        case 4: e = launch_pack<4>(pa, c->max_len, c->max_head, st); break;
+        case 5: e = launch_pack<5>(pa, c->max_len, c->max_head, st); break;
+        case 6: e = launch_pack<6>(pa, c->max_len, c->max_head, st); break;
+        case 7: e = launch_pack<7>(pa, c->max_len, c->max_head, st); break;
+        default: e = launch_pack<8>(pa, c->max_len, c->max_head, st); break;
+        }
+        CUDA_TRY(c, e);
         launches++;
     }
     if (ev)

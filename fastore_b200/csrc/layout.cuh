@@ -14,6 +14,7 @@
 #pragma once
 
 #include "signature.cuh"
+#include "pack_core.cuh"
 
 namespace fsb {
 
@@ -62,22 +63,6 @@ __global__ void bin_stats_kernel(BatchView B, DeviceParams P, SortedView S, cons
     if (P.paired) raw += B.rec[1][r].seq_len;
     atomicAdd(&A.bin_raw_dna[bin], (unsigned long long)raw);
     if (P.has_headers) atomicAdd(&A.bin_raw_head[bin], (unsigned long long)ra.head_len);
-}
-
-struct ReadBits { uint32_t meta, dna, qua, head; };
-
-__device__ __forceinline__ ReadBits read_bit_lengths(const DeviceParams& P, bool nbin, uint32_t info, uint32_t L1, uint32_t L2, uint32_t H,
-                                                     uint32_t bmin, uint32_t bmax)
-{
-    ReadBits b;
-    const bool pe = P.paired != 0;
-    const uint32_t bpl = (bmin != bmax) ? bit_length_u32(bmax - bmin) : 0;
-    b.meta = (pe ? 2 * bpl : bpl) + (nbin ? 0u : (pe ? 10u : 9u)) + 1u + (pe ? 1u : 0u);
-    const uint32_t bitsA = (info & FSB_INFO_PLAIN_A) ? 2u : 3u, bitsB = (info & FSB_INFO_PLAIN_B) ? 2u : 3u;
-    b.dna = (L1 - (nbin ? 0u : P.k)) * bitsA + (pe ? L2 * bitsB : 0u);
-    b.qua = (L1 + (pe ? L2 : 0u)) * P.qua_bits;
-    b.head = P.has_headers ? 8u + 7u * (H ? H - 1u : 0u) : 0u;
-    return b;
 }
 
 __global__ void read_bits_kernel(BatchView B, DeviceParams P, SortedView S, BinArrays A,

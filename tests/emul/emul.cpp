@@ -80,3 +80,164 @@ extern "C" int emul_signatures(const fsb_params* p, const fsb_chunk* ch, uint32_
     }
     return FSB_OK;
 }
+
+// ================================================================================================
+// pack: host-side layout (plain loops restating layout.cuh) + the per-thread packers of
+// pack_core.cuh, one stored mate after the other, into flat word buffers.
+#include <algorithm>
+#include <numeric>
+
+#include "../../fastore_b200/csrc/pack_core.cuh"
+
+namespace {
+
+struct Slot
+{
+    std::vector<uint32_t> w;     // 16-byte guard + aligned window + slack
+    uint32_t addr;               // byte offset of the first source byte
+    void fill(const uint8_t* text, uint64_t text_size, uint32_t off, uint32_t len)
+    {
+        const int64_t a0 = (int64_t)(off & ~15u);
+        const uint32_t npieces = ((off & 15u) + len + 15u) >> 4;
+        w.assign((npieces + 4) * 4, 0xCDCDCDCDu);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(w.data()) + 16;
+        for (uint32_t j = 0; j < npieces * 16; ++j)
+        {
+            const int64_t src = a0 + j;
+            dst[j] = (src >= 0 && (uint64_t)src < text_size) ? text[src] : 0x5A;
+        }
+        addr = 16 + (off & 15u);
+    }
+};
+
+template <int NW>
+void pack_mate(const DeviceParams& P, const Slot& seq, const Slot& qua, uint32_t len, bool rev, bool plain, uint32_t cut_pos, uint32_t cut_len,
+               uint32_t* dna_words, uint32_t dna_off, uint32_t* qua_words, uint32_t qua_off)
+{
+    if (plain) pack_dna<NW, 2>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, dna_words, dna_off);
+    else pack_dna<NW, 3>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, dna_words, dna_off);
+    const SymReader rq = reader_open(qua.w.data(), qua.addr, len, rev);
+    switch (P.qua_bits)
+    {
+    case 6: pack_quality<6>(rq, len, P, qua_words, qua_off); break;
+    case 3: pack_quality<3>(rq, len, P, qua_words, qua_off); break;
+    default: pack_quality<1>(rq, len, P, qua_words, qua_off); break;
+    }
+}
+
+template <int NW>
+int run_pack(const DeviceParams& P, const fsb_chunk* ch, const uint32_t* sig, const uint32_t* info, uint8_t* out[4], uint64_t out_size[4])
+{
+    const uint64_t n = ch->n_records;
+    const bool pe = P.paired != 0;
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sig[a] < sig[b]; });
+    // bins
+    std::vector<uint64_t> bin_start;
+    for (uint64_t i = 0; i < n; ++i) if (i == 0 || sig[order[i]] != sig[order[i - 1]]) bin_start.push_back(i);
+    bin_start.push_back(n);
+    const uint64_t nb = bin_start.size() - 1;
+    // per-record bit offsets
+    std::vector<uint64_t> off[4];
+    for (auto& v : off) v.resize(n);
+    std::vector<uint32_t> bmin(nb), bmax(nb);
+    uint64_t pos[4] = {0, 0, 0, 0};          // running byte-aligned stream positions, in bits
+    for (uint64_t b = 0; b < nb; ++b)
+    {
+        uint32_t mn = 0xFFFFFFFFu, mx = 0;
+        for (uint64_t i = bin_start[b]; i < bin_start[b + 1]; ++i)
+        {
+            const uint32_t L = ch->records[0][order[i]].seq_len;
+            mn = std::min(mn, L); mx = std::max(mx, L);
+        }
+        bmin[b] = mn; bmax[b] = mx;
+        pos[0] += 17;
+        for (uint64_t i = bin_start[b]; i < bin_start[b + 1]; ++i)
+        {
+            const uint32_t r = order[i];
+            const fsb_record& ra = ch->records[0][r];
+            const uint32_t L2 = pe ? ch->records[1][r].seq_len : 0;
+            const ReadBits rb = read_bit_lengths(P, sig[r] == P.nbin, info[r], ra.seq_len, L2, P.has_headers ? ra.head_len : 0, mn, mx);
+            const uint32_t bits[4] = {rb.meta, rb.dna, rb.qua, rb.head};
+            for (int s = 0; s < 4; ++s) { off[s][i] = pos[s]; pos[s] += bits[s]; }
+        }
+        for (int s = 0; s < 4; ++s) pos[s] = (pos[s] + 7) & ~7ull;
+    }
+    std::vector<uint32_t> words[4];
+    for (int s = 0; s < 4; ++s) { words[s].assign(pos[s] / 32 + 4, 0u); out_size[s] = pos[s] / 8; }
+
+    Slot seqA, quaA, seqB, quaB, head;
+    for (uint64_t b = 0; b < nb; ++b)
+    {
+        for (uint64_t i = bin_start[b]; i < bin_start[b + 1]; ++i)
+        {
+            const uint32_t r = order[i], inf = info[r];
+            const bool nbin = sig[r] == P.nbin;
+            const bool rev = (inf & FSB_INFO_REVERSE) != 0, swp = (inf & FSB_INFO_SWAPPED) != 0;
+            const bool a_is_m2 = pe && (rev != swp);
+            const int ma = a_is_m2 ? 1 : 0, mb = a_is_m2 ? 0 : 1;
+            const fsb_record& ra = ch->records[ma][r];
+            seqA.fill(ch->text[ma], ch->text_size[ma], ra.seq_off, ra.seq_len);
+            quaA.fill(ch->text[ma], ch->text_size[ma], ra.qua_off, ra.seq_len);
+            const uint32_t sfx = nbin ? 0u : P.k, mpos = inf & FSB_INFO_POS_MASK;
+            const bool plainA = (inf & FSB_INFO_PLAIN_A) != 0, plainB = (inf & FSB_INFO_PLAIN_B) != 0;
+            if (i == bin_start[b])
+            {   // PackToBin header (FastqPacker.cpp:581-583): minLen, maxLen, hasReadGroups = 0
+                or_bits(words[0].data(), (uint32_t)(off[0][i] - 17), ((bmin[b] & 0xFFu) << 9) | ((bmax[b] & 0xFFu) << 1), 17);
+            }
+            uint32_t lenB = 0;
+            pack_mate<NW>(P, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, words[1].data(), (uint32_t)off[1][i], words[2].data(), (uint32_t)off[2][i]);
+            if (pe)
+            {
+                const fsb_record& rbm = ch->records[mb][r];
+                lenB = rbm.seq_len;
+                seqB.fill(ch->text[mb], ch->text_size[mb], rbm.seq_off, rbm.seq_len);
+                quaB.fill(ch->text[mb], ch->text_size[mb], rbm.qua_off, rbm.seq_len);
+                const uint32_t dna_off = (uint32_t)off[1][i] + (ra.seq_len - sfx) * (plainA ? 2u : 3u);
+                const uint32_t qua_off = (uint32_t)off[2][i] + ra.seq_len * P.qua_bits;
+                pack_mate<NW>(P, seqB, quaB, rbm.seq_len, rev, plainB, 0, 0, words[1].data(), dna_off, words[2].data(), qua_off);
+            }
+            uint32_t mbits;
+            const uint32_t mv = meta_fields(P, nbin, inf, ra.seq_len, lenB, bmin[b], bmax[b], mbits);
+            or_bits(words[0].data(), (uint32_t)off[0][i], mv, mbits);
+            if (P.has_headers)
+            {
+                const fsb_record& r1 = ch->records[0][r];
+                head.fill(ch->text[0], ch->text_size[0], r1.head_off, r1.head_len);
+                pack_head(head.w.data(), head.addr, r1.head_len, words[3].data(), (uint32_t)off[3][i]);
+            }
+        }
+    }
+    for (int s = 0; s < 4; ++s)
+        for (uint64_t j = 0; j < out_size[s]; ++j) out[s][j] = (uint8_t)(words[s][j >> 2] >> (24 - 8 * (j & 3)));
+    return FSB_OK;
+}
+
+} // namespace
+
+// out[s] must have room for the oracle's stream size + 64 bytes
+extern "C" int emul_pack(const fsb_params* p, const fsb_chunk* ch, uint8_t* meta, uint8_t* dna, uint8_t* qua, uint8_t* head, uint64_t* sizes)
+{
+    const DeviceParams P = make_device_params(*p);
+    const uint64_t n = ch->n_records;
+    std::vector<uint32_t> sig(n), info(n);
+    int rc = emul_signatures(p, ch, sig.data(), info.data());
+    if (rc != FSB_OK) return rc;
+    uint32_t maxL = 1;
+    for (int m = 0; m < (P.paired ? 2 : 1); ++m)
+        for (uint64_t i = 0; i < n; ++i) maxL = std::max<uint32_t>(maxL, ch->records[m][i].seq_len);
+    uint8_t* out[4] = {meta, dna, qua, head};
+    switch ((maxL + 31) / 32)
+    {
+    case 1: return run_pack<1>(P, ch, sig.data(), info.data(), out, sizes);
+    case 2: return run_pack<2>(P, ch, sig.data(), info.data(), out, sizes);
+    case 3: return run_pack<3>(P, ch, sig.data(), info.data(), out, sizes);
+    case 4: return run_pack<4>(P, ch, sig.data(), info.data(), out, sizes);
+    case 5: return run_pack<5>(P, ch, sig.data(), info.data(), out, sizes);
+    case 6: return run_pack<6>(P, ch, sig.data(), info.data(), out, sizes);
+    case 7: return run_pack<7>(P, ch, sig.data(), info.data(), out, sizes);
+    case 8: return run_pack<8>(P, ch, sig.data(), info.data(), out, sizes);
+    }
+    return FSB_ERR_INPUT;
+}

@@ -42,3 +42,19 @@ def test_signature_core_matches_oracle(emul, name):
     assert bad.size == 0, f"{name}: signature of read {bad[0]}: {sig[bad[0]]:#x} vs {want['read_signature'][bad[0]]:#x} ({bad.size} differ)"
     bad = np.nonzero(info != want["read_info"])[0]
     assert bad.size == 0, f"{name}: info of read {bad[0]}: {info[bad[0]]:#x} vs {want['read_info'][bad[0]]:#x} ({bad.size} differ)"
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_pack_core_matches_oracle(emul, name):
+    params, chunk, keep = make_case(name)
+    want = O.bin_chunk("orc", params, chunk)
+    emul.emul_pack.restype = C.c_int
+    emul.emul_pack.argtypes = [C.POINTER(N.FsbParams), C.POINTER(N.FsbChunk)] + [C.c_void_p] * 5
+    bufs = [np.zeros(want[s].size + 64, dtype=np.uint8) for s in ("meta", "dna", "qua", "head")]
+    sizes = np.zeros(4, dtype=np.uint64)
+    assert emul.emul_pack(C.byref(params), C.byref(chunk), *[N.np_ptr(b) for b in bufs], N.np_ptr(sizes)) == N.FSB_OK
+    for k, s in enumerate(("meta", "dna", "qua", "head")):
+        assert int(sizes[k]) == want[s].size, f"{name}: stream {s} size {int(sizes[k])} vs {want[s].size}"
+        got = bufs[k][: want[s].size]
+        bad = np.nonzero(got != want[s])[0]
+        assert bad.size == 0, f"{name}: stream {s} differs at byte {bad[0]} of {want[s].size} ({bad.size} bytes differ)"
