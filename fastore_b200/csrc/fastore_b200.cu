@@ -156,16 +156,26 @@ cudaError_t launch_signature(const BatchView& B, const DeviceParams& P, uint32_t
 }
 
 template <int NW>
-cudaError_t launch_pack(const PackArgs& pa, uint32_t max_len, uint32_t max_head, cudaStream_t st)
+cudaError_t launch_pack(const PackArgs& pa, uint32_t max_len, uint32_t max_head, cudaStream_t st, int* launches)
 {
-    // largest tile whose shared memory still lets three blocks share an SM; smaller tiles for long reads
-    uint32_t T = pa.P.paired ? 64u : 128u;
-    PackTilePlan pl = make_pack_plan<NW>(pa.P, T, max_len, max_head);
-    while (pl.total_bytes > 74u * 1024u && T > 16u) { T >>= 1; pl = make_pack_plan<NW>(pa.P, T, max_len, max_head); }
-    cudaError_t e = cudaFuncSetAttribute(pack_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
-    if (e != cudaSuccess) return e;
-    const unsigned blocks = (unsigned)((pa.B.n_records + T - 1) / T);
-    pack_kernel<NW><<<blocks, pl.threads, pl.total_bytes, st>>>(pa, pl);
+    const uint64_t n = pa.B.n_records;
+    cudaError_t e;
+    {
+        const PackPlan pl = make_mate_plan<NW>(pa.P, max_len, pa.P.qua_bits);
+        if ((e = cudaFuncSetAttribute(pack_quality_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes)) != cudaSuccess) return e;
+        pack_quality_kernel<NW><<<(unsigned)((n + pl.T - 1) / pl.T), pl.threads, pl.total_bytes, st>>>(pa, pl);
+    }
+    {
+        const PackPlan pl = make_mate_plan<NW>(pa.P, max_len, 3);
+        if ((e = cudaFuncSetAttribute(pack_dna_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes)) != cudaSuccess) return e;
+        pack_dna_kernel<NW><<<(unsigned)((n + pl.T - 1) / pl.T), pl.threads, pl.total_bytes, st>>>(pa, pl);
+    }
+    {
+        const PackPlan pl = make_aux_plan(pa.P, max_head);
+        if ((e = cudaFuncSetAttribute(pack_aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes)) != cudaSuccess) return e;
+        pack_aux_kernel<<<(unsigned)((n + pl.T - 1) / pl.T), pl.threads, pl.total_bytes, st>>>(pa, pl);
+    }
+    *launches += 3;
     return cudaGetLastError();
 }
 
@@ -576,19 +586,20 @@ extern "C" int fsb_run(fsb_ctx* c)
     {
         PackArgs pa{B, P, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}}, nb_ptr};
         cudaError_t e = cudaSuccess;
+        int pack_launches = 0;
         switch ((c->max_len + 31) / 32)
         {
-        case 0: case 1: e = launch_pack<1>(pa, c->max_len, c->max_head, st); break;
-        case 2: e = launch_pack<2>(pa, c->max_len, c->max_head, st); break;
-        case 3: e = launch_pack<3>(pa, c->max_len, c->max_head, st); break;
-        case 4: e = launch_pack<4>(pa, c->max_len, c->max_head, st); break;
-        case 5: e = launch_pack<5>(pa, c->max_len, c->max_head, st); break;
-        case 6: e = launch_pack<6>(pa, c->max_len, c->max_head, st); break;
-        case 7: e = launch_pack<7>(pa, c->max_len, c->max_head, st); break;
-        default: e = launch_pack<8>(pa, c->max_len, c->max_head, st); break;
+        case 0: case 1: e = launch_pack<1>(pa, c->max_len, c->max_head, st, &pack_launches); break;
+        case 2: e = launch_pack<2>(pa, c->max_len, c->max_head, st, &pack_launches); break;
+        case 3: e = launch_pack<3>(pa, c->max_len, c->max_head, st, &pack_launches); break;
+        case 4: e = launch_pack<4>(pa, c->max_len, c->max_head, st, &pack_launches); break;
+        case 5: e = launch_pack<5>(pa, c->max_len, c->max_head, st, &pack_launches); break;
+        case 6: e = launch_pack<6>(pa, c->max_len, c->max_head, st, &pack_launches); break;
+        case 7: e = launch_pack<7>(pa, c->max_len, c->max_head, st, &pack_launches); break;
+        default: e = launch_pack<8>(pa, c->max_len, c->max_head, st, &pack_launches); break;
         }
         CUDA_TRY(c, e);
-        launches++;
+        launches += pack_launches;
     }
     if (ev)
     {

@@ -194,38 +194,74 @@ FSB_HD uint32_t quality4(uint32_t b, uint32_t off4 /* offset * 0x01010101 */, ui
     return gather4x3(v);
 }
 
+// ---- emission of a whole segment held in registers ------------------------------------------------------------
+// X[0 .. NX) are the segment's stream words (MSB-first; bits past `nbits` may hold anything).  The
+// segment goes to bit offset `off` of `words`: interior words are plain stores, the first and the
+// last word -- shared with the neighbouring segments -- are ORed into the zero-initialised buffer.
+template <int NX>
+FSB_HD void emit_words(const uint32_t (&X)[NX], uint32_t nbits, uint32_t* words, uint32_t off)
+{
+    if (nbits == 0) return;
+    const uint32_t phi = off & 31u;
+    uint32_t* w = words + (off >> 5);
+    const uint32_t end = phi + nbits;
+    const uint32_t last = (end - 1u) >> 5;                       // index of the last output word
+    const uint32_t tailbits = end - 32u * last;                  // 1..32 valid bits in it
+    const uint32_t lastmask = tailbits >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> tailbits);
+    uint32_t prev = 0;
+#pragma unroll
+    for (int j = 0; j <= NX; ++j)
+    {
+        if ((j & 3) == 0 && (uint32_t)j > last) break;
+        const uint32_t x = j < NX ? X[j] : 0u;
+        const uint32_t v = funnel_r(x, prev, phi);              // stream bits [32j - phi, 32j - phi + 32)
+        prev = x;
+        if ((uint32_t)j == last) or_word(w + j, v & lastmask);
+        else if (j == 0) or_word(w, v);
+        else if ((uint32_t)j < last) w[j] = v;
+    }
+}
+
 // ---- quality stream of one stored mate --------------------------------------------------------------------
 // 32 symbols -> Q stream words per round.
-template <int Q>
+template <int NW, int Q>
 FSB_HD void pack_quality(SymReader rd, uint32_t len, const DeviceParams& P, uint32_t* words, uint32_t off)
 {
-    if (len == 0) return;
-    BitSink s = sink_open(words, off, len * (uint32_t)Q);
+    uint32_t X[NW * Q];
     const uint32_t off4 = P.qua_offset * 0x01010101u, thr4 = P.qua_threshold * 0x01010101u;
-    for (uint32_t base = 0; base < len; base += 32)
-    {
-        uint32_t t[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = quality4<Q>(reader_next(rd), off4, thr4);
-        if (Q == 6)
+    for (int j = 0; j < NW; ++j)
+    {
+        if (32u * j < len)
         {
-            sink_push(s, (t[0] << 8) | (t[1] >> 16));
-            sink_push(s, (t[1] << 16) | (t[2] >> 8));
-            sink_push(s, (t[2] << 24) | t[3]);
-            sink_push(s, (t[4] << 8) | (t[5] >> 16));
-            sink_push(s, (t[5] << 16) | (t[6] >> 8));
-            sink_push(s, (t[6] << 24) | t[7]);
-        }
-        else if (Q == 3)
-        {
-            sink_push(s, (t[0] << 20) | (t[1] << 8) | (t[2] >> 4));
-            sink_push(s, (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8));
-            sink_push(s, (t[5] << 24) | (t[6] << 12) | t[7]);
+            uint32_t t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = quality4<Q>(reader_next(rd), off4, thr4);
+            if (Q == 6)
+            {
+                X[6 * j + 0] = (t[0] << 8) | (t[1] >> 16);
+                X[6 * j + 1] = (t[1] << 16) | (t[2] >> 8);
+                X[6 * j + 2] = (t[2] << 24) | t[3];
+                X[6 * j + 3] = (t[4] << 8) | (t[5] >> 16);
+                X[6 * j + 4] = (t[5] << 16) | (t[6] >> 8);
+                X[6 * j + 5] = (t[6] << 24) | t[7];
+            }
+            else if (Q == 3)
+            {
+                X[3 * j + 0] = (t[0] << 20) | (t[1] << 8) | (t[2] >> 4);
+                X[3 * j + 1] = (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8);
+                X[3 * j + 2] = (t[5] << 24) | (t[6] << 12) | t[7];
+            }
+            else
+                X[j] = (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7];
         }
         else
-            sink_push(s, (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7]);
+        {
+#pragma unroll
+            for (int u = 0; u < Q; ++u) X[Q * j + u] = 0;
+        }
     }
-    sink_close(s);
+    emit_words<NW * Q>(X, len * (uint32_t)Q, words, off);
 }
 
 // ---- DNA stream of one stored mate (StoreDna, FastqPacker.cpp:157-202) ----------------------------------
@@ -236,8 +272,6 @@ template <int NW, int SB>
 FSB_HD void pack_dna(SymReader rd, uint32_t len, bool rev, uint32_t cut_pos, uint32_t cut_len, uint32_t* words, uint32_t off)
 {
     constexpr int NX = SB * NW;                                  // stream words of 32*NW symbols
-    const uint32_t nbits = (len - cut_len) * (uint32_t)SB;
-    if (nbits == 0) return;
     uint32_t D[NX + 2];
     const uint32_t comp = rev ? 0x03030303u : 0u;                // rcCodes (FastqRecord.h:62-76): A<->T, C<->G, N stays
 #pragma unroll
@@ -277,20 +311,24 @@ FSB_HD void pack_dna(SymReader rd, uint32_t len, bool rev, uint32_t cut_pos, uin
         }
     }
     D[NX] = 0; D[NX + 1] = 0;
-    BitSink s = sink_open(words, off, nbits);
-    const uint32_t cb = cut_pos * (uint32_t)SB;                  // bit where the cut starts
-    const uint32_t cw = cut_len * (uint32_t)SB;                  // bits removed (< 64)
-    const uint32_t q = cw >> 5, r = cw & 31u;
-#pragma unroll
-    for (int j = 0; j < NX; ++j)
+    if (cut_len)
     {
-        if (32u * j >= nbits) break;
-        const uint32_t shifted = q ? funnel_l(D[j + 2], D[j + 1], r) : funnel_l(D[j + 1], D[j], r);      // stream bits 32j + cw ..
-        const int32_t keep = (int32_t)cb - 32 * j;                // leading bits of this word that precede the cut
-        const uint32_t m = keep <= 0 ? 0u : (keep >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> keep));
-        sink_push(s, (D[j] & m) | (shifted & ~m));
+        const uint32_t cb = cut_pos * (uint32_t)SB;              // bit where the cut starts
+        const uint32_t cw = cut_len * (uint32_t)SB;              // bits removed (< 64)
+        const uint32_t q = cw >> 5, r = cw & 31u;
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+        {
+            const uint32_t shifted = q ? funnel_l(D[j + 2], D[j + 1], r) : funnel_l(D[j + 1], D[j], r);      // stream bits 32j + cw ..
+            const int32_t keep = (int32_t)cb - 32 * j;            // leading bits of this word that precede the cut
+            const uint32_t m = keep <= 0 ? 0u : (keep >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> keep));
+            D[j] = (D[j] & m) | (shifted & ~m);
+        }
     }
-    sink_close(s);
+    uint32_t E[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) E[j] = D[j];
+    emit_words<NX>(E, (len - cut_len) * (uint32_t)SB, words, off);
 }
 
 // ---- title (StoreHeader, FastqPacker.cpp:272-287): 8 bits headLen, then 7 bits per char after '@' ---------

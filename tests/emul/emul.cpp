@@ -119,9 +119,9 @@ void pack_mate(const DeviceParams& P, const Slot& seq, const Slot& qua, uint32_t
     const SymReader rq = reader_open(qua.w.data(), qua.addr, len, rev);
     switch (P.qua_bits)
     {
-    case 6: pack_quality<6>(rq, len, P, qua_words, qua_off); break;
-    case 3: pack_quality<3>(rq, len, P, qua_words, qua_off); break;
-    default: pack_quality<1>(rq, len, P, qua_words, qua_off); break;
+    case 6: pack_quality<NW, 6>(rq, len, P, qua_words, qua_off); break;
+    case 3: pack_quality<NW, 3>(rq, len, P, qua_words, qua_off); break;
+    default: pack_quality<NW, 1>(rq, len, P, qua_words, qua_off); break;
     }
 }
 
