@@ -160,22 +160,23 @@ cudaError_t launch_pack(const PackArgs& pa, uint32_t max_len, uint32_t max_head,
 {
     const uint64_t n = pa.B.n_records;
     cudaError_t e;
+    const PackPlan pq = make_mate_plan<NW>(pa.P, max_len, pa.P.qua_bits);
+    const PackPlan pd = make_mate_plan<NW>(pa.P, max_len, 3);
+    const PackPlan px = make_aux_plan(pa.P, max_head);
     {
-        const PackPlan pl = make_mate_plan<NW>(pa.P, max_len, pa.P.qua_bits);
-        if ((e = cudaFuncSetAttribute(pack_quality_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes)) != cudaSuccess) return e;
-        pack_quality_kernel<NW><<<(unsigned)((n + pl.T - 1) / pl.T), pl.threads, pl.total_bytes, st>>>(pa, pl);
+        // only the words two tiles share have to be zero before the pack kernels run
+        const TileSizes ts{{px.T, pd.T, pq.T, px.T}};
+        const uint32_t minT = std::min(std::min(pq.T, pd.T), px.T);
+        const uint64_t tiles = (n + minT - 1) / minT;
+        zero_boundary_words_kernel<<<dim3((unsigned)((tiles + 255) / 256), 4), 256, 0, st>>>(pa, ts);
     }
-    {
-        const PackPlan pl = make_mate_plan<NW>(pa.P, max_len, 3);
-        if ((e = cudaFuncSetAttribute(pack_dna_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes)) != cudaSuccess) return e;
-        pack_dna_kernel<NW><<<(unsigned)((n + pl.T - 1) / pl.T), pl.threads, pl.total_bytes, st>>>(pa, pl);
-    }
-    {
-        const PackPlan pl = make_aux_plan(pa.P, max_head);
-        if ((e = cudaFuncSetAttribute(pack_aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes)) != cudaSuccess) return e;
-        pack_aux_kernel<<<(unsigned)((n + pl.T - 1) / pl.T), pl.threads, pl.total_bytes, st>>>(pa, pl);
-    }
-    *launches += 3;
+    if ((e = cudaFuncSetAttribute(pack_quality_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq.total_bytes)) != cudaSuccess) return e;
+    pack_quality_kernel<NW><<<(unsigned)((n + pq.T - 1) / pq.T), pq.threads, pq.total_bytes, st>>>(pa, pq);
+    if ((e = cudaFuncSetAttribute(pack_dna_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd.total_bytes)) != cudaSuccess) return e;
+    pack_dna_kernel<NW><<<(unsigned)((n + pd.T - 1) / pd.T), pd.threads, pd.total_bytes, st>>>(pa, pd);
+    if ((e = cudaFuncSetAttribute(pack_aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)px.total_bytes)) != cudaSuccess) return e;
+    pack_aux_kernel<<<(unsigned)((n + px.T - 1) / px.T), px.threads, px.total_bytes, st>>>(pa, px);
+    *launches += 4;
     return cudaGetLastError();
 }
 
@@ -434,7 +435,7 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
     CUDA_TRY(c, c->d_counts.ensure((ncounts + 1) * 4));
     CUDA_TRY(c, c->d_counts_scan.ensure((ncounts + 1) * 4));
     const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(n, ncounts), c->nb_max) + 1;
-    CUDA_TRY(c, c->d_scan_tmp.ensure((scan_num_tiles(max_scan_n) + 2) * 8));
+    CUDA_TRY(c, c->d_scan_tmp.ensure(4 * (scan_num_tiles(max_scan_n) + 2) * 8));
     CUDA_TRY(c, c->d_flags.ensure((n + 1) * 4));
     CUDA_TRY(c, c->d_flags_excl.ensure((n + 2) * 4));
     CUDA_TRY(c, c->d_bin_of.ensure((n + 1) * 4));
@@ -564,8 +565,11 @@ extern "C" int fsb_run(fsb_ctx* c)
                                                       c->d_bits[3].as<uint32_t>());
             launches += 2;
         }
-        for (int s = 0; s < 4; ++s)
-            launches += exclusive_scan<uint32_t, uint64_t>(c->d_bits[s].as<uint32_t>(), n, c->d_P[s].as<uint64_t>(), c->d_scan_tmp.as<uint64_t>(), st);
+        {
+            Ptr4<const uint32_t> in4{{c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(), c->d_bits[3].as<uint32_t>()}};
+            Ptr4<uint64_t> out4{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
+            launches += exclusive_scan4<uint32_t, uint64_t>(in4, n, out4, c->d_scan_tmp.as<uint64_t>(), st);
+        }
         if (nbm)
         {
             const unsigned grid_b = (unsigned)((nbm + tpb - 1) / tpb);
@@ -573,15 +577,17 @@ extern "C" int fsb_run(fsb_ctx* c)
                                                       c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>(), c->d_desc.as<fsb_bin_descriptor>());
             launches++;
         }
-        for (int s = 0; s < 4; ++s)
-            launches += exclusive_scan<uint64_t, uint64_t>(c->d_bytes[s].as<uint64_t>(), nbm, c->d_BO[s].as<uint64_t>(), c->d_scan_tmp.as<uint64_t>(), st);
+        {
+            Ptr4<const uint64_t> in4{{c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(), c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>()}};
+            Ptr4<uint64_t> out4{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
+            launches += exclusive_scan4<uint64_t, uint64_t>(in4, nbm, out4, c->d_scan_tmp.as<uint64_t>(), st);
+        }
         chunk_summary_kernel<<<c->n_chunks, 128, 0, st>>>(B, nb_ptr, A.bin_of, BO, c->d_desc.as<fsb_bin_descriptor>(), c->d_summary.as<ChunkSummary>());
         launches++;
     }
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[3], st));
 
     // ---- K4: pack ------------------------------------------------------------------------------------
-    for (int s = 0; s < 4; ++s) CUDA_TRY(c, cudaMemsetAsync(c->d_out[s].p, 0, c->out_cap[s], st));
     if (n)
     {
         PackArgs pa{B, P, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}}, nb_ptr};

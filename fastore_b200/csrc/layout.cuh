@@ -44,25 +44,39 @@ __global__ void bin_flags_kernel(const uint32_t* __restrict__ skeys, uint64_t n,
     if (i < n) flags[i] = (i == 0 || skeys[i] != skeys[i - 1]) ? 1u : 0u;
 }
 
-// bin index per sorted position, bin starts, per-bin min/max seqLen and raw sizes
+// bin index per sorted position, bin starts, per-bin min/max seqLen and raw sizes.  Records of a
+// bin are neighbours in the sorted order, so a warp first combines its lanes per bin
+// (__match_any_sync) and only one lane per (warp, bin) touches the per-bin counters.
 __global__ void bin_stats_kernel(BatchView B, DeviceParams P, SortedView S, const uint32_t* __restrict__ flags,
                                  const uint32_t* __restrict__ flags_excl, BinArrays A)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B.n_records) return;
-    const uint32_t f = flags[i];
-    const uint32_t bin = flags_excl[i] + f - 1;
-    A.bin_of[i] = bin;
-    if (f) A.bin_start[bin] = (uint32_t)i;
-    const uint32_t r = S.perm[i];
-    const fsb_record ra = B.rec[0][r];
-    const uint32_t L = ra.seq_len;
-    atomicMin(&A.bin_min[bin], L);
-    atomicMax(&A.bin_max[bin], L);
-    uint32_t raw = L;
-    if (P.paired) raw += B.rec[1][r].seq_len;
-    atomicAdd(&A.bin_raw_dna[bin], (unsigned long long)raw);
-    if (P.has_headers) atomicAdd(&A.bin_raw_head[bin], (unsigned long long)ra.head_len);
+    const bool live = i < B.n_records;
+    uint32_t bin = 0xFFFFFFFFu, L = 0, raw = 0, hl = 0;
+    if (live)
+    {
+        const uint32_t f = flags[i];
+        bin = flags_excl[i] + f - 1;
+        A.bin_of[i] = bin;
+        if (f) A.bin_start[bin] = (uint32_t)i;
+        const uint32_t r = S.perm[i];
+        const fsb_record ra = B.rec[0][r];
+        L = ra.seq_len;
+        raw = L;
+        if (P.paired) raw += B.rec[1][r].seq_len;
+        hl = ra.head_len;
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+    const uint32_t mn = __reduce_min_sync(peers, L), mx = __reduce_max_sync(peers, L);
+    const uint32_t sraw = __reduce_add_sync(peers, raw), shl = __reduce_add_sync(peers, hl);
+    if (live && (unsigned)(__ffs(peers) - 1) == lane)
+    {
+        atomicMin(&A.bin_min[bin], mn);
+        atomicMax(&A.bin_max[bin], mx);
+        atomicAdd(&A.bin_raw_dna[bin], (unsigned long long)sraw);
+        if (P.has_headers) atomicAdd(&A.bin_raw_head[bin], (unsigned long long)shl);
+    }
 }
 
 __global__ void read_bits_kernel(BatchView B, DeviceParams P, SortedView S, BinArrays A,

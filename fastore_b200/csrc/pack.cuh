@@ -251,6 +251,25 @@ __device__ __forceinline__ MyMate my_mate(const PackArgs& a, const TileRec& t, b
     return mm;
 }
 
+// ---- boundary words ---------------------------------------------------------------------------------------------
+// The pack kernels merge the first / last word of a tile with atomicOr when it is shared with the
+// neighbouring tile; those words -- and only those -- must be zero beforehand (this replaces a
+// memset of the whole output).  blockIdx.y = stream; tile sizes per stream in T[].
+struct TileSizes { uint32_t T[4]; };
+__global__ void __launch_bounds__(256) zero_boundary_words_kernel(PackArgs a, TileSizes ts)
+{
+    const int s = blockIdx.y;
+    const uint32_t T = ts.T[s];
+    const uint64_t n = a.B.n_records;
+    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i0 = tile * T;
+    if (i0 >= n) return;
+    unsigned long long b0, b1;
+    tile_range(a, s, i0, T, b0, b1);
+    if (b0 & 31u) a.O.w[s][b0 >> 5] = 0;
+    if (i0 + T >= n && (b1 & 31u)) a.O.w[s][b1 >> 5] = 0;
+}
+
 // ---- K4q: quality stream -------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__(kPackThreads) pack_quality_kernel(PackArgs a, PackPlan pl)

@@ -121,6 +121,92 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const IN* __restrict_
 
 inline uint64_t scan_num_tiles(uint64_t n) { return (n + kScanTile - 1) / kScanTile; }
 
+// ---- the same scan over four arrays of equal length in one set of launches (blockIdx.y = array) ----------
+template <typename T> struct Ptr4 { T* p[4]; };
+template <typename T> __device__ __forceinline__ T* pick4(const Ptr4<T>& a, unsigned k) { return k == 0 ? a.p[0] : (k == 1 ? a.p[1] : (k == 2 ? a.p[2] : a.p[3])); }
+
+template <typename IN, typename OUT>
+__global__ void __launch_bounds__(kScanThreads) scan4_tile_sums(Ptr4<const IN> in, uint64_t n, OUT* __restrict__ tile_sums, uint64_t tiles_stride)
+{
+    __shared__ OUT sm[kScanThreads / 32 + 1];
+    const IN* __restrict__ src = pick4(in, blockIdx.y);
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+    OUT s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const uint64_t idx = base + (uint64_t)i * kScanThreads + threadIdx.x;
+        if (idx < n) s += (OUT)src[idx];
+    }
+    OUT total;
+    block_exclusive_scan<OUT, kScanThreads>(s, total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.y * tiles_stride + blockIdx.x] = total;
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(1024) scan4_small(OUT* __restrict__ data, uint64_t n, uint64_t tiles_stride)
+{
+    __shared__ OUT sm[1024 / 32 + 1];
+    OUT* d = data + blockIdx.x * tiles_stride;                   // one block per array
+    OUT carry = 0;
+    for (uint64_t base = 0; base < n; base += 1024)
+    {
+        const uint64_t idx = base + threadIdx.x;
+        const OUT v = idx < n ? d[idx] : OUT(0);
+        OUT total;
+        const OUT ex = block_exclusive_scan<OUT, 1024>(v, total, sm);
+        if (idx < n) d[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) d[n] = carry;
+}
+
+template <typename IN, typename OUT>
+__global__ void __launch_bounds__(kScanThreads) scan4_apply(Ptr4<const IN> in, uint64_t n, const OUT* __restrict__ tile_offsets, uint64_t tiles_stride,
+                                                             Ptr4<OUT> out)
+{
+    __shared__ OUT sm[kScanThreads / 32 + 1];
+    const IN* __restrict__ src = pick4(in, blockIdx.y);
+    OUT* __restrict__ dst = pick4(out, blockIdx.y);
+    const OUT* toff = tile_offsets + blockIdx.y * tiles_stride;
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    OUT v[kScanItems];
+    OUT s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const uint64_t idx = base + i;
+        v[i] = idx < n ? (OUT)src[idx] : OUT(0);
+        s += v[i];
+    }
+    OUT total;
+    OUT ex = block_exclusive_scan<OUT, kScanThreads>(s, total, sm) + toff[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const uint64_t idx = base + i;
+        if (idx < n) dst[idx] = ex;
+        ex += v[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) dst[n] = toff[gridDim.x];
+}
+
+// out[k] must hold n + 1 entries; tmp must hold 4 * (scan_num_tiles(n) + 1) entries.  3 launches.
+template <typename IN, typename OUT>
+inline int exclusive_scan4(Ptr4<const IN> in, uint64_t n, Ptr4<OUT> out, OUT* tmp, cudaStream_t st)
+{
+    if (n == 0)
+    {
+        for (int k = 0; k < 4; ++k) cudaMemsetAsync(out.p[k], 0, sizeof(OUT), st);
+        return 0;
+    }
+    const uint64_t tiles = scan_num_tiles(n), stride = tiles + 1;
+    scan4_tile_sums<IN, OUT><<<dim3((unsigned)tiles, 4), kScanThreads, 0, st>>>(in, n, tmp, stride);
+    scan4_small<OUT><<<4, 1024, 0, st>>>(tmp, tiles, stride);
+    scan4_apply<IN, OUT><<<dim3((unsigned)tiles, 4), kScanThreads, 0, st>>>(in, n, tmp, stride, out);
+    return 3;
+}
+
 // out must hold n + 1 entries; tmp must hold scan_num_tiles(n) + 1 entries.  3 launches.
 template <typename IN, typename OUT>
 inline int exclusive_scan(const IN* in, uint64_t n, OUT* out, OUT* tmp, cudaStream_t st)
