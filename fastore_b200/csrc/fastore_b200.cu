@@ -7,6 +7,7 @@
 // chunk still yields exactly its own BinaryBinBlock, byte for byte.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -243,6 +244,7 @@ extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fs
     c->dp = make_device_params(*p);
 
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail(nullptr, FSB_ERR_CUDA, "cudaSetDevice failed"); }
+    if (const char* g = std::getenv("FSB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else
     {
