@@ -72,6 +72,52 @@ FSB_HD uint32_t find_chunk(const BatchView& b, uint64_t i)
     return lo;
 }
 
+// ---- the per-record card carried through the sort -------------------------------------------------------
+// K1 knows everything later stages need about a record except where it lands; instead of leaving it
+// in per-record tables that would have to be gathered by sorted index (one 128-byte DRAM line per
+// 16-byte entry on B200), it rides through the radix sort as the 64-bit value of the (key, value) pair:
+//   bits  0..3   flags   FSB_INFO_REVERSE | SWAPPED | PLAIN_A | PLAIN_B  (>> 16)
+//   bits  4..11  minimPos in the stored orientation
+//   bits 12..19  length of stored mate A        bits 20..27  length of stored mate B (0 for SE)
+//   bits 28..35  headLen (0 when titles are not kept)
+//   bits 36..63  record index inside the batch (< 2^28)
+constexpr uint32_t kMaxBatchRecords = (1u << 28) - 1u;
+FSB_HD uint64_t card_make(uint32_t rec, uint32_t info, uint32_t lenA, uint32_t lenB, uint32_t H)
+{
+    return ((uint64_t)rec << 36) | ((uint64_t)(H & 0xFFu) << 28) | ((uint64_t)(lenB & 0xFFu) << 20) | ((uint64_t)(lenA & 0xFFu) << 12) |
+           ((uint64_t)(info & 0xFFu) << 4) | (uint64_t)((info >> 16) & 0xFu);
+}
+FSB_HD uint32_t card_rec(uint64_t c) { return (uint32_t)(c >> 36); }
+FSB_HD uint32_t card_info(uint64_t c) { return (((uint32_t)c & 0xFu) << 16) | (((uint32_t)c >> 4) & 0xFFu); }      // minimPos | FSB_INFO_*
+FSB_HD uint32_t card_lenA(uint64_t c) { return ((uint32_t)c >> 12) & 0xFFu; }
+FSB_HD uint32_t card_lenB(uint64_t c) { return ((uint32_t)c >> 20) & 0xFFu; }
+FSB_HD uint32_t card_head(uint64_t c) { return (uint32_t)(c >> 28) & 0xFFu; }
+
+// ---- the per-record slot K1 writes and K4 gathers -----------------------------------------------------------
+// One slot per record (pair) in input order, 128-byte aligned so that a gather by sorted index only
+// touches lines it uses completely.  It holds the record's contribution to the quality, title and
+// DNA streams exactly as they will appear in the output (stored orientation, MSB-first), each
+// region starting at bit 0 of a 16-byte aligned word offset:
+//   [0, qw)            quality of stored mate A then B      (lenA + lenB) * q bits
+//   [qw, qw + hw)      title: 8 bits headLen + 7 bits/char   (mate-1 title)
+//   [qw + hw, words)   DNA of mate A without the signature, then mate B, 2 or 3 bits per symbol
+struct SlotGeom
+{
+    uint32_t qw, hw, dw;     // region sizes in 32-bit words, multiples of 4
+    uint32_t words;          // slot stride in words, multiple of 32 (128 bytes)
+};
+inline SlotGeom make_slot_geom(const DeviceParams& P, uint32_t max_len, uint32_t max_head)
+{
+    SlotGeom g{};
+    const uint32_t mates = P.paired ? 2u : 1u;
+    auto up4 = [](uint32_t bits) { return (((bits + 31u) >> 5) + 3u) & ~3u; };
+    g.qw = up4(mates * max_len * P.qua_bits);
+    g.hw = P.has_headers ? up4(8u + 7u * (max_head ? max_head - 1u : 0u)) : 0u;
+    g.dw = up4(mates * max_len * 3u);
+    g.words = (g.qw + g.hw + g.dw + 31u) & ~31u;
+    return g;
+}
+
 // ---- intrinsics with host equivalents --------------------------------------------------------------
 FSB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s)      // low word of (hi:lo) >> s, s in [0, 31]
 {

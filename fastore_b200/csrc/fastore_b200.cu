@@ -1,5 +1,5 @@
 // fastore_b200.cu -- the C ABI of include/fastore_b200.h: context, staging, the kernel pipeline
-// (K1 signature -> stable radix sort -> layout scans -> K4 pack) and result fetch.
+// (K1 ingest -> stable radix sort -> layout scans -> K4 place) and result fetch.
 //
 // Host-side structure mirrors what the reference does per chunk in its -t1 loop
 // (BinModule.cpp:124-167): Categorize(reads, bins); PackToBins(bins, block).  Several chunks may be
@@ -18,9 +18,9 @@
 #include "../../include/fastore_b200.h"
 #include "scan_sort.cuh"
 #include "stage.cuh"
-#include "signature.cuh"
+#include "ingest.cuh"
 #include "layout.cuh"
-#include "pack.cuh"
+#include "place.cuh"
 
 using namespace fsb;
 
@@ -97,12 +97,13 @@ struct fsb_ctx
     DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats;
     PinBuf h_stage_stats;
     uint32_t min_len = 0, max_len = 0, max_head = 0;
-    DevBuf d_keys[2], d_vals[2], d_info, d_sig, d_counts, d_counts_scan, d_scan_tmp;
+    SlotGeom slot_geom{};
+    DevBuf d_keys[2], d_cards[2], d_slots, d_info, d_sig, d_counts, d_counts_scan, d_scan_tmp;
     DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head;
     DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4], d_desc, d_summary, d_out[4];
     PinBuf h_summary, h_out[4], h_desc, h_sig, h_info;
     uint32_t* sorted_keys = nullptr;
-    uint32_t* sorted_vals = nullptr;
+    unsigned long long* sorted_cards = nullptr;
 
     // ---- profiling -----------------------------------------------------------------------------
     std::vector<cudaEvent_t> events;             // kMaxPendingProfiles * (FSB_STAGE_COUNT + 1)
@@ -145,39 +146,29 @@ BatchView batch_view(const fsb_ctx* c)
 }
 
 template <int NW>
-cudaError_t launch_signature(const BatchView& B, const DeviceParams& P, uint32_t* keys, uint32_t* info, uint32_t* sig, cudaStream_t st)
+cudaError_t launch_ingest(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t* keys, unsigned long long* cards,
+                          uint32_t* slots, uint32_t* sig, uint32_t* info, cudaStream_t st)
 {
-    const size_t smem = sig_smem_bytes<NW>();
-    cudaError_t e = cudaFuncSetAttribute(signature_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const IngestPlan pl = make_ingest_plan<NW>(P, G, max_head);
+    cudaError_t e = cudaFuncSetAttribute(ingest_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
     if (e != cudaSuccess) return e;
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
-    const unsigned blocks = (unsigned)((n_mates + kSigWarps * 32 - 1) / (kSigWarps * 32));
-    signature_kernel<NW><<<blocks, kSigWarps * 32, smem, st>>>(B, P, keys, info, sig);
+    const unsigned blocks = (unsigned)((n_mates + pl.warps * 32 - 1) / (pl.warps * 32));
+    ingest_kernel<NW><<<blocks, pl.warps * 32, pl.total_bytes, st>>>(B, P, G, pl, keys, cards, slots, sig, info);
     return cudaGetLastError();
 }
 
-template <int NW>
-cudaError_t launch_pack(const PackArgs& pa, uint32_t max_len, uint32_t max_head, cudaStream_t st, int* launches)
+cudaError_t launch_place(const PlaceArgs& pa, uint32_t max_len, uint32_t max_head, cudaStream_t st, int* launches)
 {
     const uint64_t n = pa.B.n_records;
-    cudaError_t e;
-    const PackPlan pq = make_mate_plan<NW>(pa.P, max_len, pa.P.qua_bits);
-    const PackPlan pd = make_mate_plan<NW>(pa.P, max_len, 3);
-    const PackPlan px = make_aux_plan(pa.P, max_head);
-    {
-        // only the words two tiles share have to be zero before the pack kernels run
-        const TileSizes ts{{px.T, pd.T, pq.T, px.T}};
-        const uint32_t minT = std::min(std::min(pq.T, pd.T), px.T);
-        const uint64_t tiles = (n + minT - 1) / minT;
-        zero_boundary_words_kernel<<<dim3((unsigned)((tiles + 255) / 256), 4), 256, 0, st>>>(pa, ts);
-    }
-    if ((e = cudaFuncSetAttribute(pack_quality_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq.total_bytes)) != cudaSuccess) return e;
-    pack_quality_kernel<NW><<<(unsigned)((n + pq.T - 1) / pq.T), pq.threads, pq.total_bytes, st>>>(pa, pq);
-    if ((e = cudaFuncSetAttribute(pack_dna_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd.total_bytes)) != cudaSuccess) return e;
-    pack_dna_kernel<NW><<<(unsigned)((n + pd.T - 1) / pd.T), pd.threads, pd.total_bytes, st>>>(pa, pd);
-    if ((e = cudaFuncSetAttribute(pack_aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)px.total_bytes)) != cudaSuccess) return e;
-    pack_aux_kernel<<<(unsigned)((n + px.T - 1) / px.T), px.threads, px.total_bytes, st>>>(pa, px);
-    *launches += 4;
+    const PlacePlan pl = make_place_plan(pa.P, pa.G, max_len, max_head);
+    const uint64_t tiles = (n + pl.T - 1) / pl.T;
+    // only the words two tiles share have to be zero before K4 runs
+    zero_boundary_words_kernel<<<dim3((unsigned)((tiles + 255) / 256), 4), 256, 0, st>>>(pa, pl.T);
+    cudaError_t e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
+    if (e != cudaSuccess) return e;
+    place_kernel<<<(unsigned)tiles, pl.threads, pl.total_bytes, st>>>(pa, pl);
+    *launches += 2;
     return cudaGetLastError();
 }
 
@@ -261,8 +252,8 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& e : c->events) cudaEventDestroy(e);
-    DevBuf* dev[] = {&c->d_text[0], &c->d_text[1], &c->d_rec[0], &c->d_rec[1], &c->d_chunk_meta, &c->d_stage_stats, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0],
-                     &c->d_vals[1], &c->d_info, &c->d_sig, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags, &c->d_flags_excl,
+    DevBuf* dev[] = {&c->d_text[0], &c->d_text[1], &c->d_rec[0], &c->d_rec[1], &c->d_chunk_meta, &c->d_stage_stats, &c->d_keys[0], &c->d_keys[1], &c->d_cards[0],
+                     &c->d_cards[1], &c->d_slots, &c->d_info, &c->d_sig, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags, &c->d_flags_excl,
                      &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
                      &c->d_bits[2], &c->d_bits[3], &c->d_P[0], &c->d_P[1], &c->d_P[2], &c->d_P[3], &c->d_bytes[0], &c->d_bytes[1],
                      &c->d_bytes[2], &c->d_bytes[3], &c->d_BO[0], &c->d_BO[1], &c->d_BO[2], &c->d_BO[3], &c->d_desc, &c->d_summary,
@@ -355,7 +346,7 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
         n += ch.n_records;
     }
     c->chunk_first_rec[n_chunks] = n;
-    if (n >= 0xFFFFFFFFull) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^32-2 records in one batch");
+    if (n > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
     c->n_records = n;
     c->nb_max = std::min<uint64_t>(n, (uint64_t)n_chunks * ((uint64_t)c->dp.nbin + 1));
     c->sort_passes = (int)((c->dp.key_bits + bits_for(n_chunks - 1) + 7) / 8);
@@ -430,8 +421,10 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
     for (int i = 0; i < 2; ++i)
     {
         CUDA_TRY(c, c->d_keys[i].ensure((n + 1) * 4));
-        CUDA_TRY(c, c->d_vals[i].ensure((n + 1) * 4));
+        CUDA_TRY(c, c->d_cards[i].ensure((n + 1) * 8));
     }
+    c->slot_geom = make_slot_geom(c->dp, c->max_len, c->max_head);
+    CUDA_TRY(c, c->d_slots.ensure((n + 1) * (size_t)c->slot_geom.words * 4));
     CUDA_TRY(c, c->d_info.ensure((n + 1) * 4));
     CUDA_TRY(c, c->d_sig.ensure((n + 1) * 4));
     CUDA_TRY(c, c->d_counts.ensure((ncounts + 1) * 4));
@@ -495,23 +488,26 @@ extern "C" int fsb_run(fsb_ctx* c)
     const unsigned tpb = 256;
     const unsigned grid_n = (unsigned)std::max<uint64_t>(1, (n + tpb - 1) / tpb);
 
-    // ---- K1: signatures ---------------------------------------------------------------------------
+    // ---- K1: ingest (signature + prepacked slots) -----------------------------------------------------------
     if (n)
     {
         uint32_t* keys = c->d_keys[0].as<uint32_t>();
-        uint32_t* info = c->d_info.as<uint32_t>();
+        unsigned long long* cards = c->d_cards[0].as<unsigned long long>();
+        uint32_t* slots = c->d_slots.as<uint32_t>();
         uint32_t* sig = c->per_read ? c->d_sig.as<uint32_t>() : nullptr;
+        uint32_t* info = c->per_read ? c->d_info.as<uint32_t>() : nullptr;
+        const SlotGeom& G = c->slot_geom;
         cudaError_t e = cudaSuccess;
         switch ((c->max_len + 31) / 32)              // words of 32 bases per mate
         {
-        case 0: case 1: e = launch_signature<1>(B, P, keys, info, sig, st); break;
-        case 2: e = launch_signature<2>(B, P, keys, info, sig, st); break;
-        case 3: e = launch_signature<3>(B, P, keys, info, sig, st); break;
-        case 4: e = launch_signature<4>(B, P, keys, info, sig, st); break;
-        case 5: e = launch_signature<5>(B, P, keys, info, sig, st); break;
-        case 6: e = launch_signature<6>(B, P, keys, info, sig, st); break;
-        case 7: e = launch_signature<7>(B, P, keys, info, sig, st); break;
-        default: e = launch_signature<8>(B, P, keys, info, sig, st); break;
+        case 0: case 1: e = launch_ingest<1>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
+        case 2: e = launch_ingest<2>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
+        case 3: e = launch_ingest<3>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
+        case 4: e = launch_ingest<4>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
+        case 5: e = launch_ingest<5>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
+        case 6: e = launch_ingest<6>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
+        case 7: e = launch_ingest<7>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
+        default: e = launch_ingest<8>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
         }
         CUDA_TRY(c, e);
         launches++;
@@ -530,19 +526,19 @@ extern "C" int fsb_run(fsb_ctx* c)
             sort_histogram<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), n, shift, c->d_counts.as<uint32_t>(), nblocks);
             launches++;
             launches += exclusive_scan<uint32_t, uint32_t>(c->d_counts.as<uint32_t>(), ncounts, c->d_counts_scan.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
-            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), pass == 0 ? nullptr : c->d_vals[cur].as<uint32_t>(), n, shift,
+            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), c->d_cards[cur].as<unsigned long long>(), n, shift,
                                                             c->d_counts_scan.as<uint32_t>(), nblocks, c->d_keys[cur ^ 1].as<uint32_t>(),
-                                                            c->d_vals[cur ^ 1].as<uint32_t>());
+                                                            c->d_cards[cur ^ 1].as<unsigned long long>());
             launches++;
             cur ^= 1;
         }
     }
     c->sorted_keys = c->d_keys[cur].as<uint32_t>();
-    c->sorted_vals = c->d_vals[cur].as<uint32_t>();
+    c->sorted_cards = c->d_cards[cur].as<unsigned long long>();
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[2], st));
 
     // ---- layout --------------------------------------------------------------------------------------
-    SortedView S{c->sorted_keys, c->sorted_vals, c->d_info.as<uint32_t>()};
+    SortedView S{c->sorted_keys, c->sorted_cards};
     BinArrays A{c->d_bin_of.as<uint32_t>(), c->d_bin_start.as<uint32_t>(), c->d_bin_min.as<uint32_t>(), c->d_bin_max.as<uint32_t>(),
                 c->d_raw_dna.as<unsigned long long>(), c->d_raw_head.as<unsigned long long>()};
     StreamScans SC{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
@@ -562,8 +558,8 @@ extern "C" int fsb_run(fsb_ctx* c)
         launches += exclusive_scan<uint32_t, uint32_t>(c->d_flags.as<uint32_t>(), n, c->d_flags_excl.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
         if (n)
         {
-            bin_stats_kernel<<<grid_n, tpb, 0, st>>>(B, P, S, c->d_flags.as<uint32_t>(), c->d_flags_excl.as<uint32_t>(), A);
-            read_bits_kernel<<<grid_n, tpb, 0, st>>>(B, P, S, A, c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(),
+            bin_stats_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, c->d_flags.as<uint32_t>(), c->d_flags_excl.as<uint32_t>(), A);
+            read_bits_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, A, c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(),
                                                       c->d_bits[3].as<uint32_t>());
             launches += 2;
         }
@@ -589,25 +585,14 @@ extern "C" int fsb_run(fsb_ctx* c)
     }
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[3], st));
 
-    // ---- K4: pack ------------------------------------------------------------------------------------
+    // ---- K4: place ------------------------------------------------------------------------------------
     if (n)
     {
-        PackArgs pa{B, P, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}}, nb_ptr};
-        cudaError_t e = cudaSuccess;
-        int pack_launches = 0;
-        switch ((c->max_len + 31) / 32)
-        {
-        case 0: case 1: e = launch_pack<1>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        case 2: e = launch_pack<2>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        case 3: e = launch_pack<3>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        case 4: e = launch_pack<4>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        case 5: e = launch_pack<5>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        case 6: e = launch_pack<6>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        case 7: e = launch_pack<7>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        default: e = launch_pack<8>(pa, c->max_len, c->max_head, st, &pack_launches); break;
-        }
-        CUDA_TRY(c, e);
-        launches += pack_launches;
+        PlaceArgs pa{B, P, c->slot_geom, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}},
+                     c->d_slots.as<uint32_t>(), nb_ptr};
+        int place_launches = 0;
+        CUDA_TRY(c, launch_place(pa, c->max_len, c->max_head, st, &place_launches));
+        launches += place_launches;
     }
     if (ev)
     {

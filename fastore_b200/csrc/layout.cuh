@@ -13,16 +13,15 @@
 //              qua : q bits per base; head: 8 + 7 * (headLen - 1) bits (mate-1 header only).
 #pragma once
 
-#include "signature.cuh"
+#include "ingest.cuh"
 #include "pack_core.cuh"
 
 namespace fsb {
 
 struct SortedView
 {
-    const uint32_t* skeys;      // [n] sorted keys (chunk : signature)
-    const uint32_t* perm;       // [n] sorted position -> record index
-    const uint32_t* info;       // [n] per record (input order)
+    const uint32_t* skeys;              // [n] sorted keys (chunk : signature)
+    const unsigned long long* cards;    // [n] the records' cards in sorted order (core.cuh: card_make)
 };
 
 struct BinArrays
@@ -47,11 +46,11 @@ __global__ void bin_flags_kernel(const uint32_t* __restrict__ skeys, uint64_t n,
 // bin index per sorted position, bin starts, per-bin min/max seqLen and raw sizes.  Records of a
 // bin are neighbours in the sorted order, so a warp first combines its lanes per bin
 // (__match_any_sync) and only one lane per (warp, bin) touches the per-bin counters.
-__global__ void bin_stats_kernel(BatchView B, DeviceParams P, SortedView S, const uint32_t* __restrict__ flags,
+__global__ void bin_stats_kernel(uint64_t n, DeviceParams P, SortedView S, const uint32_t* __restrict__ flags,
                                  const uint32_t* __restrict__ flags_excl, BinArrays A)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < B.n_records;
+    const bool live = i < n;
     uint32_t bin = 0xFFFFFFFFu, L = 0, raw = 0, hl = 0;
     if (live)
     {
@@ -59,12 +58,10 @@ __global__ void bin_stats_kernel(BatchView B, DeviceParams P, SortedView S, cons
         bin = flags_excl[i] + f - 1;
         A.bin_of[i] = bin;
         if (f) A.bin_start[bin] = (uint32_t)i;
-        const uint32_t r = S.perm[i];
-        const fsb_record ra = B.rec[0][r];
-        L = ra.seq_len;
-        raw = L;
-        if (P.paired) raw += B.rec[1][r].seq_len;
-        hl = ra.head_len;
+        const uint64_t c = S.cards[i];
+        L = card_lenA(c);                       // PE mates have equal lengths (checked by fsb_stage), so A's length is "seqLen"
+        raw = L + card_lenB(c);
+        hl = card_head(c);
     }
     const unsigned lane = threadIdx.x & 31;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
@@ -79,17 +76,15 @@ __global__ void bin_stats_kernel(BatchView B, DeviceParams P, SortedView S, cons
     }
 }
 
-__global__ void read_bits_kernel(BatchView B, DeviceParams P, SortedView S, BinArrays A,
+__global__ void read_bits_kernel(uint64_t n, DeviceParams P, SortedView S, BinArrays A,
                                  uint32_t* __restrict__ bm, uint32_t* __restrict__ bd, uint32_t* __restrict__ bq, uint32_t* __restrict__ bh)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B.n_records) return;
-    const uint32_t r = S.perm[i];
+    if (i >= n) return;
+    const uint64_t c = S.cards[i];
     const uint32_t bin = A.bin_of[i];
-    const fsb_record ra = B.rec[0][r];
-    const uint32_t L2 = P.paired ? B.rec[1][r].seq_len : 0;
     const bool nbin = (S.skeys[i] & ((1u << P.key_bits) - 1)) == P.nbin;
-    const ReadBits b = read_bit_lengths(P, nbin, S.info[r], ra.seq_len, L2, P.has_headers ? ra.head_len : 0, A.bin_min[bin], A.bin_max[bin]);
+    const ReadBits b = read_bit_lengths(P, nbin, card_info(c), card_lenA(c), card_lenB(c), card_head(c), A.bin_min[bin], A.bin_max[bin]);
     bm[i] = b.meta; bd[i] = b.dna; bq[i] = b.qua; bh[i] = b.head;
 }
 

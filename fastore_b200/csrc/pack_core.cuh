@@ -222,6 +222,61 @@ FSB_HD void emit_words(const uint32_t (&X)[NX], uint32_t nbits, uint32_t* words,
     }
 }
 
+// ---- K4: move one prepacked segment to its final bit position ------------------------------------------------
+// `src` (16-byte aligned) holds `nbits` bits starting at bit 0 of src[0], MSB-first; they go to bit
+// offset `off` of `words`.  Interior words are plain stores, the first and the last word -- shared
+// with the neighbouring segments -- are ORed into the zero-initialised buffer.  Reads whole groups
+// of four source words (up to 3 words past the segment; the caller's buffer covers them).
+FSB_HD void load4(const uint32_t* p, uint32_t (&x)[4])
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+#else
+    for (int u = 0; u < 4; ++u) x[u] = p[u];
+#endif
+}
+FSB_HD void shift_copy(const uint32_t* src, uint32_t nbits, uint32_t* words, uint32_t off)
+{
+    if (nbits == 0) return;
+    const uint32_t phi = off & 31u;
+    uint32_t* w = words + (off >> 5);
+    const uint32_t end = phi + nbits;
+    const uint32_t last = (end - 1u) >> 5;                       // index of the last output word
+    const uint32_t tailbits = end - 32u * last;                  // 1..32 valid bits in it
+    const uint32_t lastmask = tailbits >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> tailbits);
+    uint32_t prev = 0, j = 0, x[4];
+    if (last >= 4u)
+    {   // first group: output word 0 is shared with the previous segment
+        load4(src, x);
+        or_word(w, funnel_r(x[0], 0u, phi));
+        w[1] = funnel_r(x[1], x[0], phi); w[2] = funnel_r(x[2], x[1], phi); w[3] = funnel_r(x[3], x[2], phi);
+        prev = x[3];
+        for (j = 4; j + 4u <= last; j += 4)                       // groups whose four output words all lie strictly inside the segment
+        {
+            load4(src + j, x);
+            w[j] = funnel_r(x[0], prev, phi); w[j + 1] = funnel_r(x[1], x[0], phi);
+            w[j + 2] = funnel_r(x[2], x[1], phi); w[j + 3] = funnel_r(x[3], x[2], phi);
+            prev = x[3];
+        }
+    }
+    // last group: output words j .. last (1 to 4 of them; bits past the segment in the source are masked off)
+    load4(src + j, x);
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u)
+    {
+        const uint32_t jj = j + u;
+        if (jj <= last)
+        {
+            const uint32_t v = funnel_r(x[u], prev, phi);       // stream bits [32 jj - phi, 32 jj - phi + 32)
+            prev = x[u];
+            if (jj == last) or_word(w + jj, v & lastmask);
+            else if (jj == 0) or_word(w, v);
+            else w[jj] = v;
+        }
+    }
+}
+
 // ---- quality stream of one stored mate --------------------------------------------------------------------
 // 32 symbols -> Q stream words per round.
 template <int NW, int Q>

@@ -1,0 +1,292 @@
+// place.cuh -- K4: scatter the prepacked records into the four output streams (sm_100a).
+//
+// Replaces the sequential appends of FastqRecordsPackerSE/PE::StoreRecords / StoreNextRecord into the
+// four BitMemoryWriters and the per-bin framing of PackToBin (FastqPacker.cpp:113-153, 541-602,
+// 734-759, 815-859; BitMemory.h:216-433).
+//
+// K1 (ingest.cuh) has left every record's quality, title and DNA bits in a 128-byte aligned slot in
+// input order.  Bins are laid out back to back in the sorted order, so the T consecutive sorted
+// records a block owns cover one contiguous bit range of every stream.  A block
+//   1. looks up its records (sorted key + card, bin, bit offsets from the layout scans);
+//   2. gathers their slots -- whole, fully used 128-byte lines -- into shared memory with cp.async;
+//   3. funnel-shifts every segment to its bit phase into per-stream staging buffers (one thread per
+//      (record, segment); the record's meta fields and the 17-bit bin headers are produced here);
+//   4. writes the staging buffers out with coalesced 16-byte stores; only the first / last word of a
+//      tile, shared with the neighbouring tiles, is merged with atomicOr into pre-zeroed words.
+#pragma once
+
+#include "layout.cuh"
+#include "pack_core.cuh"
+
+namespace fsb {
+
+struct OutStreams
+{
+    uint32_t* w[4];          // meta, dna, qua, head as 32-bit words (tile-boundary words zero-initialised)
+};
+
+struct PlaceArgs
+{
+    BatchView B;
+    DeviceParams P;
+    SlotGeom G;
+    SortedView S;
+    BinArrays A;
+    StreamScans SC;
+    BinOffsets BO;
+    OutStreams O;
+    const uint32_t* slots;   // [n_records][G.words]
+    const uint32_t* nb_ptr;  // number of bins (device)
+};
+
+// bit offset of the record at sorted position i in stream s
+__device__ __forceinline__ uint64_t stream_offset(const PlaceArgs& a, int s, uint64_t i, uint32_t bin, uint64_t start)
+{
+    return 8ull * a.BO.B[s][bin] + (a.SC.P[s][i] - a.SC.P[s][start]) + (s == 0 ? 17ull : 0ull);
+}
+
+// The tile's bit range in stream s: from its first record (or the start of that record's bin,
+// header and all) to the same point of the next tile.
+__device__ __forceinline__ void tile_range(const PlaceArgs& a, int s, uint64_t i0, uint32_t T, unsigned long long& b0, unsigned long long& b1)
+{
+    const uint64_t n = a.B.n_records;
+    {
+        const uint32_t bin = a.A.bin_of[i0];
+        const uint64_t start = a.A.bin_start[bin];
+        b0 = (i0 == start) ? 8ull * a.BO.B[s][bin] : stream_offset(a, s, i0, bin, start);
+    }
+    const uint64_t in = i0 + T;
+    if (in < n)
+    {
+        const uint32_t bin = a.A.bin_of[in];
+        const uint64_t start = a.A.bin_start[bin];
+        b1 = (in == start) ? 8ull * a.BO.B[s][bin] : stream_offset(a, s, in, bin, start);
+    }
+    else b1 = 8ull * a.BO.B[s][*a.nb_ptr];
+}
+
+// Write a tile's staging buffer to its stream.  Staging word j is stream word base + j with base a
+// multiple of 4 (16-byte aligned), so whole groups of four go out as vector stores; the few words
+// at both ends are handled one by one, and the first / last word are merged with atomicOr when
+// they are shared with the neighbouring tile.
+__device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_words, uint64_t b0, uint64_t b1)
+{
+    if (b1 <= b0) return;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t base = (b0 >> 5) & ~3ull;
+    const uint32_t ws = (uint32_t)((b0 >> 5) - base), we = (uint32_t)(((b1 - 1) >> 5) - base);       // first / last word with bits of this tile
+    const bool head_shared = (b0 & 31u) != 0, tail_shared = (b1 & 31u) != 0;
+    const uint32_t fs = ws + (head_shared ? 1u : 0u), fe1 = we + 1u - (tail_shared ? 1u : 0u);      // words [fs, fe1) belong to this tile alone
+    const uint32_t vs = (fs + 3u) >> 2, ve = fe1 >> 2;                                              // vectors [vs, ve)
+    uint32_t* g = stream_words + base;
+    const uint4* sv = reinterpret_cast<const uint4*>(stg);
+    uint4* gv = reinterpret_cast<uint4*>(g);
+    for (uint32_t j = vs + tid; j < ve; j += blockDim.x)
+    {
+        uint4 v = sv[j];
+        v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
+        gv[j] = v;
+    }
+    // leftovers: [ws, min(4 vs, we + 1)) and [max(4 ve, 4 vs), we]; at most 3 + 3 + 2 words
+    const uint32_t lo_end = ve > vs ? 4u * vs : we + 1u, hi_begin = ve > vs ? 4u * ve : we + 1u;
+    const uint32_t nlo = lo_end > ws ? lo_end - ws : 0u, nhi = we + 1u > hi_begin ? we + 1u - hi_begin : 0u;
+    if (tid < nlo + nhi)
+    {
+        const uint32_t j = tid < nlo ? ws + tid : hi_begin + (tid - nlo);
+        const uint32_t v = bswap32(stg[j]);
+        if ((j == ws && head_shared) || (j == we && tail_shared)) atomicOr(g + j, v);
+        else g[j] = v;
+    }
+}
+// bit offset of a global stream position inside the tile's staging buffer
+__device__ __forceinline__ uint32_t staging_bit(uint64_t off, uint64_t tile_b0) { return (uint32_t)(off - (((tile_b0 >> 5) & ~3ull) << 5)); }
+
+// ---- shared-memory plan, computed on the host from the batch statistics --------------------------------------
+constexpr uint32_t kPlaceRoles = 4;          // quality first half, quality second half, DNA, title + meta
+
+struct PlacePlan
+{
+    uint32_t T;              // records per tile
+    uint32_t threads;        // kPlaceRoles * T
+    uint32_t slot_stride;    // words per slot in shared memory (odd number of 16-byte units: conflict-free 16-byte reads)
+    uint32_t off_plan, off_slots, off_staging[4], staging_bytes, total_bytes;
+};
+inline uint32_t staging_words(uint32_t T, uint32_t bits_per_record) { return ((T * bits_per_record + 31u) / 32u + 6u + 3u) & ~3u; }
+
+struct RecPlan
+{
+    uint32_t rec;            // record index (slot)
+    uint32_t loc[4];         // bit offset of the record inside the tile's staging buffers (meta, dna, qua, head)
+    uint32_t nbits[4];
+    uint32_t meta_val;
+    uint32_t bin_header;     // 0, or 0x80000000 | the bin's 17 header bits when the record opens its bin
+    uint32_t need[2];        // which 16-byte pieces of the slot hold bits of this record (bit p of the 64-bit mask)
+};
+
+inline PlacePlan make_place_plan(const DeviceParams& P, const SlotGeom& G, uint32_t max_len, uint32_t max_head)
+{
+    PlacePlan pl{};
+    const uint32_t mates = P.paired ? 2u : 1u;
+    pl.slot_stride = G.words + 4u;
+    for (pl.T = 64; ; pl.T >>= 1)
+    {
+        pl.threads = kPlaceRoles * pl.T;
+        uint32_t o = 0;
+        pl.off_plan = o; o += pl.T * (uint32_t)sizeof(RecPlan);
+        o = (o + 15u) & ~15u;
+        pl.off_slots = o; o += pl.T * pl.slot_stride * 4u + 16u;                       // + slack: shift_copy reads whole groups of four words
+        pl.off_staging[0] = o; o += staging_words(pl.T, 28u + 17u) * 4u;
+        pl.off_staging[1] = o; o += staging_words(pl.T, mates * max_len * 3u + 7u) * 4u;
+        pl.off_staging[2] = o; o += staging_words(pl.T, mates * max_len * P.qua_bits + 7u) * 4u;
+        pl.off_staging[3] = o; o += staging_words(pl.T, P.has_headers ? 8u + 7u * (max_head ? max_head - 1u : 0u) + 7u : 0u) * 4u;
+        pl.staging_bytes = o - pl.off_staging[0];
+        pl.total_bytes = o;
+        if (o <= 100u * 1024u || pl.T == 8) break;
+    }
+    return pl;
+}
+
+// ---- tile-boundary words ---------------------------------------------------------------------------------------
+// write_out merges the first / last word of a tile with atomicOr when it is shared with the
+// neighbouring tile; those words -- and only those -- must be zero beforehand (this replaces a
+// memset of the whole output).  blockIdx.y = stream.
+__global__ void __launch_bounds__(256) zero_boundary_words_kernel(PlaceArgs a, uint32_t T)
+{
+    const int s = blockIdx.y;
+    const uint64_t n = a.B.n_records;
+    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i0 = tile * T;
+    if (i0 >= n) return;
+    unsigned long long b0, b1;
+    tile_range(a, s, i0, T, b0, b1);
+    if (b0 & 31u) a.O.w[s][b0 >> 5] = 0;
+    if (i0 + T >= n && (b1 & 31u)) a.O.w[s][b1 >> 5] = 0;
+}
+
+// ---- K4 --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) place_kernel(PlaceArgs a, PlacePlan pl)
+{
+    extern __shared__ uint4 place_smem[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(place_smem);
+    __shared__ unsigned long long tb0[4], tb1[4];
+    const DeviceParams& P = a.P;
+    const SlotGeom& G = a.G;
+    const uint32_t T = pl.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint64_t i0 = (uint64_t)blockIdx.x * T, n = a.B.n_records;
+    const uint32_t ntile = (uint32_t)min((uint64_t)T, n - i0);
+    RecPlan* plan = reinterpret_cast<RecPlan*>(smem + pl.off_plan);
+    uint32_t* slot_buf = reinterpret_cast<uint32_t*>(smem + pl.off_slots);
+    uint32_t* stg[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) stg[s] = reinterpret_cast<uint32_t*>(smem + pl.off_staging[s]);
+
+    // ---- 1. look the tile's records up: thread (s, t) works out where record t goes in stream s ------------------
+    const uint32_t role = tid / T, t = tid - role * T;
+    uint64_t off = 0;
+    RecPlan rp{};
+    const bool live = t < ntile;
+    if (live)
+    {
+        const int s = (int)role;
+        const uint64_t i = i0 + t;
+        const uint32_t key = a.S.skeys[i];
+        const uint64_t card = a.S.cards[i];
+        const bool nbin = (key & ((1u << P.key_bits) - 1u)) == P.nbin;
+        const uint32_t bin = a.A.bin_of[i];
+        const uint64_t start = a.A.bin_start[bin];
+        const uint32_t bmin = a.A.bin_min[bin], bmax = a.A.bin_max[bin];
+        const uint32_t info = card_info(card), lenA = card_lenA(card), lenB = card_lenB(card), H = card_head(card);
+        const bool has = !(s == 3 && !P.has_headers);
+        off = has ? stream_offset(a, s, i, bin, start) : 0ull;
+        if (t == 0)
+        {   // the tile's bit range in this stream (the first record's bin header belongs to the tile when it opens the bin)
+            tb0[s] = !has ? 0ull : ((i == start) ? 8ull * a.BO.B[s][bin] : off);
+            unsigned long long e = 0;
+            if (has)
+            {
+                const uint64_t in = i0 + T;
+                if (in < n)
+                {
+                    const uint32_t bin2 = a.A.bin_of[in];
+                    const uint64_t start2 = a.A.bin_start[bin2];
+                    e = (in == start2) ? 8ull * a.BO.B[s][bin2] : stream_offset(a, s, in, bin2, start2);
+                }
+                else e = 8ull * a.BO.B[s][*a.nb_ptr];
+            }
+            tb1[s] = e;
+        }
+        if (s == 0)
+        {
+            const ReadBits rb = read_bit_lengths(P, nbin, info, lenA, lenB, H, bmin, bmax);
+            rp.rec = card_rec(card);
+            rp.nbits[0] = rb.meta; rp.nbits[1] = rb.dna; rp.nbits[2] = rb.qua; rp.nbits[3] = rb.head;
+            uint32_t mbits;
+            rp.meta_val = meta_fields(P, nbin, info, lenA, lenB, bmin, bmax, mbits);
+            rp.bin_header = (i == start) ? (0x80000000u | ((bmin & 0xFFu) << 9) | ((bmax & 0xFFu) << 1)) : 0u;   // PackToBin (FastqPacker.cpp:581-583)
+            // used pieces: [0, uq) of the quality region, [qp, qp + uh) of the title region, [qp + hp, .. + ud) of the DNA region
+            const uint32_t uq = (rb.qua + 127u) >> 7, uh = (rb.head + 127u) >> 7, ud = (rb.dna + 127u) >> 7;
+            const uint32_t qp = G.qw >> 2, hp = G.hw >> 2;
+            const unsigned long long m = (uq >= 64u ? ~0ull : ((1ull << uq) - 1ull)) | (((1ull << uh) - 1ull) << qp) | (((1ull << ud) - 1ull) << (qp + hp));
+            rp.need[0] = (uint32_t)m; rp.need[1] = (uint32_t)(m >> 32);
+        }
+    }
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
+        for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (live)
+    {
+        if (role == 0)
+        {
+            RecPlan& q = plan[t];
+            q.rec = rp.rec; q.meta_val = rp.meta_val; q.bin_header = rp.bin_header; q.need[0] = rp.need[0]; q.need[1] = rp.need[1];
+            q.nbits[0] = rp.nbits[0]; q.nbits[1] = rp.nbits[1]; q.nbits[2] = rp.nbits[2]; q.nbits[3] = rp.nbits[3];
+        }
+        plan[t].loc[role] = staging_bit(off, tb0[role]);
+    }
+    __syncthreads();
+
+    // ---- 2. gather the slots: one warp per record, lane p copies 16-byte piece p (and p + 32) ---------------------------
+    {
+        const uint32_t npieces = G.words >> 2;
+        for (uint32_t r = warp; r < ntile; r += nwarps)
+        {
+            const RecPlan& q = plan[r];
+            const uint4* src = reinterpret_cast<const uint4*>(a.slots) + (uint64_t)q.rec * npieces;
+            uint32_t* dst = slot_buf + (size_t)r * pl.slot_stride;
+            if ((q.need[0] >> lane) & 1u) cp_async16(dst + 4u * lane, src + lane);
+            if (npieces > 32u && ((q.need[1] >> lane) & 1u)) cp_async16(dst + 4u * (lane + 32u), src + lane + 32u);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    // ---- 3. every (record, segment) to its bit phase ---------------------------------------------------------------------
+    {
+        if (live)
+        {
+            const RecPlan& q = plan[t];
+            const uint32_t* slot = slot_buf + (size_t)t * pl.slot_stride;
+            const uint32_t nq = q.nbits[2];
+            const uint32_t half = (((((nq + 31u) >> 5) + 1u) >> 1) + 3u) & ~3u;            // words of the first half, a multiple of 4
+            if (role == 0) shift_copy(slot, min(nq, 32u * half), stg[2], q.loc[2]);
+            else if (role == 1) { if (nq > 32u * half) shift_copy(slot + half, nq - 32u * half, stg[2], q.loc[2] + 32u * half); }
+            else if (role == 2) shift_copy(slot + G.qw + G.hw, q.nbits[1], stg[1], q.loc[1]);
+            else
+            {
+                if (q.bin_header) or_bits(stg[0], q.loc[0] - 17u, q.bin_header & 0x1FFFFu, 17);
+                or_bits(stg[0], q.loc[0], q.meta_val, q.nbits[0]);
+                if (P.has_headers) shift_copy(slot + G.qw, q.nbits[3], stg[3], q.loc[3]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. out ------------------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < 4; ++s) write_out(stg[s], a.O.w[s], tb0[s], tb1[s]);
+}
+
+} // namespace fsb

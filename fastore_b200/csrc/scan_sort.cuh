@@ -251,10 +251,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* _
     counts[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
 }
 
-// offsets: exclusive scan of counts (same layout).  vals_in == nullptr means "identity" (first pass).
-__global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+// offsets: exclusive scan of counts (same layout).  The 64-bit values are the records' cards (core.cuh).
+__global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __restrict__ keys_in, const unsigned long long* __restrict__ vals_in,
                                                               uint64_t n, int shift, const uint32_t* __restrict__ offsets, uint32_t nblocks,
-                                                              uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
+                                                              uint32_t* __restrict__ keys_out, unsigned long long* __restrict__ vals_out)
 {
     __shared__ uint32_t warp_hist[kSortThreads / 32][kRadix];   // 8 KB
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
             const uint32_t d = (key[i] >> shift) & 0xFFu;
             const uint32_t dst = warp_hist[warp][d] + rank[i];
             keys_out[dst] = key[i];
-            vals_out[dst] = vals_in ? vals_in[idx] : (uint32_t)idx;
+            vals_out[dst] = vals_in[idx];
         }
     }
 }

@@ -82,8 +82,9 @@ extern "C" int emul_signatures(const fsb_params* p, const fsb_chunk* ch, uint32_
 }
 
 // ================================================================================================
-// pack: host-side layout (plain loops restating layout.cuh) + the per-thread packers of
-// pack_core.cuh, one stored mate after the other, into flat word buffers.
+// pack: host-side layout (plain loops restating layout.cuh) + the per-thread routines of
+// pack_core.cuh in the order the kernels use them: K1 codes every stored mate into the record's
+// slot, K4 shifts the slot's segments to their final bit positions in flat word buffers.
 #include <algorithm>
 #include <numeric>
 
@@ -110,18 +111,20 @@ struct Slot
     }
 };
 
+// What K1 (ingest.cuh) does for one stored mate: code its DNA and quality bits into the record's slot.
 template <int NW>
-void pack_mate(const DeviceParams& P, const Slot& seq, const Slot& qua, uint32_t len, bool rev, bool plain, uint32_t cut_pos, uint32_t cut_len,
-               uint32_t* dna_words, uint32_t dna_off, uint32_t* qua_words, uint32_t qua_off)
+void prepack_mate(const DeviceParams& P, const SlotGeom& G, const Slot& seq, const Slot& qua, uint32_t len, bool rev, bool plain, uint32_t cut_pos, uint32_t cut_len,
+                  uint32_t* slot, uint32_t dna_off, uint32_t qua_off)
 {
-    if (plain) pack_dna<NW, 2>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, dna_words, dna_off);
-    else pack_dna<NW, 3>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, dna_words, dna_off);
+    const uint32_t dbase = 32u * (G.qw + G.hw);
+    if (plain) pack_dna<NW, 2>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, slot, dbase + dna_off);
+    else pack_dna<NW, 3>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, slot, dbase + dna_off);
     const SymReader rq = reader_open(qua.w.data(), qua.addr, len, rev);
     switch (P.qua_bits)
     {
-    case 6: pack_quality<NW, 6>(rq, len, P, qua_words, qua_off); break;
-    case 3: pack_quality<NW, 3>(rq, len, P, qua_words, qua_off); break;
-    default: pack_quality<NW, 1>(rq, len, P, qua_words, qua_off); break;
+    case 6: pack_quality<NW, 6>(rq, len, P, slot, qua_off); break;
+    case 3: pack_quality<NW, 3>(rq, len, P, slot, qua_off); break;
+    default: pack_quality<NW, 1>(rq, len, P, slot, qua_off); break;
     }
 }
 
@@ -167,6 +170,10 @@ int run_pack(const DeviceParams& P, const fsb_chunk* ch, const uint32_t* sig, co
     std::vector<uint32_t> words[4];
     for (int s = 0; s < 4; ++s) { words[s].assign(pos[s] / 32 + 4, 0u); out_size[s] = pos[s] / 8; }
 
+    uint32_t maxH = 0;
+    for (uint64_t i = 0; i < n; ++i) maxH = std::max<uint32_t>(maxH, ch->records[0][i].head_len);
+    const SlotGeom G = make_slot_geom(P, 32 * NW < 255 ? 32 * NW : 255, P.has_headers ? maxH : 0);
+    std::vector<uint32_t> slot(G.words + 8);
     Slot seqA, quaA, seqB, quaB, head;
     for (uint64_t b = 0; b < nb; ++b)
     {
@@ -182,31 +189,43 @@ int run_pack(const DeviceParams& P, const fsb_chunk* ch, const uint32_t* sig, co
             quaA.fill(ch->text[ma], ch->text_size[ma], ra.qua_off, ra.seq_len);
             const uint32_t sfx = nbin ? 0u : P.k, mpos = inf & FSB_INFO_POS_MASK;
             const bool plainA = (inf & FSB_INFO_PLAIN_A) != 0, plainB = (inf & FSB_INFO_PLAIN_B) != 0;
-            if (i == bin_start[b])
-            {   // PackToBin header (FastqPacker.cpp:581-583): minLen, maxLen, hasReadGroups = 0
-                or_bits(words[0].data(), (uint32_t)(off[0][i] - 17), ((bmin[b] & 0xFFu) << 9) | ((bmax[b] & 0xFFu) << 1), 17);
-            }
+            // ---- K1: the record's slot ----
+            std::fill(slot.begin(), slot.end(), 0u);
             uint32_t lenB = 0;
-            pack_mate<NW>(P, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, words[1].data(), (uint32_t)off[1][i], words[2].data(), (uint32_t)off[2][i]);
+            prepack_mate<NW>(P, G, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, slot.data(), 0, 0);
             if (pe)
             {
                 const fsb_record& rbm = ch->records[mb][r];
                 lenB = rbm.seq_len;
                 seqB.fill(ch->text[mb], ch->text_size[mb], rbm.seq_off, rbm.seq_len);
                 quaB.fill(ch->text[mb], ch->text_size[mb], rbm.qua_off, rbm.seq_len);
-                const uint32_t dna_off = (uint32_t)off[1][i] + (ra.seq_len - sfx) * (plainA ? 2u : 3u);
-                const uint32_t qua_off = (uint32_t)off[2][i] + ra.seq_len * P.qua_bits;
-                pack_mate<NW>(P, seqB, quaB, rbm.seq_len, rev, plainB, 0, 0, words[1].data(), dna_off, words[2].data(), qua_off);
+                prepack_mate<NW>(P, G, seqB, quaB, rbm.seq_len, rev, plainB, 0, 0, slot.data(), (ra.seq_len - sfx) * (plainA ? 2u : 3u), ra.seq_len * P.qua_bits);
+            }
+            const fsb_record& r1 = ch->records[0][r];
+            const uint32_t H = P.has_headers ? r1.head_len : 0u;
+            if (P.has_headers)
+            {
+                head.fill(ch->text[0], ch->text_size[0], r1.head_off, r1.head_len);
+                pack_head(head.w.data(), head.addr, r1.head_len, slot.data(), 32u * G.qw);
+            }
+            // the card must survive the trip through the sort
+            const uint64_t card = card_make(r, inf, ra.seq_len, lenB, H);
+            if (card_rec(card) != r || card_info(card) != inf || card_lenA(card) != ra.seq_len || card_lenB(card) != lenB || card_head(card) != H) return FSB_ERR_STATE;
+            // ---- K4: place the slot's segments ----
+            const ReadBits rb = read_bit_lengths(P, nbin, inf, ra.seq_len, lenB, H, bmin[b], bmax[b]);
+            if (i == bin_start[b])
+            {   // PackToBin header (FastqPacker.cpp:581-583): minLen, maxLen, hasReadGroups = 0
+                or_bits(words[0].data(), (uint32_t)(off[0][i] - 17), ((bmin[b] & 0xFFu) << 9) | ((bmax[b] & 0xFFu) << 1), 17);
             }
             uint32_t mbits;
             const uint32_t mv = meta_fields(P, nbin, inf, ra.seq_len, lenB, bmin[b], bmax[b], mbits);
+            if (mbits != rb.meta) return FSB_ERR_STATE;
             or_bits(words[0].data(), (uint32_t)off[0][i], mv, mbits);
-            if (P.has_headers)
-            {
-                const fsb_record& r1 = ch->records[0][r];
-                head.fill(ch->text[0], ch->text_size[0], r1.head_off, r1.head_len);
-                pack_head(head.w.data(), head.addr, r1.head_len, words[3].data(), (uint32_t)off[3][i]);
-            }
+            const uint32_t nq = rb.qua, half = (((((nq + 31u) >> 5) + 1u) >> 1) + 3u) & ~3u;
+            shift_copy(slot.data(), std::min(nq, 32u * half), words[2].data(), (uint32_t)off[2][i]);
+            if (nq > 32u * half) shift_copy(slot.data() + half, nq - 32u * half, words[2].data(), (uint32_t)off[2][i] + 32u * half);
+            shift_copy(slot.data() + G.qw + G.hw, rb.dna, words[1].data(), (uint32_t)off[1][i]);
+            if (P.has_headers) shift_copy(slot.data() + G.qw, rb.head, words[3].data(), (uint32_t)off[3][i]);
         }
     }
     for (int s = 0; s < 4; ++s)
