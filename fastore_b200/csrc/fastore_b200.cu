@@ -145,17 +145,25 @@ BatchView batch_view(const fsb_ctx* c)
     return B;
 }
 
+template <int NW, int Q>
+cudaError_t launch_ingest_q(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t* keys, unsigned long long* cards,
+                            uint32_t* slots, uint32_t* sig, uint32_t* info, cudaStream_t st)
+{
+    const IngestPlan pl = make_ingest_plan<NW>(P, G, max_head);
+    cudaError_t e = cudaFuncSetAttribute(ingest_kernel<NW, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
+    if (e != cudaSuccess) return e;
+    const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
+    const unsigned blocks = (unsigned)((n_mates + pl.warps * 32 - 1) / (pl.warps * 32));
+    ingest_kernel<NW, Q><<<blocks, pl.warps * 32, pl.total_bytes, st>>>(B, P, G, pl, keys, cards, slots, sig, info);
+    return cudaGetLastError();
+}
 template <int NW>
 cudaError_t launch_ingest(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t* keys, unsigned long long* cards,
                           uint32_t* slots, uint32_t* sig, uint32_t* info, cudaStream_t st)
 {
-    const IngestPlan pl = make_ingest_plan<NW>(P, G, max_head);
-    cudaError_t e = cudaFuncSetAttribute(ingest_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
-    if (e != cudaSuccess) return e;
-    const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
-    const unsigned blocks = (unsigned)((n_mates + pl.warps * 32 - 1) / (pl.warps * 32));
-    ingest_kernel<NW><<<blocks, pl.warps * 32, pl.total_bytes, st>>>(B, P, G, pl, keys, cards, slots, sig, info);
-    return cudaGetLastError();
+    if (P.qua_bits == 6) return launch_ingest_q<NW, 6>(B, P, G, max_head, keys, cards, slots, sig, info, st);
+    if (P.qua_bits == 3) return launch_ingest_q<NW, 3>(B, P, G, max_head, keys, cards, slots, sig, info, st);
+    return launch_ingest_q<NW, 1>(B, P, G, max_head, keys, cards, slots, sig, info, st);
 }
 
 cudaError_t launch_place(const PlaceArgs& pa, uint32_t max_len, uint32_t max_head, cudaStream_t st, int* launches)

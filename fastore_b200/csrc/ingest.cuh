@@ -89,7 +89,8 @@ __device__ __forceinline__ void gather_windows(uint8_t* warp_slots, uint32_t pie
 // K1.  NW = ceil(longest read of the batch / 32).
 //   keys[i]  = chunk : signature            cards[i] = card_make(...)  (core.cuh)
 //   slots    = [n_records][G.words] words   sig_out / info_out: optional per-read output (parity tests)
-template <int NW>
+// Q = quality bits per symbol (6, 3 or 1).
+template <int NW, int Q>
 __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P, SlotGeom G, IngestPlan pl, uint32_t* __restrict__ keys,
                                                       unsigned long long* __restrict__ cards, uint32_t* __restrict__ slots,
                                                       uint32_t* __restrict__ sig_out, uint32_t* __restrict__ info_out)
@@ -145,19 +146,24 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
         }
     }
     cp_async_commit();
-    {
-        uint4* z = reinterpret_cast<uint4*>(stg);
-        for (uint32_t j = lane; j < recs_per_warp * G.words / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
-    }
     cp_async_wait_all();
     __syncwarp();
 
+    // ---- bit planes of the sequence; from here on the windows belong to the qualities -------------------------
+    const uint32_t* win_words = reinterpret_cast<const uint32_t*>(wslots + (size_t)lane * SB);
+    BV<NW> Hp, Lp, Np;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { Hp.w[j] = 0; Lp.w[j] = 0; Np.w[j] = 0; }
+    if (live) mate_planes<NW>(win_words + 4 + (a_seq >> 2), 8u * (a_seq & 3u), L, Hp, Lp, Np);
+    __syncwarp();                                                 // every lane is done with its sequence window
+    gather_windows<NW>(wslots, qua_p0, qua_np, B.text[0], B.text[1], P.paired != 0);
+    cp_async_commit();
+
     // ---- signature -------------------------------------------------------------------------------------------
-    const uint32_t* seq_words = reinterpret_cast<const uint32_t*>(wslots + (size_t)lane * SB);
     StrandMin f, r;
     uint32_t nN = 0;
     f.sig = r.sig = P.nbin; f.pos = r.pos = 0;
-    if (live) mate_minimizers<NW>(seq_words + 4 + (a_seq >> 2), 8u * (a_seq & 3u), L, P, f, r, nN);
+    if (live) plane_minimizers<NW>(Hp, Lp, Np, L, P, f, r, nN);
     uint32_t sig, inf;
     if (!P.paired) select_se(f, r, nN, P, sig, inf);
     else
@@ -183,24 +189,24 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
     const uint32_t sfx = nbin ? 0u : P.k;
     uint32_t* my_slot = stg + (size_t)lrec * G.words;
 
-    // ---- DNA of this mate in the stored orientation (StoreDna) ---------------------------------------------------
+    // ---- DNA of this mate in the stored orientation (StoreDna), straight from the planes ----------------------------
+    SegEmit ed = seg_open(my_slot, 0, 0), eh = ed, eq = ed;
     if (live)
     {
         const uint32_t cut_len = roleB ? 0u : sfx, cut_pos = (roleB || nbin) ? 0u : (inf & FSB_INFO_POS_MASK);
         const uint32_t off = 32u * (G.qw + G.hw) + (roleB ? (lenA - sfx) * (plainA ? 2u : 3u) : 0u);
-        const SymReader rs = reader_open(seq_words, 16u + a_seq, L, rev);
-        if (nN == 0) pack_dna<NW, 2>(rs, L, rev, cut_pos, cut_len, my_slot, off);
-        else pack_dna<NW, 3>(rs, L, rev, cut_pos, cut_len, my_slot, off);
+        ed = seg_open(my_slot, off, (L - cut_len) * (nN == 0 ? 2u : 3u));
+        pack_dna_planes<NW>(Hp, Lp, Np, L, rev, nN == 0, cut_pos, cut_len, ed);
     }
-    __syncwarp();                                                 // every lane is done with its sequence window
-
-    // ---- the qualities take over the windows; title, key and card are done while they arrive --------------------
-    gather_windows<NW>(wslots, qua_p0, qua_np, B.text[0], B.text[1], P.paired != 0);
-    cp_async_commit();
+    // ---- title, key and card --------------------------------------------------------------------------------------
     if (live && m == 0)
     {
         if (P.has_headers)
-            pack_head(reinterpret_cast<const uint32_t*>(hslots + (size_t)lrec * pl.head_pieces * 16u), 16u + a_head, H, my_slot, 32u * G.qw);
+        {
+            eh = seg_open(my_slot, 32u * G.qw, 8u + 7u * (H ? H - 1u : 0u));
+            pack_head(reinterpret_cast<const uint32_t*>(hslots + (size_t)lrec * pl.head_pieces * 16u), 16u + a_head, H, eh);
+            seg_finish(eh, false);
+        }
         keys[i] = (ch << P.key_bits) | sig;
         cards[i] = card_make((uint32_t)i, inf, lenA, lenB, H);
         if (sig_out) { sig_out[i] = sig; info_out[i] = inf; }
@@ -211,12 +217,13 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
     // ---- quality of this mate in the stored orientation (StoreQuality) --------------------------------------------
     if (live)
     {
-        const SymReader rq = reader_open(seq_words, 16u + a_qua, L, rev);
-        const uint32_t off = roleB ? lenA * P.qua_bits : 0u;
-        if (P.qua_bits == 6) pack_quality<NW, 6>(rq, L, P, my_slot, off);
-        else if (P.qua_bits == 3) pack_quality<NW, 3>(rq, L, P, my_slot, off);
-        else pack_quality<NW, 1>(rq, L, P, my_slot, off);
+        eq = seg_open(my_slot, roleB ? lenA * Q : 0u, L * Q);
+        pack_quality<Q>(reader_open(win_words, 16u + a_qua, L, rev), L, P, eq);
     }
+    // word 0 of every segment: the mates A first, then the mates B merge into what A has stored
+    if (live && !roleB) { seg_finish(ed, false); seg_finish(eq, false); }
+    __syncwarp();
+    if (live && roleB) { seg_finish(ed, true); seg_finish(eq, true); }
     __syncwarp();
 
     // ---- the warp's slots leave as one contiguous block -------------------------------------------------------------

@@ -4,10 +4,11 @@
 // BitMemoryWriter they append to (FastqPacker.cpp:113-287; BitMemory.h:216-433).  The reference
 // pushes symbol after symbol into a sequential MSB-first bit writer.  Here the bit offset of every
 // record in every stream is known beforehand (layout.cuh), so one thread packs one stored mate
-// independently: it turns four ASCII symbols at a time into 8 / 12 / 24 output bits with word-wide
-// arithmetic, assembles 32-bit stream words, shifts them to the record's bit phase and stores them
-// into the tile's staging buffer.  Only the first and last word of a segment, which are shared
-// with the neighbouring records, are merged with OR; everything in between is a plain store.
+// independently: K1 turns four quality symbols at a time into 4 / 12 / 24 output bits with word-wide
+// arithmetic and derives the DNA stream from the bit planes of the signature search, streaming
+// 32-bit words into the record's slot; K4 shifts whole segments to the record's bit phase.  Only
+// the first and last word of a segment, which are shared with the neighbouring segments, need a
+// merge; everything in between is a plain store.
 //
 // FSB_HD code: also compiled for the host by tests/emul/ (CPU-tier check against the oracle).
 #pragma once
@@ -37,57 +38,49 @@ FSB_HD void or_word(uint32_t* p, uint32_t v)
 #endif
 }
 
-// ---- output: one thread's bit segment inside a word buffer --------------------------------------------
-// The segment is `nbits` bits starting at bit `off` of `words` (bit 0 = most significant bit of
-// word 0; words are kept in big-endian *bit* order and byte-swapped when they leave for memory).
-// The producer pushes its stream as consecutive 32-bit words; the sink shifts them by the phase.
-struct BitSink
+// ---- K1 output: one thread streams one segment into its record's slot ------------------------------------
+// The segment is `nbits` bits at bit offset `off` of `words` (bit 0 = most significant bit of word
+// 0; words are kept in big-endian *bit* order and byte-swapped when they leave for memory).  The
+// producer pushes its stream as consecutive 32-bit words; every output word but the first is a
+// plain store.  Word 0 may be shared with the segment in front of it (mate B follows mate A at a
+// bit boundary), so it is held back and written by seg_finish, which the caller runs for the mates
+// A first and -- after a __syncwarp -- for the mates B, merging into what A has stored.  No
+// zero-initialisation and no atomics are needed; bits past the end of a segment are unspecified
+// (K4 masks them).
+struct SegEmit
 {
-    uint32_t* words;
+    uint32_t* w;         // word holding the segment's first bit
+    uint32_t phi;        // bit phase of the segment in that word
+    uint32_t last;       // index of the last word with bits of the segment
     uint32_t idx;        // next output word
-    uint32_t last;       // last output word of the segment
-    uint32_t phi;        // off & 31
     uint32_t prev;       // previous stream word
-    uint32_t nx;         // stream words still to come
-    uint32_t lastmask;   // valid bits of the final stream word
-    bool head_shared, tail_shared;
+    uint32_t v0;         // output word 0
+    bool any;            // the segment is not empty
 };
-
-FSB_HD BitSink sink_open(uint32_t* words, uint32_t off, uint32_t nbits)
+FSB_HD SegEmit seg_open(uint32_t* words, uint32_t off, uint32_t nbits)
 {
-    BitSink s;
-    s.words = words;
-    s.idx = off >> 5;
-    s.phi = off & 31u;
-    s.prev = 0;
-    s.nx = (nbits + 31u) >> 5;
-    const uint32_t tail = nbits & 31u;
-    s.lastmask = tail ? ~(0xFFFFFFFFu >> tail) : 0xFFFFFFFFu;
-    const uint32_t end = off + nbits;                       // nbits > 0
-    s.last = (end - 1u) >> 5;
-    s.head_shared = s.phi != 0;
-    s.tail_shared = (end & 31u) != 0;
-    return s;
+    SegEmit e;
+    e.w = words + (off >> 5);
+    e.phi = off & 31u;
+    e.any = nbits != 0;
+    e.last = e.any ? (e.phi + nbits - 1u) >> 5 : 0u;
+    e.idx = 0; e.prev = 0; e.v0 = 0;
+    return e;
 }
-FSB_HD void sink_emit(BitSink& s, uint32_t v)
+FSB_HD void seg_push(SegEmit& e, uint32_t x)                  // next 32 bits of the stream
 {
-    if (s.idx > s.last) return;
-    uint32_t* p = s.words + s.idx;
-    if ((s.idx == s.last && s.tail_shared) || s.head_shared) or_word(p, v); else *p = v;
-    s.head_shared = false;                                   // only the first emitted word starts mid-word
-    s.idx++;
+    const uint32_t v = funnel_r(x, e.prev, e.phi);           // stream bits [32 idx - phi, 32 idx - phi + 32)
+    e.prev = x;
+    if (e.idx == 0) e.v0 = v;
+    else if (e.idx <= e.last) e.w[e.idx] = v;
+    e.idx++;
 }
-// next 32 bits of the stream (bits past the end of the segment may hold anything in the last word)
-FSB_HD void sink_push(BitSink& s, uint32_t x)
+FSB_HD void seg_close(SegEmit& e) { if (e.idx <= e.last) seg_push(e, 0u); }     // the bits of the last stream word that spilled over
+FSB_HD void seg_finish(const SegEmit& e, bool merge)
 {
-    if (s.nx == 0) return;
-    if (--s.nx == 0) x &= s.lastmask;
-    sink_emit(s, s.phi ? funnel_r(x, s.prev, s.phi) : x);
-    s.prev = x;
-}
-FSB_HD void sink_close(BitSink& s)                            // the bits of the last stream word that spilled over
-{
-    if (s.phi) sink_emit(s, s.prev << (32u - s.phi));
+    if (!e.any) return;
+    if (merge && e.phi) e.w[0] = (e.w[0] & ~(0xFFFFFFFFu >> e.phi)) | e.v0;     // the bits in front belong to mate A
+    else e.w[0] = e.v0;
 }
 
 // small right-aligned values (meta fields): OR `nbits` (1..32) bits of v at bit offset off
@@ -146,15 +139,6 @@ FSB_HD uint32_t reader_next(SymReader& r)
 }
 
 // ---- symbol coding --------------------------------------------------------------------------------------
-// four ASCII bases (first in the top byte) -> their 2-bit codes per byte: A,C,G,T -> 0,1,2,3 (dnaToIdx, FastqPacker.cpp:24-30)
-FSB_HD uint32_t base_codes4(uint32_t b)
-{
-    const uint32_t x = (b >> 1) & 0x03030303u;                   // A 0, C 1, G 3, T 2
-    return x ^ ((x >> 1) & 0x01010101u);
-}
-// one code per byte -> 8 bits, first symbol in the top two bits.  Byte j lands at 24 + 2j; cross
-// terms fall below bit 24 or above bit 31.
-FSB_HD uint32_t gather4x2(uint32_t c) { return (c * 0x01041040u) >> 24; }
 // one 3-bit value per byte -> 12 bits, first symbol on top
 FSB_HD uint32_t gather4x3(uint32_t v)
 {
@@ -192,34 +176,6 @@ FSB_HD uint32_t quality4(uint32_t b, uint32_t off4 /* offset * 0x01010101 */, ui
     v += ((y - 0x23232323u) >> 7) & 0x01010101u;
     v += ((y - 0x28282828u) >> 7) & 0x01010101u;
     return gather4x3(v);
-}
-
-// ---- emission of a whole segment held in registers ------------------------------------------------------------
-// X[0 .. NX) are the segment's stream words (MSB-first; bits past `nbits` may hold anything).  The
-// segment goes to bit offset `off` of `words`: interior words are plain stores, the first and the
-// last word -- shared with the neighbouring segments -- are ORed into the zero-initialised buffer.
-template <int NX>
-FSB_HD void emit_words(const uint32_t (&X)[NX], uint32_t nbits, uint32_t* words, uint32_t off)
-{
-    if (nbits == 0) return;
-    const uint32_t phi = off & 31u;
-    uint32_t* w = words + (off >> 5);
-    const uint32_t end = phi + nbits;
-    const uint32_t last = (end - 1u) >> 5;                       // index of the last output word
-    const uint32_t tailbits = end - 32u * last;                  // 1..32 valid bits in it
-    const uint32_t lastmask = tailbits >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> tailbits);
-    uint32_t prev = 0;
-#pragma unroll
-    for (int j = 0; j <= NX; ++j)
-    {
-        if ((j & 3) == 0 && (uint32_t)j > last) break;
-        const uint32_t x = j < NX ? X[j] : 0u;
-        const uint32_t v = funnel_r(x, prev, phi);              // stream bits [32j - phi, 32j - phi + 32)
-        prev = x;
-        if ((uint32_t)j == last) or_word(w + j, v & lastmask);
-        else if (j == 0) or_word(w, v);
-        else if ((uint32_t)j < last) w[j] = v;
-    }
 }
 
 // ---- K4: move one prepacked segment to its final bit position ------------------------------------------------
@@ -277,120 +233,211 @@ FSB_HD void shift_copy(const uint32_t* src, uint32_t nbits, uint32_t* words, uin
     }
 }
 
-// ---- quality stream of one stored mate --------------------------------------------------------------------
-// 32 symbols -> Q stream words per round.
-template <int NW, int Q>
-FSB_HD void pack_quality(SymReader rd, uint32_t len, const DeviceParams& P, uint32_t* words, uint32_t off)
+// ---- quality stream of one stored mate (StoreQuality, FastqPacker.cpp:205-269) -------------------------------
+// 32 symbols -> Q stream words per round; a rolled loop (the kernel's code has to fit the
+// instruction cache).  Symbols past `len` inside the last round code to unspecified bits.
+template <int Q>
+FSB_HD void pack_quality(SymReader rd, uint32_t len, const DeviceParams& P, SegEmit& e)
 {
-    uint32_t X[NW * Q];
     const uint32_t off4 = P.qua_offset * 0x01010101u, thr4 = P.qua_threshold * 0x01010101u;
+    const uint32_t rounds = (len + 31u) >> 5;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (uint32_t j = 0; j < rounds; ++j)
+    {
+        uint32_t t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = quality4<Q>(reader_next(rd), off4, thr4);
+        if (Q == 6)
+        {   // 24 bits per group of four symbols: whole bytes, so the words are byte permutations
+            seg_push(e, byte_perm(t[1], t[0], 0x6542u));                 // t0[23:0] t1[23:16]
+            seg_push(e, byte_perm(t[2], t[1], 0x5421u));                 // t1[15:0] t2[23:8]
+            seg_push(e, byte_perm(t[3], t[2], 0x4210u));                 // t2[7:0]  t3[23:0]
+            seg_push(e, byte_perm(t[5], t[4], 0x6542u));
+            seg_push(e, byte_perm(t[6], t[5], 0x5421u));
+            seg_push(e, byte_perm(t[7], t[6], 0x4210u));
+        }
+        else if (Q == 3)
+        {
+            seg_push(e, (t[0] << 20) | (t[1] << 8) | (t[2] >> 4));
+            seg_push(e, (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8));
+            seg_push(e, (t[5] << 24) | (t[6] << 12) | t[7]);
+        }
+        else
+            seg_push(e, (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7]);
+    }
+    seg_close(e);
+}
+
+// ---- DNA stream of one stored mate straight from K1's bit planes -----------------------------------------------
+// K1 already holds the read as bit planes (sig_core.cuh: hi, lo, N; position p = bit p&31 of word
+// p>>5).  The stored symbol stream is derived from them without touching the text again:
+//   1. stored orientation, MSB-first planes: forward = bit-reversed words; reverse-complement
+//      (FastqRecord::ComputeRC, FastqRecord.h:80-111) = complemented planes shifted so that base L-1
+//      comes first.  'N' positions are cleared in hi/lo (N codes as 100b, FastqPacker.cpp:24-30);
+//   2. the k signature symbols at [cut_pos, cut_pos + cut_len) are cut out of every plane;
+//   3. hi and lo are interleaved into the 2-bit stream (perfect shuffle); a mate with 'N' expands
+//      that to 3 bits per symbol with the N plane on top.
+template <int NW> struct MsbPlanes { uint32_t h[NW + 1], l[NW + 1], n[NW + 1]; };
+
+template <int NW> FSB_HD BV<NW> bv_shl_any(BV<NW> x, uint32_t s)          // r[p] = x[p - s], any s < 32 NW
+{
+    x = bv_shl(x, s & 31u);
+    const uint32_t ws = s >> 5;
+#pragma unroll
+    for (int st = 1; st < NW; st <<= 1)
+        if (ws & (uint32_t)st)
+        {
+#pragma unroll
+            for (int j = NW - 1; j >= 0; --j) x.w[j] = j >= st ? x.w[j - st] : 0u;
+        }
+    return x;
+}
+FSB_HD uint32_t brev32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    return bswap32(x);
+#endif
+}
+
+template <int NW>
+FSB_HD void stored_planes(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, bool rev, MsbPlanes<NW>& o)
+{
+    if (!rev)
+    {
+#pragma unroll
+        for (int j = 0; j < NW; ++j)
+        {
+            o.h[j] = brev32(H.w[j] & ~Nm.w[j]); o.l[j] = brev32(Lo.w[j] & ~Nm.w[j]); o.n[j] = brev32(Nm.w[j]);
+        }
+    }
+    else
+    {
+        BV<NW> hc, lc;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) { hc.w[j] = ~(H.w[j] | Nm.w[j]); lc.w[j] = ~(Lo.w[j] | Nm.w[j]); }       // 3 - code, 'N' stays clear
+        const uint32_t sh = 32u * NW - L;
+        // only positions below L may survive the shift: the planes hold text past the read there
+        const BV<NW> valid = bv_range<NW>(0, (int32_t)L);
+        const BV<NW> hs = bv_shl_any(bv_and(hc, valid), sh), ls = bv_shl_any(bv_and(lc, valid), sh), ns = bv_shl_any(Nm, sh);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) { o.h[j] = hs.w[NW - 1 - j]; o.l[j] = ls.w[NW - 1 - j]; o.n[j] = ns.w[NW - 1 - j]; }
+    }
+    o.h[NW] = 0; o.l[NW] = 0; o.n[NW] = 0;
+}
+
+// remove cut_len (< 32) stream positions at cut_pos from MSB-first plane words
+template <int NW>
+FSB_HD void cut_planes(MsbPlanes<NW>& o, uint32_t cut_pos, uint32_t cut_len)
+{
 #pragma unroll
     for (int j = 0; j < NW; ++j)
     {
-        if (32u * j < len)
-        {
-            uint32_t t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = quality4<Q>(reader_next(rd), off4, thr4);
-            if (Q == 6)
-            {
-                X[6 * j + 0] = (t[0] << 8) | (t[1] >> 16);
-                X[6 * j + 1] = (t[1] << 16) | (t[2] >> 8);
-                X[6 * j + 2] = (t[2] << 24) | t[3];
-                X[6 * j + 3] = (t[4] << 8) | (t[5] >> 16);
-                X[6 * j + 4] = (t[5] << 16) | (t[6] >> 8);
-                X[6 * j + 5] = (t[6] << 24) | t[7];
-            }
-            else if (Q == 3)
-            {
-                X[3 * j + 0] = (t[0] << 20) | (t[1] << 8) | (t[2] >> 4);
-                X[3 * j + 1] = (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8);
-                X[3 * j + 2] = (t[5] << 24) | (t[6] << 12) | t[7];
-            }
-            else
-                X[j] = (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7];
-        }
-        else
-        {
-#pragma unroll
-            for (int u = 0; u < Q; ++u) X[Q * j + u] = 0;
-        }
+        const int32_t keep = (int32_t)cut_pos - 32 * j;            // leading positions of this word that precede the cut
+        const uint32_t m = keep <= 0 ? 0u : (keep >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> keep));
+        o.h[j] = (o.h[j] & m) | (funnel_l(o.h[j + 1], o.h[j], cut_len) & ~m);
+        o.l[j] = (o.l[j] & m) | (funnel_l(o.l[j + 1], o.l[j], cut_len) & ~m);
+        o.n[j] = (o.n[j] & m) | (funnel_l(o.n[j + 1], o.n[j], cut_len) & ~m);
     }
-    emit_words<NW * Q>(X, len * (uint32_t)Q, words, off);
 }
 
-// ---- DNA stream of one stored mate (StoreDna, FastqPacker.cpp:157-202) ----------------------------------
-// All `len` symbols are coded into stream words first; then the k signature symbols at
-// [cut_pos, cut_pos + cut_len) are cut out (they are implied by the bin) and the rest is emitted.
-// SB = bits per symbol: 2 for a mate without 'N', 3 otherwise (A,C,G,T,N -> 0..4).
-template <int NW, int SB>
-FSB_HD void pack_dna(SymReader rd, uint32_t len, bool rev, uint32_t cut_pos, uint32_t cut_len, uint32_t* words, uint32_t off)
+// [a15 .. a0 | b15 .. b0] -> a15 b15 a14 b14 .. a0 b0
+FSB_HD uint32_t shuffle16(uint32_t x)
 {
-    constexpr int NX = SB * NW;                                  // stream words of 32*NW symbols
-    uint32_t D[NX + 2];
-    const uint32_t comp = rev ? 0x03030303u : 0u;                // rcCodes (FastqRecord.h:62-76): A<->T, C<->G, N stays
+    uint32_t t;
+    t = (x ^ (x >> 8)) & 0x0000FF00u; x = x ^ t ^ (t << 8);
+    t = (x ^ (x >> 4)) & 0x00F000F0u; x = x ^ t ^ (t << 4);
+    t = (x ^ (x >> 2)) & 0x0C0C0C0Cu; x = x ^ t ^ (t << 2);
+    t = (x ^ (x >> 1)) & 0x22222222u; x = x ^ t ^ (t << 1);
+    return x;
+}
+// ten 2-bit fields (field f at bits 2f) -> stride 3 (field f at bits 3f); ten 1-bit fields -> bit 3f
+FSB_HD uint32_t spread_2to3(uint32_t x)
+{
+    uint32_t t;
+    t = x << 8; x = (x & ~0x0F000000u) | (t & 0x0F000000u);
+    t = x << 4; x = (x & ~0x000FF000u) | (t & 0x000FF000u);
+    t = x << 2; x = (x & ~0x003C03C0u) | (t & 0x003C03C0u);
+    t = x << 1; x = (x & ~0x18618618u) | (t & 0x18618618u);
+    return x & 0x1B6DB6DBu;
+}
+FSB_HD uint32_t spread_1to3(uint32_t x)
+{
+    uint32_t t;
+    t = x << 16; x = (x & ~0x03000000u) | (t & 0x03000000u);
+    t = x << 8;  x = (x & ~0x0000F000u) | (t & 0x0000F000u);
+    t = x << 4;  x = (x & ~0x000C00C0u) | (t & 0x000C00C0u);
+    t = x << 2;  x = (x & ~0x08208208u) | (t & 0x08208208u);
+    return x & 0x09249249u;
+}
+
+// 2-bit stream words D[0 .. 2 NW) (+ one zero word) of the planes
+template <int NW>
+FSB_HD void planes_to_2bit(const MsbPlanes<NW>& o, uint32_t (&D)[2 * NW + 1])
+{
 #pragma unroll
-    for (int j = 0; j < NW; ++j)                                  // 32 symbols per round
+    for (int j = 0; j < NW; ++j)
     {
-        if (32u * j < len)
-        {
-            uint32_t t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-            {
-                const uint32_t b = reader_next(rd);
-                const uint32_t c = base_codes4(b) ^ comp;
-                if (SB == 2) t[u] = gather4x2(c);
-                else
-                {
-                    const uint32_t f = (b >> 3) & 0x01010101u;   // 'N'
-                    t[u] = gather4x3((c & ~(f * 3u)) | (f << 2));
-                }
-            }
-            if (SB == 2)
-            {
-                D[2 * j] = (t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
-                D[2 * j + 1] = (t[4] << 24) | (t[5] << 16) | (t[6] << 8) | t[7];
-            }
-            else
-            {
-                D[3 * j] = (t[0] << 20) | (t[1] << 8) | (t[2] >> 4);
-                D[3 * j + 1] = (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8);
-                D[3 * j + 2] = (t[5] << 24) | (t[6] << 12) | t[7];
-            }
-        }
-        else
-        {
-#pragma unroll
-            for (int u = 0; u < SB; ++u) D[SB * j + u] = 0;
-        }
+        D[2 * j] = shuffle16(byte_perm(o.l[j], o.h[j], 0x7632u));          // [h.hi16 | l.hi16]
+        D[2 * j + 1] = shuffle16(byte_perm(o.l[j], o.h[j], 0x5410u));      // [h.lo16 | l.lo16]
     }
-    D[NX] = 0; D[NX + 1] = 0;
-    if (cut_len)
+    D[2 * NW] = 0;
+}
+// 3-bit stream words E[0 .. 3 NW) from the 2-bit stream and the N plane, ten symbols at a time
+template <int NW>
+FSB_HD void expand_to_3bit(const uint32_t (&D)[2 * NW + 1], const MsbPlanes<NW>& o, uint32_t (&E)[3 * NW])
+{
+#pragma unroll
+    for (int j = 0; j < 3 * NW; ++j) E[j] = 0;
+    constexpr int NCH = (32 * NW + 9) / 10;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
     {
-        const uint32_t cb = cut_pos * (uint32_t)SB;              // bit where the cut starts
-        const uint32_t cw = cut_len * (uint32_t)SB;              // bits removed (< 64)
-        const uint32_t q = cw >> 5, r = cw & 31u;
-#pragma unroll
-        for (int j = 0; j < NX; ++j)
-        {
-            const uint32_t shifted = q ? funnel_l(D[j + 2], D[j + 1], r) : funnel_l(D[j + 1], D[j], r);      // stream bits 32j + cw ..
-            const int32_t keep = (int32_t)cb - 32 * j;            // leading bits of this word that precede the cut
-            const uint32_t m = keep <= 0 ? 0u : (keep >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> keep));
-            D[j] = (D[j] & m) | (shifted & ~m);
-        }
+        const int wd = (20 * c) >> 5, sd = (20 * c) & 31, wn = (10 * c) >> 5, sn = (10 * c) & 31;
+        const uint32_t e = funnel_l(wd + 1 <= 2 * NW ? D[wd + 1] : 0u, D[wd], sd) >> 12;                 // symbols 10c .. 10c+9, two bits each
+        const uint32_t n = funnel_l(o.n[wn + 1 <= NW ? wn + 1 : NW], o.n[wn], sn) >> 22;                   // their N flags
+        const uint32_t t30 = spread_2to3(e) | (spread_1to3(n) << 2);                                       // 30 stream bits
+        const int wo = (30 * c) >> 5, so = (30 * c) & 31;                                                   // they start at bit 30c
+        const uint32_t top = t30 << 2;                                                                      // left-aligned
+        if (wo < 3 * NW) E[wo] |= top >> so;
+        if (so > 2 && wo + 1 < 3 * NW) E[wo + 1] |= top << (32 - so);
     }
-    uint32_t E[NX];
+}
+
+// the whole DNA segment of one stored mate
+template <int NW>
+FSB_HD void pack_dna_planes(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, bool rev, bool plain,
+                            uint32_t cut_pos, uint32_t cut_len, SegEmit& e)
+{
+    MsbPlanes<NW> o;
+    stored_planes<NW>(H, Lo, Nm, L, rev, o);
+    if (cut_len) cut_planes<NW>(o, cut_pos, cut_len);
+    uint32_t D[2 * NW + 1];
+    planes_to_2bit<NW>(o, D);
+    if (plain)
+    {
 #pragma unroll
-    for (int j = 0; j < NX; ++j) E[j] = D[j];
-    emit_words<NX>(E, (len - cut_len) * (uint32_t)SB, words, off);
+        for (int j = 0; j < 2 * NW; ++j) seg_push(e, D[j]);
+    }
+    else
+    {
+        uint32_t E[3 * NW];
+        expand_to_3bit<NW>(D, o, E);
+#pragma unroll
+        for (int j = 0; j < 3 * NW; ++j) seg_push(e, E[j]);
+    }
+    seg_close(e);
 }
 
 // ---- title (StoreHeader, FastqPacker.cpp:272-287): 8 bits headLen, then 7 bits per char after '@' ---------
-FSB_HD void pack_head(const uint32_t* w, uint32_t addr, uint32_t H, uint32_t* words, uint32_t off)
+FSB_HD void pack_head(const uint32_t* w, uint32_t addr, uint32_t H, SegEmit& e)
 {
-    const uint32_t nbits = 8u + 7u * (H ? H - 1u : 0u);
-    BitSink s = sink_open(words, off, nbits);
     uint64_t acc = H & 0xFFu;
     uint32_t n = 8;
     const uint8_t* bytes = reinterpret_cast<const uint8_t*>(w) + addr;
@@ -398,10 +445,10 @@ FSB_HD void pack_head(const uint32_t* w, uint32_t addr, uint32_t H, uint32_t* wo
     {
         acc = (acc << 7) | (uint64_t)(bytes[i] & 0x7Fu);
         n += 7;
-        if (n >= 32) { sink_push(s, (uint32_t)(acc >> (n - 32))); n -= 32; }
+        if (n >= 32) { seg_push(e, (uint32_t)(acc >> (n - 32))); n -= 32; }
     }
-    if (n) sink_push(s, (uint32_t)(acc << (32 - n)));
-    sink_close(s);
+    if (n) seg_push(e, (uint32_t)(acc << (32 - n)));
+    seg_close(e);
 }
 
 // ---- per-record framing (StoreRecords SE :734-759 / PE :815-859, StoreNextRecord :113-153) --------------

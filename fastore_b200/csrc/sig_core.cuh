@@ -151,14 +151,12 @@ FSB_HD StrandMin descend_reverse(const BV<NW>& C, const BV<NW>& H, const BV<NW>&
     return r;
 }
 
-// FM(x) and FM(rc(x)) of one mate, plus its N count.  L <= 32 * NW.
+// FM(x) and FM(rc(x)) of one mate from its bit planes (N plane already cut to the read length), plus
+// its N count.  L <= 32 * NW.
 template <int NW>
-FSB_HD void mate_minimizers(const uint32_t* words, uint32_t bshift, uint32_t L, const DeviceParams& P,
-                            StrandMin& fwd, StrandMin& rev, uint32_t& nN)
+FSB_HD void plane_minimizers(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, const DeviceParams& P,
+                             StrandMin& fwd, StrandMin& rev, uint32_t& nN)
 {
-    BV<NW> H, Lo, Nm;
-    ascii_to_planes<NW>(words, bshift, H, Lo, Nm);
-    Nm = bv_and(Nm, bv_range<NW>(0, (int32_t)L));
     nN = bv_popc(Nm);
     BV<NW> Cf, Cr;
     candidate_masks<NW>(H, Lo, Nm, L, P, Cf, Cr);
@@ -170,6 +168,19 @@ FSB_HD void mate_minimizers(const uint32_t* words, uint32_t bshift, uint32_t L, 
         if (bv_any(Cf)) fwd = descend_forward<NW>(Cf, H, Lo, P);
         if (bv_any(Cr)) rev = descend_reverse<NW>(Cr, H, Lo, L, P);
     }
+}
+template <int NW>
+FSB_HD void mate_planes(const uint32_t* words, uint32_t bshift, uint32_t L, BV<NW>& H, BV<NW>& Lo, BV<NW>& Nm)
+{
+    ascii_to_planes<NW>(words, bshift, H, Lo, Nm);
+    Nm = bv_and(Nm, bv_range<NW>(0, (int32_t)L));
+}
+template <int NW>
+FSB_HD void mate_minimizers(const uint32_t* words, uint32_t bshift, uint32_t L, const DeviceParams& P,
+                            StrandMin& fwd, StrandMin& rev, uint32_t& nN, BV<NW>& H, BV<NW>& Lo, BV<NW>& Nm)
+{
+    mate_planes<NW>(words, bshift, L, H, Lo, Nm);
+    plane_minimizers<NW>(H, Lo, Nm, L, P, fwd, rev, nN);
 }
 
 // FastqCategorizerSE::DistributeToBins (FastqCategorizer.cpp:212-245): forward wins ties.

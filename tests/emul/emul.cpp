@@ -36,7 +36,8 @@ void mate_scan(const uint8_t* text, uint64_t text_size, const fsb_record& r, con
     uint32_t slot[(2 * NW + 1) * 4 + 4];
     stage_slot<NW>(text, text_size, r.seq_off, r.seq_len, slot);
     const uint32_t a = r.seq_off & 15u;
-    mate_minimizers<NW>(slot + (a >> 2), 8 * (a & 3u), r.seq_len, P, f, rv, nN);
+    BV<NW> H, Lo, Nm;
+    mate_minimizers<NW>(slot + (a >> 2), 8 * (a & 3u), r.seq_len, P, f, rv, nN, H, Lo, Nm);
 }
 
 template <int NW>
@@ -112,20 +113,25 @@ struct Slot
 };
 
 // What K1 (ingest.cuh) does for one stored mate: code its DNA and quality bits into the record's slot.
+// `merge`: the mate is stored second (B), its segments start where mate A's end.
 template <int NW>
 void prepack_mate(const DeviceParams& P, const SlotGeom& G, const Slot& seq, const Slot& qua, uint32_t len, bool rev, bool plain, uint32_t cut_pos, uint32_t cut_len,
-                  uint32_t* slot, uint32_t dna_off, uint32_t qua_off)
+                  uint32_t* slot, uint32_t dna_off, uint32_t qua_off, bool merge)
 {
-    const uint32_t dbase = 32u * (G.qw + G.hw);
-    if (plain) pack_dna<NW, 2>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, slot, dbase + dna_off);
-    else pack_dna<NW, 3>(reader_open(seq.w.data(), seq.addr, len, rev), len, rev, cut_pos, cut_len, slot, dbase + dna_off);
+    // K1 derives the DNA from the bit planes it built for the signature search
+    BV<NW> H, Lo, Nm;
+    mate_planes<NW>(seq.w.data() + (seq.addr >> 2), 8u * (seq.addr & 3u), len, H, Lo, Nm);
+    SegEmit ed = seg_open(slot, 32u * (G.qw + G.hw) + dna_off, (len - cut_len) * (plain ? 2u : 3u));
+    pack_dna_planes<NW>(H, Lo, Nm, len, rev, plain, cut_pos, cut_len, ed);
+    SegEmit eq = seg_open(slot, qua_off, len * P.qua_bits);
     const SymReader rq = reader_open(qua.w.data(), qua.addr, len, rev);
     switch (P.qua_bits)
     {
-    case 6: pack_quality<NW, 6>(rq, len, P, slot, qua_off); break;
-    case 3: pack_quality<NW, 3>(rq, len, P, slot, qua_off); break;
-    default: pack_quality<NW, 1>(rq, len, P, slot, qua_off); break;
+    case 6: pack_quality<6>(rq, len, P, eq); break;
+    case 3: pack_quality<3>(rq, len, P, eq); break;
+    default: pack_quality<1>(rq, len, P, eq); break;
     }
+    seg_finish(ed, merge); seg_finish(eq, merge);
 }
 
 template <int NW>
@@ -190,23 +196,25 @@ int run_pack(const DeviceParams& P, const fsb_chunk* ch, const uint32_t* sig, co
             const uint32_t sfx = nbin ? 0u : P.k, mpos = inf & FSB_INFO_POS_MASK;
             const bool plainA = (inf & FSB_INFO_PLAIN_A) != 0, plainB = (inf & FSB_INFO_PLAIN_B) != 0;
             // ---- K1: the record's slot ----
-            std::fill(slot.begin(), slot.end(), 0u);
+            std::fill(slot.begin(), slot.end(), 0xDEADBEEFu);      // the slot staging is never cleared
             uint32_t lenB = 0;
-            prepack_mate<NW>(P, G, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, slot.data(), 0, 0);
+            prepack_mate<NW>(P, G, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, slot.data(), 0, 0, false);
             if (pe)
             {
                 const fsb_record& rbm = ch->records[mb][r];
                 lenB = rbm.seq_len;
                 seqB.fill(ch->text[mb], ch->text_size[mb], rbm.seq_off, rbm.seq_len);
                 quaB.fill(ch->text[mb], ch->text_size[mb], rbm.qua_off, rbm.seq_len);
-                prepack_mate<NW>(P, G, seqB, quaB, rbm.seq_len, rev, plainB, 0, 0, slot.data(), (ra.seq_len - sfx) * (plainA ? 2u : 3u), ra.seq_len * P.qua_bits);
+                prepack_mate<NW>(P, G, seqB, quaB, rbm.seq_len, rev, plainB, 0, 0, slot.data(), (ra.seq_len - sfx) * (plainA ? 2u : 3u), ra.seq_len * P.qua_bits, true);
             }
             const fsb_record& r1 = ch->records[0][r];
             const uint32_t H = P.has_headers ? r1.head_len : 0u;
             if (P.has_headers)
             {
                 head.fill(ch->text[0], ch->text_size[0], r1.head_off, r1.head_len);
-                pack_head(head.w.data(), head.addr, r1.head_len, slot.data(), 32u * G.qw);
+                SegEmit eh = seg_open(slot.data(), 32u * G.qw, 8u + 7u * (r1.head_len ? r1.head_len - 1u : 0u));
+                pack_head(head.w.data(), head.addr, r1.head_len, eh);
+                seg_finish(eh, false);
             }
             // the card must survive the trip through the sort
             const uint64_t card = card_make(r, inf, ra.seq_len, lenB, H);
