@@ -36,7 +36,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int NW> constexpr uint32_t win_pieces() { return 2 * NW + 1; }      // 16-byte pieces of the aligned window around L <= 32 NW bytes
-template <int NW> constexpr uint32_t win_slot_bytes() { return (win_pieces<NW>() + 1) * 16; }   // + one guard piece in front
+// + one guard piece in front; an odd number of pieces per window keeps the lanes' windows on different banks
+template <int NW> constexpr uint32_t win_slot_bytes() { return ((win_pieces<NW>() + 1) | 1u) * 16; }
 
 struct IngestPlan
 {

@@ -104,6 +104,22 @@ FSB_HD void candidate_masks(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm,
 }
 
 // Radix descent, forward strand.  D tracks the candidates shifted onto the symbol under test.
+// One bit step of the descent: keep the candidates whose key bit is 0 if there are any.  `plane`
+// holds the key bit (inv = false) or its complement (inv = true) at the candidates' positions.
+// Written so that a step is NW and-nots, an OR tree, one compare and NW three-input logic ops.
+template <int NW>
+FSB_HD uint32_t descend_step(BV<NW>& D, const BV<NW>& plane, bool inv)
+{
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) o |= D.w[j] & (inv ? plane.w[j] : ~plane.w[j]);
+    const uint32_t am = o ? 0xFFFFFFFFu : 0u;                   // any candidate with a 0 bit: drop those with a 1 bit
+#pragma unroll
+    for (int j = 0; j < NW; ++j) D.w[j] &= ~(am & (inv ? ~plane.w[j] : plane.w[j]));
+    return o ? 0u : 1u;
+}
+
+// Radix descent, forward strand.  D tracks the candidates shifted onto the symbol under test.
 template <int NW>
 FSB_HD StrandMin descend_forward(BV<NW> D, const BV<NW>& H, const BV<NW>& Lo, const DeviceParams& P)
 {
@@ -111,14 +127,8 @@ FSB_HD StrandMin descend_forward(BV<NW> D, const BV<NW>& H, const BV<NW>& Lo, co
     for (uint32_t d = 0; d < P.k; ++d)
     {
         if (d) D = bv_shl(D, 1);
-        BV<NW> T = bv_andn(D, H);
-        bool any = bv_any(T);
-        D = bv_select(any, T, D);
-        m = 2 * m + (any ? 0u : 1u);
-        T = bv_andn(D, Lo);
-        any = bv_any(T);
-        D = bv_select(any, T, D);
-        m = 2 * m + (any ? 0u : 1u);
+        m = 2 * m + descend_step<NW>(D, H, false);
+        m = 2 * m + descend_step<NW>(D, Lo, false);
     }
     StrandMin r;
     r.sig = m;
@@ -136,14 +146,8 @@ FSB_HD StrandMin descend_reverse(const BV<NW>& C, const BV<NW>& H, const BV<NW>&
     for (uint32_t d = 0; d < P.k; ++d)
     {
         if (d) D = bv_shr(D, 1);
-        BV<NW> T = bv_and(D, H);
-        bool any = bv_any(T);
-        D = bv_select(any, T, D);
-        m = 2 * m + (any ? 0u : 1u);
-        T = bv_and(D, Lo);
-        any = bv_any(T);
-        D = bv_select(any, T, D);
-        m = 2 * m + (any ? 0u : 1u);
+        m = 2 * m + descend_step<NW>(D, H, true);
+        m = 2 * m + descend_step<NW>(D, Lo, true);
     }
     StrandMin r;
     r.sig = m;
