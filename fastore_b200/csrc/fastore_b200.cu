@@ -5,6 +5,11 @@
 // (BinModule.cpp:124-167): Categorize(reads, bins); PackToBins(bins, block).  Several chunks may be
 // processed by one pass of the pipeline ("batch"): bins are keyed by (chunk, signature), so every
 // chunk still yields exactly its own BinaryBinBlock, byte for byte.
+//
+// fsb_bin_chunks (host buffers in, host blocks out) cuts its chunk list into sub-batches and runs
+// them as a three-stage pipeline over two sets of device buffers: host->device copy of sub-batch
+// g+1, kernels of g and device->host copy of g-1 overlap on three streams, the way the reference's
+// reader thread, encoder threads and writer overlap (BinModule.cpp:58-90).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -72,38 +77,53 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 } // namespace
 
-struct fsb_ctx
+// One staged group of chunks: its inputs and its results on the device.
+struct Batch
 {
-    fsb_params params{};
-    DeviceParams dp{};
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    std::string err;
-    bool per_read = false, profile = false, validate = true;
-
-    // ---- staged batch -------------------------------------------------------------------------
     bool staged = false, ran = false;
     uint32_t n_chunks = 0;
     uint64_t n_records = 0;
     std::vector<uint64_t> chunk_first_rec;       // n_chunks + 1
     std::vector<uint64_t> chunk_text_base[2];
-    uint64_t total_bases = 0, total_head = 0;
-    uint64_t nb_max = 0;
-    uint64_t algorithmic_in = 0;
-    size_t out_cap[4] = {0, 0, 0, 0};
+    std::vector<uint64_t> meta_host;             // host copy of the chunk tables (must outlive its async copy)
+    uint64_t total_bases = 0, total_head = 0, nb_max = 0, algorithmic_in = 0, h2d_bytes = 0;
+    uint32_t min_len = 0, max_len = 0, max_head = 0;
     int sort_passes = 0;
+    SlotGeom geom{};
+    size_t out_cap[4] = {0, 0, 0, 0};
 
     DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats;
     PinBuf h_stage_stats;
-    uint32_t min_len = 0, max_len = 0, max_head = 0;
-    SlotGeom slot_geom{};
-    DevBuf d_keys[2], d_cards[2], d_slots, d_info, d_sig, d_counts, d_counts_scan, d_scan_tmp;
+    DevBuf d_out[4], d_desc, d_summary, d_sig, d_info;
+    cudaEvent_t ev_h2d = nullptr, ev_run = nullptr, ev_d2h = nullptr;
+};
+
+// Pinned host memory holding the results of one (sub-)batch until the next call on the context.
+struct HostOut
+{
+    PinBuf out[4], desc, summary, sig, info;
+    uint64_t d2h_bytes = 0;
+};
+
+struct fsb_ctx
+{
+    fsb_params params{};
+    DeviceParams dp{};
+    int device = 0;
+    cudaStream_t stream = nullptr;               // kernels
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined fsb_bin_chunks (created on first use)
+    bool own_stream = false;
+    std::string err;
+    bool per_read = false, profile = false, validate = true;
+    uint64_t sub_batch_records = 400000;         // fsb_bin_chunks cuts its chunk list into sub-batches of at least this many records
+
+    Batch batch[2];                              // [0] is the batch of fsb_stage / fsb_run / fsb_fetch
+    std::vector<HostOut*> host;                  // [g] results of sub-batch g ([0] for the resident interface)
+
+    // intermediates, shared by all batches (the kernels of different batches run on one stream)
+    DevBuf d_keys[2], d_cards[2], d_slots, d_counts, d_counts_scan, d_scan_tmp;
     DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head;
-    DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4], d_desc, d_summary, d_out[4];
-    PinBuf h_summary, h_out[4], h_desc, h_sig, h_info;
-    uint32_t* sorted_keys = nullptr;
-    unsigned long long* sorted_cards = nullptr;
+    DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4];
 
     // ---- profiling -----------------------------------------------------------------------------
     std::vector<cudaEvent_t> events;             // kMaxPendingProfiles * (FSB_STAGE_COUNT + 1)
@@ -132,16 +152,16 @@ int fail(fsb_ctx* c, int code, const std::string& msg)
 
 uint32_t bits_for(uint32_t v) { uint32_t b = 0; while ((1ull << b) <= v) ++b; return b; }   // bits to represent v
 
-BatchView batch_view(const fsb_ctx* c)
+BatchView batch_view(const Batch& b)
 {
     BatchView B{};
-    const uint64_t* meta = c->d_chunk_meta.as<uint64_t>();
-    B.text[0] = c->d_text[0].as<uint8_t>(); B.text[1] = c->d_text[1].as<uint8_t>();
-    B.rec[0] = c->d_rec[0].as<fsb_record>(); B.rec[1] = c->d_rec[1].as<fsb_record>();
+    const uint64_t* meta = b.d_chunk_meta.as<uint64_t>();
+    B.text[0] = b.d_text[0].as<uint8_t>(); B.text[1] = b.d_text[1].as<uint8_t>();
+    B.rec[0] = b.d_rec[0].as<fsb_record>(); B.rec[1] = b.d_rec[1].as<fsb_record>();
     B.chunk_first_rec = meta;
-    B.chunk_text_base[0] = meta + (c->n_chunks + 1);
-    B.chunk_text_base[1] = meta + (c->n_chunks + 1) + c->n_chunks;
-    B.n_chunks = c->n_chunks; B.n_records = c->n_records;
+    B.chunk_text_base[0] = meta + (b.n_chunks + 1);
+    B.chunk_text_base[1] = meta + (b.n_chunks + 1) + b.n_chunks;
+    B.n_chunks = b.n_chunks; B.n_records = b.n_records;
     return B;
 }
 
@@ -180,6 +200,7 @@ cudaError_t launch_place(const PlaceArgs& pa, uint32_t max_len, uint32_t max_hea
     return cudaGetLastError();
 }
 
+
 int resolve_profiles(fsb_ctx* c)
 {
     if (c->pending_profiles == 0) return FSB_OK;
@@ -197,6 +218,391 @@ int resolve_profiles(fsb_ctx* c)
     }
     c->pending_profiles = 0;
     return FSB_OK;
+}
+
+// A shared intermediate may be in use by kernels of the previous sub-batch: wait for them before it is reallocated.
+cudaError_t ensure_shared(fsb_ctx* c, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return e;
+    return b.ensure(bytes);
+}
+
+HostOut* host_out(fsb_ctx* c, size_t g)
+{
+    while (c->host.size() <= g) c->host.push_back(new (std::nothrow) HostOut());
+    return c->host[g];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage, step 1: enqueue the host->device copies of a group of chunks on `st`, then the device-side
+// check of the record tables (offsets inside the chunk, lengths, PE mate-length equality - the
+// things the reference only ASSERTs: FastqRecord.h:87, FastqParser.cpp:130) together with the batch
+// statistics that size the buffers, and the copy of those statistics back.  The batch's input
+// buffers must not be in use.
+int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st)
+{
+    b.staged = false; b.ran = false;
+    const int nfiles = c->dp.paired ? 2 : 1;
+    const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(kMaxChunksPerBatch, 1ull << (32 - c->dp.key_bits));
+    if (n_chunks == 0) return fail(c, FSB_ERR_PARAM, "fsb_stage: no chunks");
+    if (n_chunks > max_chunks) return fail(c, FSB_ERR_PARAM, "fsb_stage: too many chunks in one batch for this signature length (max " + std::to_string(max_chunks) + ")");
+
+    b.n_chunks = n_chunks;
+    b.chunk_first_rec.assign(n_chunks + 1, 0);
+    size_t text_bytes[2] = {kTextPad, kTextPad};
+    for (int m = 0; m < 2; ++m) b.chunk_text_base[m].assign(n_chunks, 0);
+    uint64_t n = 0;
+    for (uint32_t ci = 0; ci < n_chunks; ++ci)
+    {
+        const fsb_chunk& ch = chunks[ci];
+        b.chunk_first_rec[ci] = n;
+        for (int m = 0; m < nfiles; ++m)
+        {
+            if (ch.n_records && (!ch.text[m] || !ch.records[m])) return fail(c, FSB_ERR_PARAM, "fsb_stage: null text/records");
+            if (ch.text_size[m] >= 0xFFFFFFFFull) return fail(c, FSB_ERR_INPUT, "fsb_stage: chunk text must be < 4 GiB (32-bit record offsets)");
+            b.chunk_text_base[m][ci] = text_bytes[m];
+            text_bytes[m] = align_up(text_bytes[m] + ch.text_size[m] + kTextPad, 256);
+        }
+        n += ch.n_records;
+    }
+    b.chunk_first_rec[n_chunks] = n;
+    if (n > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
+    b.n_records = n;
+    b.nb_max = std::min<uint64_t>(n, (uint64_t)n_chunks * ((uint64_t)c->dp.nbin + 1));
+    b.sort_passes = (int)((c->dp.key_bits + bits_for(n_chunks - 1) + 7) / 8);
+
+    uint64_t h2d = 0;
+    for (int m = 0; m < nfiles; ++m)
+    {
+        CUDA_TRY(c, b.d_text[m].ensure(text_bytes[m] + kTextPad));
+        CUDA_TRY(c, b.d_rec[m].ensure((n + 1) * sizeof(fsb_record)));
+        for (uint32_t ci = 0; ci < n_chunks; ++ci)
+        {
+            const fsb_chunk& ch = chunks[ci];
+            if (ch.text_size[m])
+                CUDA_TRY(c, cudaMemcpyAsync(b.d_text[m].as<uint8_t>() + b.chunk_text_base[m][ci], ch.text[m], ch.text_size[m], cudaMemcpyHostToDevice, st));
+            if (ch.n_records)
+                CUDA_TRY(c, cudaMemcpyAsync(b.d_rec[m].as<fsb_record>() + b.chunk_first_rec[ci], ch.records[m], ch.n_records * sizeof(fsb_record),
+                                            cudaMemcpyHostToDevice, st));
+            h2d += ch.text_size[m] + ch.n_records * sizeof(fsb_record);
+        }
+    }
+    // chunk tables: [first_rec (n_chunks+1)] [text_base0] [text_base1] [text_size0] [text_size1]  (n_chunks each)
+    std::vector<uint64_t>& meta = b.meta_host;
+    meta.clear();
+    meta.insert(meta.end(), b.chunk_first_rec.begin(), b.chunk_first_rec.end());
+    meta.insert(meta.end(), b.chunk_text_base[0].begin(), b.chunk_text_base[0].end());
+    meta.insert(meta.end(), b.chunk_text_base[1].begin(), b.chunk_text_base[1].end());
+    for (int m = 0; m < 2; ++m)
+        for (uint32_t ci = 0; ci < n_chunks; ++ci) meta.push_back(chunks[ci].text_size[m]);
+    CUDA_TRY(c, b.d_chunk_meta.ensure(meta.size() * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMemcpyAsync(b.d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    h2d += meta.size() * sizeof(uint64_t);
+
+    CUDA_TRY(c, b.d_stage_stats.ensure(sizeof(StageStats)));
+    CUDA_TRY(c, b.h_stage_stats.ensure(2 * sizeof(StageStats)));
+    StageStats init{};
+    init.first_bad = ~0ull; init.min_len = 0xFFFFFFFFu;
+    b.h_stage_stats.as<StageStats>()[1] = init;                  // [1] initial value going up, [0] result coming back
+    CUDA_TRY(c, cudaMemcpyAsync(b.d_stage_stats.p, b.h_stage_stats.as<StageStats>() + 1, sizeof(StageStats), cudaMemcpyHostToDevice, st));
+    if (n)
+    {
+        const BatchView B = batch_view(b);
+        const uint64_t* m64 = b.d_chunk_meta.as<uint64_t>();
+        const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
+        stage_stats_kernel<<<blocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>());
+        c->stats.kernel_launches++;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, st));
+    b.h2d_bytes = h2d;
+    c->stats.h2d_bytes += h2d;
+    return FSB_OK;
+}
+
+// Stage, step 2 (after everything stage_enqueue put on its stream has completed): reject contract
+// violations, then size the result buffers of the batch (which must not be in use) and the shared
+// intermediates.
+int stage_complete(fsb_ctx* c, Batch& b)
+{
+    const StageStats stats = *b.h_stage_stats.as<StageStats>();
+    const uint64_t n = b.n_records;
+    const uint32_t n_chunks = b.n_chunks;
+    if (stats.n_bad)
+    {
+        // never run the kernels on tables that point outside the staged text
+        uint32_t ci = 0;
+        while (ci + 1 < n_chunks && b.chunk_first_rec[ci + 1] <= stats.first_bad) ++ci;
+        return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(stats.first_bad - b.chunk_first_rec[ci]) + " of chunk " + std::to_string(ci) +
+                                          " violates the input contract (length 1..255, offsets inside the chunk, equal PE mate lengths); " +
+                                          std::to_string(stats.n_bad) + " such record(s)");
+    }
+    const uint64_t bases = stats.bases, heads = stats.heads;
+    b.total_bases = bases; b.total_head = heads;
+    b.min_len = n ? stats.min_len : 0; b.max_len = stats.max_len; b.max_head = stats.max_head;
+    b.geom = make_slot_geom(c->dp, b.max_len, b.max_head);
+
+    // ---- shared intermediates (grow-only) -----------------------------------------------------------
+    const uint64_t nsort_blocks = (n + kSortTile - 1) / kSortTile;
+    const uint64_t ncounts = (uint64_t)kRadix * std::max<uint64_t>(nsort_blocks, 1);
+    const uint64_t nbm = b.nb_max;
+    for (int i = 0; i < 2; ++i)
+    {
+        CUDA_TRY(c, ensure_shared(c, c->d_keys[i], (n + 1) * 4));
+        CUDA_TRY(c, ensure_shared(c, c->d_cards[i], (n + 1) * 8));
+    }
+    CUDA_TRY(c, ensure_shared(c, c->d_slots, (n + 1) * (size_t)b.geom.words * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_counts, (ncounts + 1) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_counts_scan, (ncounts + 1) * 4));
+    const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(n, ncounts), nbm) + 1;
+    CUDA_TRY(c, ensure_shared(c, c->d_scan_tmp, 4 * (scan_num_tiles(max_scan_n) + 2) * 8));
+    CUDA_TRY(c, ensure_shared(c, c->d_flags, (n + 1) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_flags_excl, (n + 2) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_bin_of, (n + 1) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_bin_start, (nbm + 2) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_bin_min, (nbm + 1) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_bin_max, (nbm + 1) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_raw_dna, (nbm + 1) * 8));
+    CUDA_TRY(c, ensure_shared(c, c->d_raw_head, (nbm + 1) * 8));
+    for (int s = 0; s < 4; ++s)
+    {
+        CUDA_TRY(c, ensure_shared(c, c->d_bits[s], (n + 1) * 4));
+        CUDA_TRY(c, ensure_shared(c, c->d_P[s], (n + 2) * 8));
+        CUDA_TRY(c, ensure_shared(c, c->d_bytes[s], (nbm + 1) * 8));
+        CUDA_TRY(c, ensure_shared(c, c->d_BO[s], (nbm + 2) * 8));
+    }
+    // ---- results of this batch ---------------------------------------------------------------------------
+    CUDA_TRY(c, b.d_desc.ensure((nbm + 1) * sizeof(fsb_bin_descriptor)));
+    CUDA_TRY(c, b.d_summary.ensure((size_t)n_chunks * sizeof(ChunkSummary)));
+    if (c->per_read)
+    {
+        CUDA_TRY(c, b.d_info.ensure((n + 1) * 4));
+        CUDA_TRY(c, b.d_sig.ensure((n + 1) * 4));
+    }
+    // upper bounds of the stream sizes (exact sizes are only known on the device after the layout scans)
+    const uint64_t pad_bytes = nbm + 64;                                    // < 1 byte of padding per bin and stream
+    b.out_cap[0] = align_up((28 * n + 17 * nbm) / 8 + pad_bytes, 64);
+    b.out_cap[1] = align_up(3 * bases / 8 + pad_bytes, 64);
+    b.out_cap[2] = align_up((uint64_t)c->dp.qua_bits * bases / 8 + pad_bytes, 64);
+    b.out_cap[3] = align_up(c->dp.has_headers ? (8 * n + 7 * heads) / 8 + pad_bytes : 64, 64);
+    for (int s = 0; s < 4; ++s) CUDA_TRY(c, b.d_out[s].ensure(b.out_cap[s]));
+
+    // SURVEY 8(d) algorithmic input bytes: every sequence, quality and kept header byte once
+    b.algorithmic_in = 2 * bases + (c->dp.has_headers ? heads : 0);
+    b.staged = true;
+    return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernels of one batch on the context's stream: K1 ingest -> sort -> layout -> K4 place.
+int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
+{
+    cudaStream_t st = c->stream;
+    const uint64_t n = b.n_records;
+    const DeviceParams& P = c->dp;
+    uint64_t launches = 0;
+
+    cudaEvent_t* ev = nullptr;
+    if (profile)
+    {
+        if (c->pending_profiles == kMaxPendingProfiles) { int rc = resolve_profiles(c); if (rc != FSB_OK) return rc; }
+        const size_t need = (size_t)(c->pending_profiles + 1) * (FSB_STAGE_COUNT + 1);
+        while (c->events.size() < need) { cudaEvent_t e; CUDA_TRY(c, cudaEventCreate(&e)); c->events.push_back(e); }
+        ev = &c->events[(size_t)c->pending_profiles * (FSB_STAGE_COUNT + 1)];
+        CUDA_TRY(c, cudaEventRecord(ev[0], st));
+    }
+
+    const BatchView B = batch_view(b);
+    const unsigned tpb = 256;
+    const unsigned grid_n = (unsigned)std::max<uint64_t>(1, (n + tpb - 1) / tpb);
+
+    // ---- K1: ingest (signature + prepacked slots) -----------------------------------------------------------
+    if (n)
+    {
+        uint32_t* keys = c->d_keys[0].as<uint32_t>();
+        unsigned long long* cards = c->d_cards[0].as<unsigned long long>();
+        uint32_t* slots = c->d_slots.as<uint32_t>();
+        uint32_t* sig = c->per_read ? b.d_sig.as<uint32_t>() : nullptr;
+        uint32_t* info = c->per_read ? b.d_info.as<uint32_t>() : nullptr;
+        const SlotGeom& G = b.geom;
+        cudaError_t e = cudaSuccess;
+        switch ((b.max_len + 31) / 32)              // words of 32 bases per mate
+        {
+        case 0: case 1: e = launch_ingest<1>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        case 2: e = launch_ingest<2>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        case 3: e = launch_ingest<3>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        case 4: e = launch_ingest<4>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        case 5: e = launch_ingest<5>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        case 6: e = launch_ingest<6>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        case 7: e = launch_ingest<7>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        default: e = launch_ingest<8>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        }
+        CUDA_TRY(c, e);
+        launches++;
+    }
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[1], st));
+
+    // ---- K2/K3: stable radix sort of (chunk:signature -> card) --------------------------------------------
+    int cur = 0;
+    if (n)
+    {
+        const uint32_t nblocks = (uint32_t)((n + kSortTile - 1) / kSortTile);
+        const uint64_t ncounts = (uint64_t)kRadix * nblocks;
+        for (int pass = 0; pass < b.sort_passes; ++pass)
+        {
+            const int shift = 8 * pass;
+            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), n, shift, c->d_counts.as<uint32_t>(), nblocks);
+            launches++;
+            launches += exclusive_scan<uint32_t, uint32_t>(c->d_counts.as<uint32_t>(), ncounts, c->d_counts_scan.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
+            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), c->d_cards[cur].as<unsigned long long>(), n, shift,
+                                                            c->d_counts_scan.as<uint32_t>(), nblocks, c->d_keys[cur ^ 1].as<uint32_t>(),
+                                                            c->d_cards[cur ^ 1].as<unsigned long long>());
+            launches++;
+            cur ^= 1;
+        }
+    }
+    const uint32_t* sorted_keys = c->d_keys[cur].as<uint32_t>();
+    const unsigned long long* sorted_cards = c->d_cards[cur].as<unsigned long long>();
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[2], st));
+
+    // ---- layout --------------------------------------------------------------------------------------
+    SortedView S{sorted_keys, sorted_cards};
+    BinArrays A{c->d_bin_of.as<uint32_t>(), c->d_bin_start.as<uint32_t>(), c->d_bin_min.as<uint32_t>(), c->d_bin_max.as<uint32_t>(),
+                c->d_raw_dna.as<unsigned long long>(), c->d_raw_head.as<unsigned long long>()};
+    StreamScans SC{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
+    BinOffsets BO{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
+    const uint32_t* nb_ptr = c->d_flags_excl.as<uint32_t>() + n;
+    {
+        const uint64_t nbm = b.nb_max;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_min.p, 0xFF, (nbm + 1) * 4, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_max.p, 0, (nbm + 1) * 4, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_dna.p, 0, (nbm + 1) * 8, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_head.p, 0, (nbm + 1) * 8, st));
+        if (n)
+        {
+            bin_flags_kernel<<<grid_n, tpb, 0, st>>>(sorted_keys, n, c->d_flags.as<uint32_t>());
+            launches++;
+        }
+        launches += exclusive_scan<uint32_t, uint32_t>(c->d_flags.as<uint32_t>(), n, c->d_flags_excl.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
+        if (n)
+        {
+            bin_stats_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, c->d_flags.as<uint32_t>(), c->d_flags_excl.as<uint32_t>(), A);
+            read_bits_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, A, c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(),
+                                                      c->d_bits[3].as<uint32_t>());
+            launches += 2;
+        }
+        {
+            Ptr4<const uint32_t> in4{{c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(), c->d_bits[3].as<uint32_t>()}};
+            Ptr4<uint64_t> out4{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
+            launches += exclusive_scan4<uint32_t, uint64_t>(in4, n, out4, c->d_scan_tmp.as<uint64_t>(), st);
+        }
+        if (nbm)
+        {
+            const unsigned grid_b = (unsigned)((nbm + tpb - 1) / tpb);
+            bin_sizes_kernel<<<grid_b, tpb, 0, st>>>(P, n, nb_ptr, nbm, sorted_keys, A, SC, c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(),
+                                                      c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>(), b.d_desc.as<fsb_bin_descriptor>());
+            launches++;
+        }
+        {
+            Ptr4<const uint64_t> in4{{c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(), c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>()}};
+            Ptr4<uint64_t> out4{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
+            launches += exclusive_scan4<uint64_t, uint64_t>(in4, nbm, out4, c->d_scan_tmp.as<uint64_t>(), st);
+        }
+        chunk_summary_kernel<<<b.n_chunks, 128, 0, st>>>(B, nb_ptr, A.bin_of, BO, b.d_desc.as<fsb_bin_descriptor>(), b.d_summary.as<ChunkSummary>());
+        launches++;
+    }
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[3], st));
+
+    // ---- K4: place ------------------------------------------------------------------------------------
+    if (n)
+    {
+        PlaceArgs pa{B, P, b.geom, S, A, SC, BO, {{b.d_out[0].as<uint32_t>(), b.d_out[1].as<uint32_t>(), b.d_out[2].as<uint32_t>(), b.d_out[3].as<uint32_t>()}},
+                     c->d_slots.as<uint32_t>(), nb_ptr};
+        int place_launches = 0;
+        CUDA_TRY(c, launch_place(pa, b.max_len, b.max_head, st, &place_launches));
+        launches += place_launches;
+    }
+    if (ev)
+    {
+        CUDA_TRY(c, cudaEventRecord(ev[4], st));
+        c->pending_profiles++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->stats.kernel_launches += launches;
+    c->stats.records += n;
+    b.ran = true;
+    return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Results, step 1: the per-chunk summary (sizes are only known on the device).
+int summary_enqueue(fsb_ctx* c, Batch& b, HostOut& h, cudaStream_t st)
+{
+    CUDA_TRY(c, h.summary.ensure((size_t)b.n_chunks * sizeof(ChunkSummary)));
+    CUDA_TRY(c, cudaMemcpyAsync(h.summary.p, b.d_summary.p, (size_t)b.n_chunks * sizeof(ChunkSummary), cudaMemcpyDeviceToHost, st));
+    return FSB_OK;
+}
+// Results, step 2 (summary on the host): enqueue the copies of the streams and descriptors.
+int fetch_enqueue(fsb_ctx* c, Batch& b, HostOut& h, cudaStream_t st)
+{
+    const uint64_t n = b.n_records;
+    uint64_t d2h = (size_t)b.n_chunks * sizeof(ChunkSummary);
+    const ChunkSummary* sum = h.summary.as<ChunkSummary>();
+    const ChunkSummary& last = sum[b.n_chunks - 1];
+    const uint64_t nb = last.first_bin + last.n_bins;
+    for (int s = 0; s < 4; ++s)
+    {
+        const uint64_t total = last.off[s] + last.size[s];
+        if (total > b.out_cap[s]) return fail(c, FSB_ERR_STATE, "internal error: stream size exceeds its bound");
+        CUDA_TRY(c, h.out[s].ensure(total + 64));
+        if (total) CUDA_TRY(c, cudaMemcpyAsync(h.out[s].p, b.d_out[s].p, total, cudaMemcpyDeviceToHost, st));
+        d2h += total;
+    }
+    CUDA_TRY(c, h.desc.ensure((nb + 1) * sizeof(fsb_bin_descriptor)));
+    if (nb) CUDA_TRY(c, cudaMemcpyAsync(h.desc.p, b.d_desc.p, nb * sizeof(fsb_bin_descriptor), cudaMemcpyDeviceToHost, st));
+    d2h += nb * sizeof(fsb_bin_descriptor);
+    if (c->per_read)
+    {
+        CUDA_TRY(c, h.sig.ensure((n + 1) * 4));
+        CUDA_TRY(c, h.info.ensure((n + 1) * 4));
+        if (n)
+        {
+            CUDA_TRY(c, cudaMemcpyAsync(h.sig.p, b.d_sig.p, n * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaMemcpyAsync(h.info.p, b.d_info.p, n * 4, cudaMemcpyDeviceToHost, st));
+        }
+        d2h += 8 * n;
+    }
+    h.d2h_bytes = d2h;
+    c->stats.d2h_bytes += d2h;
+    return FSB_OK;
+}
+// Results, step 3 (copies complete): describe every chunk's block.
+void fill_blocks(fsb_ctx* c, const Batch& b, const HostOut& h, fsb_block* blocks)
+{
+    const ChunkSummary* sum = h.summary.as<ChunkSummary>();
+    uint64_t alg_out = 0;
+    for (uint32_t ci = 0; ci < b.n_chunks; ++ci)
+    {
+        const ChunkSummary& s = sum[ci];
+        fsb_block& o = blocks[ci];
+        std::memset(&o, 0, sizeof(o));
+        o.meta = h.out[0].as<uint8_t>() + s.off[0]; o.meta_size = s.size[0];
+        o.dna = h.out[1].as<uint8_t>() + s.off[1];  o.dna_size = s.size[1];
+        o.qua = h.out[2].as<uint8_t>() + s.off[2];  o.qua_size = s.size[2];
+        o.head = h.out[3].as<uint8_t>() + s.off[3]; o.head_size = s.size[3];
+        o.raw_dna_size = s.raw_dna; o.raw_head_size = s.raw_head;
+        o.bins = h.desc.as<fsb_bin_descriptor>() + s.first_bin;
+        o.n_bins = s.n_bins;
+        o.n_records = b.chunk_first_rec[ci + 1] - b.chunk_first_rec[ci];
+        if (c->per_read)
+        {
+            o.read_signature = h.sig.as<uint32_t>() + b.chunk_first_rec[ci];
+            o.read_info = h.info.as<uint32_t>() + b.chunk_first_rec[ci];
+        }
+        alg_out += s.size[0] + s.size[1] + s.size[2] + s.size[3];
+    }
+    c->stats.algorithmic_bytes += b.algorithmic_in + alg_out;
 }
 
 } // namespace
@@ -243,12 +649,20 @@ extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fs
     c->dp = make_device_params(*p);
 
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail(nullptr, FSB_ERR_CUDA, "cudaSetDevice failed"); }
-    if (const char* g = std::getenv("FSB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else
     {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(nullptr, FSB_ERR_CUDA, "cudaStreamCreate failed"); }
         c->own_stream = true;
+    }
+    for (Batch& b : c->batch)
+    {
+        if (cudaEventCreateWithFlags(&b.ev_h2d, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b.ev_run, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b.ev_d2h, cudaEventDisableTiming) != cudaSuccess)
+        {
+            fsb_destroy(c);
+            return fail(nullptr, FSB_ERR_CUDA, "cudaEventCreate failed");
+        }
     }
     *out = c;
     return FSB_OK;
@@ -259,16 +673,31 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->s_h2d) { cudaStreamSynchronize(c->s_h2d); cudaStreamDestroy(c->s_h2d); }
+    if (c->s_d2h) { cudaStreamSynchronize(c->s_d2h); cudaStreamDestroy(c->s_d2h); }
     for (auto& e : c->events) cudaEventDestroy(e);
-    DevBuf* dev[] = {&c->d_text[0], &c->d_text[1], &c->d_rec[0], &c->d_rec[1], &c->d_chunk_meta, &c->d_stage_stats, &c->d_keys[0], &c->d_keys[1], &c->d_cards[0],
-                     &c->d_cards[1], &c->d_slots, &c->d_info, &c->d_sig, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags, &c->d_flags_excl,
-                     &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
+    for (Batch& b : c->batch)
+    {
+        DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
+                         &b.d_desc, &b.d_summary, &b.d_sig, &b.d_info};
+        for (DevBuf* d : dev) d->release();
+        b.h_stage_stats.release();
+        if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
+        if (b.ev_run) cudaEventDestroy(b.ev_run);
+        if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);
+    }
+    DevBuf* dev[] = {&c->d_keys[0], &c->d_keys[1], &c->d_cards[0], &c->d_cards[1], &c->d_slots, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags,
+                     &c->d_flags_excl, &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
                      &c->d_bits[2], &c->d_bits[3], &c->d_P[0], &c->d_P[1], &c->d_P[2], &c->d_P[3], &c->d_bytes[0], &c->d_bytes[1],
-                     &c->d_bytes[2], &c->d_bytes[3], &c->d_BO[0], &c->d_BO[1], &c->d_BO[2], &c->d_BO[3], &c->d_desc, &c->d_summary,
-                     &c->d_out[0], &c->d_out[1], &c->d_out[2], &c->d_out[3]};
-    for (DevBuf* b : dev) b->release();
-    PinBuf* pin[] = {&c->h_stage_stats, &c->h_summary, &c->h_out[0], &c->h_out[1], &c->h_out[2], &c->h_out[3], &c->h_desc, &c->h_sig, &c->h_info};
-    for (PinBuf* b : pin) b->release();
+                     &c->d_bytes[2], &c->d_bytes[3], &c->d_BO[0], &c->d_BO[1], &c->d_BO[2], &c->d_BO[3]};
+    for (DevBuf* d : dev) d->release();
+    for (HostOut* h : c->host)
+    {
+        if (!h) continue;
+        PinBuf* pin[] = {&h->out[0], &h->out[1], &h->out[2], &h->out[3], &h->desc, &h->summary, &h->sig, &h->info};
+        for (PinBuf* q : pin) q->release();
+        delete h;
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -281,6 +710,7 @@ extern "C" int fsb_set_option(fsb_ctx* c, int option, int64_t value)
     case FSB_OPT_PER_READ: c->per_read = value != 0; return FSB_OK;
     case FSB_OPT_PROFILE: c->profile = value != 0; return FSB_OK;
     case FSB_OPT_VALIDATE: c->validate = value != 0; return FSB_OK;
+    case FSB_OPT_SUBBATCH_RECORDS: c->sub_batch_records = value > 0 ? (uint64_t)value : 1; return FSB_OK;
     }
     return fail(c, FSB_ERR_PARAM, "unknown option");
 }
@@ -321,372 +751,124 @@ extern "C" int fsb_stage_times(fsb_ctx* c, float* ms, uint32_t n_stages, uint32_
     return FSB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// fsb_stage: enqueue the host->device copies, then check the record tables on the device (offsets
-// inside the chunk, lengths, PE mate-length equality - the things the reference only ASSERTs:
-// FastqRecord.h:87, FastqParser.cpp:130) and collect the batch statistics that size the buffers.
+// ---- the resident interface: one batch, everything on the context's stream ---------------------------------
 extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
 {
     if (!c || (!chunks && n_chunks)) return FSB_ERR_PARAM;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    c->staged = false; c->ran = false;
-    const int nfiles = c->dp.paired ? 2 : 1;
-    const uint32_t max_chunks = std::min<uint64_t>(kMaxChunksPerBatch, 1ull << (32 - c->dp.key_bits));
-    if (n_chunks == 0) return fail(c, FSB_ERR_PARAM, "fsb_stage: no chunks");
-    if (n_chunks > max_chunks) return fail(c, FSB_ERR_PARAM, "fsb_stage: too many chunks in one batch for this signature length (max " + std::to_string(max_chunks) + ")");
-
-    c->n_chunks = n_chunks;
-    c->chunk_first_rec.assign(n_chunks + 1, 0);
-    size_t text_bytes[2] = {kTextPad, kTextPad};
-    for (int m = 0; m < 2; ++m) c->chunk_text_base[m].assign(n_chunks, 0);
-    uint64_t n = 0;
-    for (uint32_t ci = 0; ci < n_chunks; ++ci)
-    {
-        const fsb_chunk& ch = chunks[ci];
-        c->chunk_first_rec[ci] = n;
-        for (int m = 0; m < nfiles; ++m)
-        {
-            if (ch.n_records && (!ch.text[m] || !ch.records[m])) return fail(c, FSB_ERR_PARAM, "fsb_stage: null text/records");
-            if (ch.text_size[m] >= 0xFFFFFFFFull) return fail(c, FSB_ERR_INPUT, "fsb_stage: chunk text must be < 4 GiB (32-bit record offsets)");
-            c->chunk_text_base[m][ci] = text_bytes[m];
-            text_bytes[m] = align_up(text_bytes[m] + ch.text_size[m] + kTextPad, 256);
-        }
-        n += ch.n_records;
-    }
-    c->chunk_first_rec[n_chunks] = n;
-    if (n > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
-    c->n_records = n;
-    c->nb_max = std::min<uint64_t>(n, (uint64_t)n_chunks * ((uint64_t)c->dp.nbin + 1));
-    c->sort_passes = (int)((c->dp.key_bits + bits_for(n_chunks - 1) + 7) / 8);
-
-    // ---- device input buffers + copies ----------------------------------------------------------
-    uint64_t h2d = 0;
-    for (int m = 0; m < nfiles; ++m)
-    {
-        CUDA_TRY(c, c->d_text[m].ensure(text_bytes[m] + kTextPad));
-        CUDA_TRY(c, c->d_rec[m].ensure((n + 1) * sizeof(fsb_record)));
-        for (uint32_t ci = 0; ci < n_chunks; ++ci)
-        {
-            const fsb_chunk& ch = chunks[ci];
-            if (ch.text_size[m])
-                CUDA_TRY(c, cudaMemcpyAsync(c->d_text[m].as<uint8_t>() + c->chunk_text_base[m][ci], ch.text[m], ch.text_size[m], cudaMemcpyHostToDevice, c->stream));
-            if (ch.n_records)
-                CUDA_TRY(c, cudaMemcpyAsync(c->d_rec[m].as<fsb_record>() + c->chunk_first_rec[ci], ch.records[m], ch.n_records * sizeof(fsb_record),
-                                            cudaMemcpyHostToDevice, c->stream));
-            h2d += ch.text_size[m] + ch.n_records * sizeof(fsb_record);
-        }
-    }
-    // chunk tables: [first_rec (n_chunks+1)] [text_base0] [text_base1] [text_size0] [text_size1]  (n_chunks each)
-    StageStats stats{};
-    {
-        std::vector<uint64_t> meta;
-        meta.insert(meta.end(), c->chunk_first_rec.begin(), c->chunk_first_rec.end());
-        meta.insert(meta.end(), c->chunk_text_base[0].begin(), c->chunk_text_base[0].end());
-        meta.insert(meta.end(), c->chunk_text_base[1].begin(), c->chunk_text_base[1].end());
-        for (int m = 0; m < 2; ++m)
-            for (uint32_t ci = 0; ci < n_chunks; ++ci) meta.push_back(chunks[ci].text_size[m]);
-        CUDA_TRY(c, c->d_chunk_meta.ensure(meta.size() * sizeof(uint64_t)));
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-        h2d += meta.size() * sizeof(uint64_t);
-
-        CUDA_TRY(c, c->d_stage_stats.ensure(sizeof(StageStats)));
-        CUDA_TRY(c, c->h_stage_stats.ensure(sizeof(StageStats)));
-        StageStats init{};
-        init.first_bad = ~0ull; init.min_len = 0xFFFFFFFFu;
-        *c->h_stage_stats.as<StageStats>() = init;
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_stage_stats.p, c->h_stage_stats.p, sizeof(StageStats), cudaMemcpyHostToDevice, c->stream));
-        if (n)
-        {
-            const BatchView B = batch_view(c);
-            const uint64_t* m64 = c->d_chunk_meta.as<uint64_t>();
-            const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
-            stage_stats_kernel<<<blocks, 256, 0, c->stream>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1),
-                                                              c->d_stage_stats.as<StageStats>());
-            c->stats.kernel_launches++;
-        }
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // the H2D of the init block must finish before the D2H reuses the pinned block
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_stage_stats.p, c->d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // `meta` (and pageable user buffers) must outlive the copies
-        stats = *c->h_stage_stats.as<StageStats>();
-    }
-    c->stats.h2d_bytes += h2d;
-    if (stats.n_bad)
-    {
-        // never run the kernels on tables that point outside the staged text
-        uint32_t ci = 0;
-        while (ci + 1 < n_chunks && c->chunk_first_rec[ci + 1] <= stats.first_bad) ++ci;
-        return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(stats.first_bad - c->chunk_first_rec[ci]) + " of chunk " + std::to_string(ci) +
-                                          " violates the input contract (length 1..255, offsets inside the chunk, equal PE mate lengths); " +
-                                          std::to_string(stats.n_bad) + " such record(s)");
-    }
-    const uint64_t bases = stats.bases, heads = stats.heads;
-    c->total_bases = bases; c->total_head = heads;
-    c->min_len = n ? stats.min_len : 0; c->max_len = stats.max_len; c->max_head = stats.max_head;
-
-    // ---- intermediate + output buffers (grow-only) -----------------------------------------------
-    const uint64_t nsort_blocks = (n + kSortTile - 1) / kSortTile;
-    const uint64_t ncounts = (uint64_t)kRadix * std::max<uint64_t>(nsort_blocks, 1);
-    for (int i = 0; i < 2; ++i)
-    {
-        CUDA_TRY(c, c->d_keys[i].ensure((n + 1) * 4));
-        CUDA_TRY(c, c->d_cards[i].ensure((n + 1) * 8));
-    }
-    c->slot_geom = make_slot_geom(c->dp, c->max_len, c->max_head);
-    CUDA_TRY(c, c->d_slots.ensure((n + 1) * (size_t)c->slot_geom.words * 4));
-    CUDA_TRY(c, c->d_info.ensure((n + 1) * 4));
-    CUDA_TRY(c, c->d_sig.ensure((n + 1) * 4));
-    CUDA_TRY(c, c->d_counts.ensure((ncounts + 1) * 4));
-    CUDA_TRY(c, c->d_counts_scan.ensure((ncounts + 1) * 4));
-    const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(n, ncounts), c->nb_max) + 1;
-    CUDA_TRY(c, c->d_scan_tmp.ensure(4 * (scan_num_tiles(max_scan_n) + 2) * 8));
-    CUDA_TRY(c, c->d_flags.ensure((n + 1) * 4));
-    CUDA_TRY(c, c->d_flags_excl.ensure((n + 2) * 4));
-    CUDA_TRY(c, c->d_bin_of.ensure((n + 1) * 4));
-    CUDA_TRY(c, c->d_bin_start.ensure((c->nb_max + 2) * 4));
-    CUDA_TRY(c, c->d_bin_min.ensure((c->nb_max + 1) * 4));
-    CUDA_TRY(c, c->d_bin_max.ensure((c->nb_max + 1) * 4));
-    CUDA_TRY(c, c->d_raw_dna.ensure((c->nb_max + 1) * 8));
-    CUDA_TRY(c, c->d_raw_head.ensure((c->nb_max + 1) * 8));
-    for (int s = 0; s < 4; ++s)
-    {
-        CUDA_TRY(c, c->d_bits[s].ensure((n + 1) * 4));
-        CUDA_TRY(c, c->d_P[s].ensure((n + 2) * 8));
-        CUDA_TRY(c, c->d_bytes[s].ensure((c->nb_max + 1) * 8));
-        CUDA_TRY(c, c->d_BO[s].ensure((c->nb_max + 2) * 8));
-    }
-    CUDA_TRY(c, c->d_desc.ensure((c->nb_max + 1) * sizeof(fsb_bin_descriptor)));
-    CUDA_TRY(c, c->d_summary.ensure((size_t)n_chunks * sizeof(ChunkSummary)));
-    // upper bounds of the stream sizes (exact sizes are only known on the device after the layout scans)
-    const uint64_t pad_bytes = c->nb_max + 64;                              // < 1 byte of padding per bin and stream
-    c->out_cap[0] = align_up((28 * n + 17 * c->nb_max) / 8 + pad_bytes, 64);
-    c->out_cap[1] = align_up(3 * bases / 8 + pad_bytes, 64);
-    c->out_cap[2] = align_up((uint64_t)c->dp.qua_bits * bases / 8 + pad_bytes, 64);
-    c->out_cap[3] = align_up(c->dp.has_headers ? (8 * n + 7 * heads) / 8 + pad_bytes : 64, 64);
-    for (int s = 0; s < 4; ++s) CUDA_TRY(c, c->d_out[s].ensure(c->out_cap[s]));
-
-    // SURVEY 8(d) algorithmic input bytes: every sequence, quality and kept header byte once
-    c->algorithmic_in = 2 * bases + (c->dp.has_headers ? heads : 0);
-    c->staged = true;
-    return FSB_OK;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // nothing may still be using the batch's buffers
+    Batch& b = c->batch[0];
+    int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream);
+    if (rc != FSB_OK) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // pageable user buffers must outlive the copies; the statistics are back
+    return stage_complete(c, b);
 }
 
-// ------------------------------------------------------------------------------------------------
 extern "C" int fsb_run(fsb_ctx* c)
 {
     if (!c) return FSB_ERR_PARAM;
-    if (!c->staged) return fail(c, FSB_ERR_STATE, "fsb_run: nothing staged");
+    if (!c->batch[0].staged) return fail(c, FSB_ERR_STATE, "fsb_run: nothing staged");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    const uint64_t n = c->n_records;
-    const DeviceParams& P = c->dp;
-    uint64_t launches = 0;
-
-    cudaEvent_t* ev = nullptr;
-    if (c->profile)
-    {
-        if (c->pending_profiles == kMaxPendingProfiles) { int rc = resolve_profiles(c); if (rc != FSB_OK) return rc; }
-        const size_t need = (size_t)(c->pending_profiles + 1) * (FSB_STAGE_COUNT + 1);
-        while (c->events.size() < need) { cudaEvent_t e; CUDA_TRY(c, cudaEventCreate(&e)); c->events.push_back(e); }
-        ev = &c->events[(size_t)c->pending_profiles * (FSB_STAGE_COUNT + 1)];
-        CUDA_TRY(c, cudaEventRecord(ev[0], st));
-    }
-
-    const BatchView B = batch_view(c);
-
-    const unsigned tpb = 256;
-    const unsigned grid_n = (unsigned)std::max<uint64_t>(1, (n + tpb - 1) / tpb);
-
-    // ---- K1: ingest (signature + prepacked slots) -----------------------------------------------------------
-    if (n)
-    {
-        uint32_t* keys = c->d_keys[0].as<uint32_t>();
-        unsigned long long* cards = c->d_cards[0].as<unsigned long long>();
-        uint32_t* slots = c->d_slots.as<uint32_t>();
-        uint32_t* sig = c->per_read ? c->d_sig.as<uint32_t>() : nullptr;
-        uint32_t* info = c->per_read ? c->d_info.as<uint32_t>() : nullptr;
-        const SlotGeom& G = c->slot_geom;
-        cudaError_t e = cudaSuccess;
-        switch ((c->max_len + 31) / 32)              // words of 32 bases per mate
-        {
-        case 0: case 1: e = launch_ingest<1>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        case 2: e = launch_ingest<2>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        case 3: e = launch_ingest<3>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        case 4: e = launch_ingest<4>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        case 5: e = launch_ingest<5>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        case 6: e = launch_ingest<6>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        case 7: e = launch_ingest<7>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        default: e = launch_ingest<8>(B, P, G, c->max_head, keys, cards, slots, sig, info, st); break;
-        }
-        CUDA_TRY(c, e);
-        launches++;
-    }
-    if (ev) CUDA_TRY(c, cudaEventRecord(ev[1], st));
-
-    // ---- K2/K3: stable radix sort of (chunk:signature, record index) ----------------------------------
-    int cur = 0;
-    if (n)
-    {
-        const uint32_t nblocks = (uint32_t)((n + kSortTile - 1) / kSortTile);
-        const uint64_t ncounts = (uint64_t)kRadix * nblocks;
-        for (int pass = 0; pass < c->sort_passes; ++pass)
-        {
-            const int shift = 8 * pass;
-            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), n, shift, c->d_counts.as<uint32_t>(), nblocks);
-            launches++;
-            launches += exclusive_scan<uint32_t, uint32_t>(c->d_counts.as<uint32_t>(), ncounts, c->d_counts_scan.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
-            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), c->d_cards[cur].as<unsigned long long>(), n, shift,
-                                                            c->d_counts_scan.as<uint32_t>(), nblocks, c->d_keys[cur ^ 1].as<uint32_t>(),
-                                                            c->d_cards[cur ^ 1].as<unsigned long long>());
-            launches++;
-            cur ^= 1;
-        }
-    }
-    c->sorted_keys = c->d_keys[cur].as<uint32_t>();
-    c->sorted_cards = c->d_cards[cur].as<unsigned long long>();
-    if (ev) CUDA_TRY(c, cudaEventRecord(ev[2], st));
-
-    // ---- layout --------------------------------------------------------------------------------------
-    SortedView S{c->sorted_keys, c->sorted_cards};
-    BinArrays A{c->d_bin_of.as<uint32_t>(), c->d_bin_start.as<uint32_t>(), c->d_bin_min.as<uint32_t>(), c->d_bin_max.as<uint32_t>(),
-                c->d_raw_dna.as<unsigned long long>(), c->d_raw_head.as<unsigned long long>()};
-    StreamScans SC{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
-    BinOffsets BO{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
-    const uint32_t* nb_ptr = c->d_flags_excl.as<uint32_t>() + n;
-    {
-        const uint64_t nbm = c->nb_max;
-        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_min.p, 0xFF, (nbm + 1) * 4, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_max.p, 0, (nbm + 1) * 4, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_dna.p, 0, (nbm + 1) * 8, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_head.p, 0, (nbm + 1) * 8, st));
-        if (n)
-        {
-            bin_flags_kernel<<<grid_n, tpb, 0, st>>>(c->sorted_keys, n, c->d_flags.as<uint32_t>());
-            launches++;
-        }
-        launches += exclusive_scan<uint32_t, uint32_t>(c->d_flags.as<uint32_t>(), n, c->d_flags_excl.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
-        if (n)
-        {
-            bin_stats_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, c->d_flags.as<uint32_t>(), c->d_flags_excl.as<uint32_t>(), A);
-            read_bits_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, A, c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(),
-                                                      c->d_bits[3].as<uint32_t>());
-            launches += 2;
-        }
-        {
-            Ptr4<const uint32_t> in4{{c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(), c->d_bits[3].as<uint32_t>()}};
-            Ptr4<uint64_t> out4{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
-            launches += exclusive_scan4<uint32_t, uint64_t>(in4, n, out4, c->d_scan_tmp.as<uint64_t>(), st);
-        }
-        if (nbm)
-        {
-            const unsigned grid_b = (unsigned)((nbm + tpb - 1) / tpb);
-            bin_sizes_kernel<<<grid_b, tpb, 0, st>>>(P, n, nb_ptr, nbm, c->sorted_keys, A, SC, c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(),
-                                                      c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>(), c->d_desc.as<fsb_bin_descriptor>());
-            launches++;
-        }
-        {
-            Ptr4<const uint64_t> in4{{c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(), c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>()}};
-            Ptr4<uint64_t> out4{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
-            launches += exclusive_scan4<uint64_t, uint64_t>(in4, nbm, out4, c->d_scan_tmp.as<uint64_t>(), st);
-        }
-        chunk_summary_kernel<<<c->n_chunks, 128, 0, st>>>(B, nb_ptr, A.bin_of, BO, c->d_desc.as<fsb_bin_descriptor>(), c->d_summary.as<ChunkSummary>());
-        launches++;
-    }
-    if (ev) CUDA_TRY(c, cudaEventRecord(ev[3], st));
-
-    // ---- K4: place ------------------------------------------------------------------------------------
-    if (n)
-    {
-        PlaceArgs pa{B, P, c->slot_geom, S, A, SC, BO, {{c->d_out[0].as<uint32_t>(), c->d_out[1].as<uint32_t>(), c->d_out[2].as<uint32_t>(), c->d_out[3].as<uint32_t>()}},
-                     c->d_slots.as<uint32_t>(), nb_ptr};
-        int place_launches = 0;
-        CUDA_TRY(c, launch_place(pa, c->max_len, c->max_head, st, &place_launches));
-        launches += place_launches;
-    }
-    if (ev)
-    {
-        CUDA_TRY(c, cudaEventRecord(ev[4], st));
-        c->pending_profiles++;
-    }
-    CUDA_TRY(c, cudaGetLastError());
-    c->stats.kernel_launches += launches;
-    c->stats.records += n;
-    c->ran = true;
-    return FSB_OK;
+    return run_enqueue(c, c->batch[0], c->profile);
 }
 
-// ------------------------------------------------------------------------------------------------
 extern "C" int fsb_fetch(fsb_ctx* c, fsb_block* blocks, uint32_t n_blocks)
 {
     if (!c || !blocks) return FSB_ERR_PARAM;
-    if (!c->ran) return fail(c, FSB_ERR_STATE, "fsb_fetch: fsb_run has not been called on the staged batch");
-    if (n_blocks != c->n_chunks) return fail(c, FSB_ERR_PARAM, "fsb_fetch: n_blocks must equal the number of staged chunks");
+    Batch& b = c->batch[0];
+    if (!b.ran) return fail(c, FSB_ERR_STATE, "fsb_fetch: fsb_run has not been called on the staged batch");
+    if (n_blocks != b.n_chunks) return fail(c, FSB_ERR_PARAM, "fsb_fetch: n_blocks must equal the number of staged chunks");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    const uint64_t n = c->n_records;
-    uint64_t d2h = 0;
-
-    CUDA_TRY(c, c->h_summary.ensure((size_t)c->n_chunks * sizeof(ChunkSummary)));
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_summary.p, c->d_summary.p, (size_t)c->n_chunks * sizeof(ChunkSummary), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(c, cudaStreamSynchronize(st));
-    d2h += (size_t)c->n_chunks * sizeof(ChunkSummary);
-    const ChunkSummary* sum = c->h_summary.as<ChunkSummary>();
-    const ChunkSummary& last = sum[c->n_chunks - 1];
-    uint64_t total[4], nb = last.first_bin + last.n_bins;
-    for (int s = 0; s < 4; ++s)
-    {
-        total[s] = last.off[s] + last.size[s];
-        if (total[s] > c->out_cap[s]) return fail(c, FSB_ERR_STATE, "internal error: stream size exceeds its bound");
-        CUDA_TRY(c, c->h_out[s].ensure(total[s] + 64));
-        if (total[s]) CUDA_TRY(c, cudaMemcpyAsync(c->h_out[s].p, c->d_out[s].p, total[s], cudaMemcpyDeviceToHost, st));
-        d2h += total[s];
-    }
-    CUDA_TRY(c, c->h_desc.ensure((nb + 1) * sizeof(fsb_bin_descriptor)));
-    if (nb) CUDA_TRY(c, cudaMemcpyAsync(c->h_desc.p, c->d_desc.p, nb * sizeof(fsb_bin_descriptor), cudaMemcpyDeviceToHost, st));
-    d2h += nb * sizeof(fsb_bin_descriptor);
-    if (c->per_read)
-    {
-        CUDA_TRY(c, c->h_sig.ensure((n + 1) * 4));
-        CUDA_TRY(c, c->h_info.ensure((n + 1) * 4));
-        if (n)
-        {
-            CUDA_TRY(c, cudaMemcpyAsync(c->h_sig.p, c->d_sig.p, n * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(c, cudaMemcpyAsync(c->h_info.p, c->d_info.p, n * 4, cudaMemcpyDeviceToHost, st));
-        }
-        d2h += 8 * n;
-    }
-    CUDA_TRY(c, cudaStreamSynchronize(st));
-    c->stats.d2h_bytes += d2h;
-
-    uint64_t alg_out = 0;
-    for (uint32_t ci = 0; ci < c->n_chunks; ++ci)
-    {
-        const ChunkSummary& s = sum[ci];
-        fsb_block& b = blocks[ci];
-        std::memset(&b, 0, sizeof(b));
-        b.meta = c->h_out[0].as<uint8_t>() + s.off[0]; b.meta_size = s.size[0];
-        b.dna = c->h_out[1].as<uint8_t>() + s.off[1];  b.dna_size = s.size[1];
-        b.qua = c->h_out[2].as<uint8_t>() + s.off[2];  b.qua_size = s.size[2];
-        b.head = c->h_out[3].as<uint8_t>() + s.off[3]; b.head_size = s.size[3];
-        b.raw_dna_size = s.raw_dna; b.raw_head_size = s.raw_head;
-        b.bins = c->h_desc.as<fsb_bin_descriptor>() + s.first_bin;
-        b.n_bins = s.n_bins;
-        b.n_records = c->chunk_first_rec[ci + 1] - c->chunk_first_rec[ci];
-        if (c->per_read)
-        {
-            b.read_signature = c->h_sig.as<uint32_t>() + c->chunk_first_rec[ci];
-            b.read_info = c->h_info.as<uint32_t>() + c->chunk_first_rec[ci];
-        }
-        alg_out += s.size[0] + s.size[1] + s.size[2] + s.size[3];
-    }
-    c->stats.algorithmic_bytes += c->algorithmic_in + alg_out;
+    HostOut* h = host_out(c, 0);
+    if (!h) return fail(c, FSB_ERR_NOMEM, "out of host memory");
+    int rc = summary_enqueue(c, b, *h, c->stream);
+    if (rc != FSB_OK) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    rc = fetch_enqueue(c, b, *h, c->stream);
+    if (rc != FSB_OK) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    fill_blocks(c, b, *h, blocks);
     return FSB_OK;
 }
 
+// ---- host buffers in, host blocks out ----------------------------------------------------------------------------
+// The chunk list is cut into sub-batches of at least sub_batch_records records (whole chunks) which
+// run as a pipeline over the two device buffer sets:
+//     s_h2d   : copy in g+1 ......... (waits until the kernels of g-1 have released that buffer set)
+//     stream  : kernels of g ........ (wait for copy in g, and for copy out g-2 to release the result buffers)
+//     s_d2h   : copy out g-1
+// The host only blocks on small things: the staging statistics of a sub-batch (they size the
+// buffers and carry the input validation) and its chunk summary (the stream sizes).
 extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks, fsb_block* blocks)
 {
-    int rc = fsb_stage(c, chunks, n_chunks);
-    if (rc != FSB_OK) return rc;
-    rc = fsb_run(c);
-    if (rc != FSB_OK) return rc;
-    return fsb_fetch(c, blocks, n_chunks);
+    if (!c || !blocks || (!chunks && n_chunks)) return FSB_ERR_PARAM;
+    if (n_chunks == 0) return fail(c, FSB_ERR_PARAM, "fsb_bin_chunks: no chunks");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+
+    // sub-batches: [first[g], first[g + 1])
+    const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(kMaxChunksPerBatch, 1ull << (32 - c->dp.key_bits));
+    std::vector<uint32_t> first{0};
+    {
+        uint64_t recs = 0;
+        for (uint32_t ci = 0; ci < n_chunks; ++ci)
+        {
+            if (ci > first.back() && (recs >= c->sub_batch_records || ci - first.back() >= max_chunks || recs + chunks[ci].n_records > kMaxBatchRecords))
+            {
+                first.push_back(ci);
+                recs = 0;
+            }
+            recs += chunks[ci].n_records;
+        }
+        first.push_back(n_chunks);
+    }
+    const uint32_t G = (uint32_t)first.size() - 1;
+    if (!c->s_h2d) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    if (!c->s_d2h) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (uint32_t g = 0; g < G; ++g) if (!host_out(c, g)) return fail(c, FSB_ERR_NOMEM, "out of host memory");
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // earlier work on the context (resident interface) is done
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_d2h));
+
+    int rc = FSB_OK;
+    auto drain = [&]() { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h); };
+    // copy out of sub-batch g: its summary is on the host once ev_run has fired
+    auto finish = [&](uint32_t g) -> int
+    {
+        Batch& b = c->batch[g & 1];
+        CUDA_TRY(c, cudaEventSynchronize(b.ev_run));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_d2h, b.ev_run, 0));
+        int r = fetch_enqueue(c, b, *c->host[g], c->s_d2h);
+        if (r != FSB_OK) return r;
+        CUDA_TRY(c, cudaEventRecord(b.ev_d2h, c->s_d2h));
+        // the batch object is reused two sub-batches later: describe the blocks now (the pointers are final,
+        // the bytes arrive before the call returns)
+        fill_blocks(c, b, *c->host[g], blocks + first[g]);
+        return FSB_OK;
+    };
+
+    rc = stage_enqueue(c, c->batch[0], chunks + first[0], first[1] - first[0], c->s_h2d);
+    if (rc == FSB_OK) { cudaError_t e = cudaEventRecord(c->batch[0].ev_h2d, c->s_h2d); if (e != cudaSuccess) rc = fail(c, FSB_ERR_CUDA, cudaGetErrorString(e)); }
+    for (uint32_t g = 0; g < G && rc == FSB_OK; ++g)
+    {
+        Batch& b = c->batch[g & 1];
+        if (cudaEventSynchronize(b.ev_h2d) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy to the device failed"); break; }
+        if (g >= 2 && cudaEventSynchronize(b.ev_d2h) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy from the device failed"); break; }   // result buffers of g-2 are free
+        if ((rc = stage_complete(c, b)) != FSB_OK) break;
+        if (cudaStreamWaitEvent(c->stream, b.ev_h2d, 0) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+        if ((rc = run_enqueue(c, b, false)) != FSB_OK) break;
+        if ((rc = summary_enqueue(c, b, *c->host[g], c->stream)) != FSB_OK) break;
+        if (cudaEventRecord(b.ev_run, c->stream) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
+        // copy out g-1 first: staging g+1 below reuses that batch object (and, once its kernels are done, its input buffers)
+        if (g >= 1 && (rc = finish(g - 1)) != FSB_OK) break;
+        if (g + 1 < G)
+        {
+            Batch& nx = c->batch[(g + 1) & 1];
+            if ((rc = stage_enqueue(c, nx, chunks + first[g + 1], first[g + 2] - first[g + 1], c->s_h2d)) != FSB_OK) break;
+            if (cudaEventRecord(nx.ev_h2d, c->s_h2d) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
+        }
+    }
+    if (rc == FSB_OK) rc = finish(G - 1);
+    drain();
+    if (rc == FSB_OK && cudaGetLastError() != cudaSuccess) rc = fail(c, FSB_ERR_CUDA, "CUDA error in the pipeline");
+    c->batch[0].staged = c->batch[0].ran = false;                // the resident interface starts from a fresh fsb_stage
+    return rc;
 }

@@ -144,15 +144,16 @@ typedef struct fsb_ctx fsb_ctx;
 enum {
     FSB_OPT_PER_READ = 1,    /* also return per-read signature/info arrays (parity Mode B)        */
     FSB_OPT_PROFILE = 2,     /* record CUDA events around every pipeline stage of fsb_run         */
-    FSB_OPT_VALIDATE = 3     /* device-side input validation (symbols / quality range), default 1 */
+    FSB_OPT_VALIDATE = 3,    /* device-side input validation (symbols / quality range), default 1 */
+    FSB_OPT_SUBBATCH_RECORDS = 4  /* fsb_bin_chunks pipelines sub-batches of at least this many records (default 400000) */
 };
 
 /* pipeline stages reported by fsb_stage_times (order of execution inside fsb_run) */
 enum {
-    FSB_STAGE_SIGNATURE = 0, /* K1: per-read minimizer signature, both strands                    */
+    FSB_STAGE_INGEST = 0,    /* K1: signature on both strands + prepacked per-record slots        */
     FSB_STAGE_SORT = 1,      /* K2/K3: histogram + scan + stable rank (radix passes)              */
     FSB_STAGE_LAYOUT = 2,    /* bin boundaries, per-bin length stats, bit-offset scans            */
-    FSB_STAGE_PACK = 3,      /* K4: bit-pack + scatter into the four streams                      */
+    FSB_STAGE_PLACE = 3,     /* K4: gather the slots and shift them into the four streams         */
     FSB_STAGE_COUNT = 4
 };
 
@@ -180,7 +181,8 @@ int fsb_set_option(fsb_ctx* ctx, int option, int64_t value);
 
 /*
  * Categorise + pack `n_chunks` chunks held in host memory: host->device copies, kernels,
- * device->host copies, synchronous.  blocks[i] describes chunk i.  This is the call that replaces
+ * device->host copies, synchronous; internally the chunks run as a pipeline of sub-batches so that
+ * the copies in both directions overlap the kernels.  blocks[i] describes chunk i.  This is the call that replaces
  * the Categorize + PackToBins pair at BinModule.cpp:130-133 / :379-382 and
  * BinOperator.cpp:97+205 / :375+472.
  */

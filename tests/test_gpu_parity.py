@@ -49,6 +49,40 @@ def test_multi_chunk_batch(paired):
         O.assert_blocks_equal(gpu_block_dict(got2[len(chunks) - 1 - ci]), want, f"chunk {ci} (reversed batch)")
 
 
+@pytest.mark.parametrize("paired", [False, True])
+def test_pipelined_sub_batches(paired):
+    """fsb_bin_chunks with every chunk as its own sub-batch: copies and kernels of neighbouring sub-batches
+    overlap on three streams over two buffer sets; every chunk must still yield exactly its own block."""
+    params = N.make_params(signature_len=8, skip_zone_len=0, paired_end=paired)
+    keep, chunks = [], []
+    for ci, (n, L) in enumerate([(6000, 100), (3, 100), (9000, 151), (2500, 36), (4097, 100), (7000, 120), (1, 50)]):
+        cfg = synth.synth_config(n, L, paired=paired, seed=700 + ci, first_index=ci * 100000, nrich=0.05, lowcomplex=0.05, alln=0.01, tie=0.02)
+        t = synth.generate(cfg, threads=2)
+        keep.append(t)
+        chunks.append(N.make_chunk(t[0], t[2], t[1], t[3]))
+    want = [O.bin_chunk("orc", params, ch) for ch in chunks]
+    with GpuBinner(params, per_read=True, sub_batch_records=1) as g:
+        for rep in range(2):                               # second call reuses every buffer
+            got = g.bin_chunks(chunks)
+            for ci in range(len(chunks)):
+                O.assert_blocks_equal(gpu_block_dict(got[ci]), want[ci], f"chunk {ci} (rep {rep})")
+        # a contract violation in a later sub-batch stops the pipeline cleanly
+        t1, t2, r1, r2 = keep[4]
+        bad = r1.copy()
+        bad["seq_off"][17] = t1.size
+        broken = list(chunks)
+        broken[4] = N.make_chunk(t1, bad, t2, r2)
+        with pytest.raises(FastoreError):
+            g.bin_chunks(broken)
+        got = g.bin_chunks(chunks[:3])
+        for ci in range(3):
+            O.assert_blocks_equal(gpu_block_dict(got[ci]), want[ci], f"chunk {ci} (after error)")
+    with GpuBinner(params, sub_batch_records=10000) as g:   # sub-batches of several chunks
+        got = g.bin_chunks(chunks)
+        for ci in range(len(chunks)):
+            O.assert_blocks_equal(gpu_block_dict(got[ci]), want[ci], f"chunk {ci} (grouped)", per_read=False)
+
+
 def test_stage_run_fetch_repeatable():
     params, chunk, keep = make_case("c2_pe150_lossless")
     want = O.bin_chunk("orc", params, chunk)
