@@ -83,6 +83,13 @@ class FshParseStats(C.Structure):
     ]
 
 
+class FshBinConfig(C.Structure):
+    _fields_ = [
+        ("params", FsbParams), ("min_block_bin_size", C.c_uint32), ("keep_comments", C.c_uint8), ("verbose", C.c_uint8),
+        ("reserved", C.c_uint8 * 2), ("fastq_block_size", C.c_uint64),
+    ]
+
+
 class FshSynthConfig(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64), ("first_index", C.c_uint64), ("n_records", C.c_uint64),
@@ -124,6 +131,22 @@ def host_lib() -> C.CDLL:
         lib.fsh_max_records.argtypes = [C.c_void_p, C.c_uint64]
         lib.fsh_cut_position.restype = C.c_uint64
         lib.fsh_cut_position.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        lib.fsh_reader_open.restype = C.c_void_p
+        lib.fsh_reader_open.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint64]
+        lib.fsh_reader_next.restype = C.c_int
+        lib.fsh_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.fsh_reader_close.restype = None
+        lib.fsh_reader_close.argtypes = [C.c_void_p]
+        lib.fsh_writer_open.restype = C.c_void_p
+        lib.fsh_writer_open.argtypes = [C.c_char_p, C.POINTER(FshBinConfig)]
+        lib.fsh_writer_add_titles.restype = C.c_int
+        lib.fsh_writer_add_titles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.fsh_writer_add_block.restype = C.c_int
+        lib.fsh_writer_add_block.argtypes = [C.c_void_p, C.c_void_p]
+        lib.fsh_writer_close.restype = C.c_int
+        lib.fsh_writer_close.argtypes = [C.c_void_p]
+        lib.fsh_last_error.restype = C.c_char_p
+        lib.fsh_last_error.argtypes = []
         lib.fsh_synth_size.restype = C.c_int
         lib.fsh_synth_size.argtypes = [C.POINTER(FshSynthConfig), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.fsh_synth_fill.restype = C.c_int

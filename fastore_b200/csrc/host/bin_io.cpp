@@ -1,0 +1,416 @@
+// bin_io.cpp -- host code either side of the device path: FASTQ chunk reader and bin-file writer.
+//
+// Restates, from their behaviour, IFastqStreamReaderSE/PE::ReadNextChunk (FastqStream.cpp:44-256),
+// FastqRawBlockStats::Update for titles (Stats.cpp:90-169, 205-236) and BinFileWriter
+// (BinFile.cpp:47-462).  The bytes these produce define chunk boundaries and the bin-file container,
+// so they have to be the reference's; tests/test_bin_files.py compares whole files with the output
+// of the reference's fastore_bin -t1.
+#include "host_api.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+// ---------------------------------------------------------------------------------------------------
+struct MultiFile                       // IMultiFileStreamReader::Read (FileStream.cpp:401-416): files back to back
+{
+    std::vector<std::string> names;
+    size_t next = 0;
+    FILE* f = nullptr;
+    bool open_next()
+    {
+        if (f) { std::fclose(f); f = nullptr; }
+        if (next >= names.size()) return false;
+        f = std::fopen(names[next++].c_str(), "rb");
+        if (f) std::setvbuf(f, nullptr, _IOFBF, 8u << 20);
+        return f != nullptr;
+    }
+    int64_t read(uint8_t* mem, uint64_t size)
+    {
+        if (!f) return 0;
+        int64_t n = (int64_t)std::fread(mem, 1, size, f);
+        while (n < (int64_t)size && open_next())
+        {
+            const size_t n2 = std::fread(mem + n, 1, size - n, f);
+            if (n2 > 0) n += (int64_t)n2;
+        }
+        return n;
+    }
+    ~MultiFile() { if (f) std::fclose(f); }
+};
+
+} // namespace
+
+struct fsh_reader
+{
+    bool paired = false, eof = false, uses_crlf = false;
+    uint64_t block = 0, window = 0;
+    MultiFile in[2];
+    std::vector<uint8_t> carry[2];
+
+    void skip_to_eol(const uint8_t* d, uint64_t& p, uint64_t size)        // FastqStream.h:47-62
+    {
+        while (p < size && d[p] != '\n' && d[p] != '\r') ++p;
+        if (p < size && d[p] == '\r' && p + 1 < size && d[p + 1] == '\n') { uses_crlf = true; ++p; }
+    }
+    uint64_t next_record_pos(const uint8_t* d, uint64_t pos, uint64_t size)   // GetNextRecordPos (FastqStream.cpp:15-40)
+    {
+        skip_to_eol(d, pos, size); ++pos;
+        while (pos < size && d[pos] != '@') { skip_to_eol(d, pos, size); ++pos; }
+        const uint64_t pos0 = pos;
+        skip_to_eol(d, pos, size); ++pos;
+        if (pos < size && d[pos] == '@') return pos;                        // pos0 was a quality line
+        return pos0;
+    }
+    static uint64_t next_read_id(const uint8_t* d, uint64_t max_len)       // ParseNextReadId (FastqStream.cpp:231-256)
+    {
+        static const char seps[] = " ._,=:/-#";                            // the reference's list also matches '\0'
+        const uint8_t* tag = nullptr;
+        uint64_t len = 0;
+        for (const uint8_t* p = d; p < d + max_len; ++p)
+        {
+            if (!(std::memchr(seps, *p, sizeof(seps)) != nullptr) && *p != '\n') continue;
+            if (!tag) tag = ++p;
+            else { len = (uint64_t)(p - tag); break; }
+        }
+        uint64_t v = 0;                                                    // to_num (Utils.h): decimal digits
+        for (uint64_t i = 0; tag && i < len; ++i) v = v * 10 + (uint64_t)(tag[i] - '0');
+        return v;
+    }
+};
+
+extern "C" fsh_reader* fsh_reader_open(const char* const* files1, uint32_t n1, const char* const* files2, uint32_t n2, uint64_t block_size)
+{
+    fsh_reader* r = new fsh_reader();
+    r->paired = n2 != 0;
+    r->block = block_size;
+    r->window = r->paired ? (1u << 20) : (1u << 13);                       // FastqStream.h:99,142
+    for (uint32_t i = 0; i < n1; ++i) r->in[0].names.push_back(files1[i]);
+    for (uint32_t i = 0; i < n2; ++i) r->in[1].names.push_back(files2[i]);
+    if (block_size <= r->window || n1 == 0 || !r->in[0].open_next() || (r->paired && !r->in[1].open_next()))
+    {
+        g_err = block_size <= r->window ? "block size must exceed the cut window" : "cannot open input file";
+        delete r;
+        return nullptr;
+    }
+    return r;
+}
+
+extern "C" void fsh_reader_close(fsh_reader* r) { delete r; }
+
+extern "C" int fsh_reader_next(fsh_reader* r, uint8_t* buf1, uint64_t* size1, uint8_t* buf2, uint64_t* size2)
+{
+    if (!r || !buf1 || !size1 || (r->paired && (!buf2 || !size2))) return -1;
+    *size1 = 0;
+    if (size2) *size2 = 0;
+    if (r->eof) return 0;
+    const int nf = r->paired ? 2 : 1;
+    uint8_t* buf[2] = {buf1, buf2};
+    uint64_t have[2] = {0, 0};
+    int64_t got[2] = {0, 0}, want[2] = {0, 0};
+    for (int m = 0; m < nf; ++m)
+    {
+        have[m] = r->carry[m].size();
+        if (have[m]) std::memcpy(buf[m], r->carry[m].data(), have[m]);
+        r->carry[m].clear();
+        want[m] = (int64_t)(r->block - have[m]);
+        got[m] = r->in[m].read(buf[m] + have[m], (uint64_t)want[m]);
+    }
+    uint64_t out[2] = {have[0], have[1]};
+    const bool full = got[0] == want[0] && (!r->paired || got[1] == want[1]);
+    if (full && (r->paired || got[0] > 0))
+    {
+        uint64_t end[2] = {0, 0};
+        for (int m = 0; m < nf; ++m) end[m] = r->next_record_pos(buf[m], r->block - r->window, r->block);
+        if (r->paired)
+        {
+            uint64_t id1 = fsh_reader::next_read_id(buf[0] + end[0], r->window), id2 = fsh_reader::next_read_id(buf[1] + end[1], r->window);
+            if (id1 < id2) { for (uint64_t i = 0, nl = (id2 - id1) * 4; i < nl; ++i) { r->skip_to_eol(buf[0], end[0], r->block); end[0]++; } id1 = id2; }
+            if (id1 > id2) { for (uint64_t i = 0, nl = (id1 - id2) * 4; i < nl; ++i) { r->skip_to_eol(buf[1], end[1], r->block); end[1]++; } }
+        }
+        for (int m = 0; m < nf; ++m)
+        {
+            out[m] = end[m] - 1 - (r->uses_crlf ? 1 : 0);
+            r->carry[m].assign(buf[m] + end[m], buf[m] + r->block);
+        }
+    }
+    else if (r->paired)
+    {
+        for (int m = 0; m < 2; ++m) if (got[m] > 0) out[m] = have[m] + (uint64_t)got[m] - 1 - (r->uses_crlf ? 1 : 0);   // drop the final line end
+        r->eof = true;
+    }
+    else
+    {
+        if (got[0] > 0) out[0] = have[0] + (uint64_t)got[0] - 1 - (r->uses_crlf ? 1 : 0);
+        r->eof = true;
+    }
+    *size1 = out[0];
+    if (size2) *size2 = out[1];
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct HeadField                        // FastqRawBlockStats::HeaderStats::Field (Stats.h:52-70)
+{
+    bool is_const = false, is_numeric = false;
+    char separator = 0;
+    uint64_t min_value = ~0ull, max_value = 0;
+    std::set<std::string> values;
+};
+
+bool is_num(const char* s, uint32_t len, uint64_t& v)                      // Utils.h:220-232
+{
+    v = 0;
+    uint32_t i;
+    for (i = 0; i < len; ++i)
+    {
+        if (s[i] < '0' || s[i] > '9') break;
+        v = v * 10 + (uint64_t)(s[i] - '0');
+    }
+    return i == len && (len == 1 || s[0] != '0');
+}
+
+struct BlockMeta                         // BinFileFooter::BlockMetaData: descriptor + file offsets, 11 x u64, dumped raw
+{
+    uint64_t meta_size, dna_size, qua_size, head_size, records, raw_dna, raw_head, meta_off, dna_off, qua_off, head_off;
+};
+struct BinInfo
+{
+    uint64_t total_meta = 0, total_dna = 0, total_qua = 0, total_head = 0, total_raw_dna = 0, total_raw_head = 0, total_records = 0;
+    std::vector<BlockMeta> blocks;
+};
+
+} // namespace
+
+struct fsh_writer
+{
+    fsh_bin_config cfg{};
+    FILE* f[4] = {nullptr, nullptr, nullptr, nullptr};                      // meta, dna, qua, head
+    uint64_t pos[4] = {0, 0, 0, 0};
+    uint64_t records = 0;
+    std::map<uint32_t, BinInfo> bins;
+    std::vector<HeadField> fields;
+
+    bool put(int s, const void* p, uint64_t n)
+    {
+        if (n && std::fwrite(p, 1, n, f[s]) != n) return false;
+        pos[s] += n;
+        return true;
+    }
+};
+
+extern "C" const char* fsh_last_error(void) { return g_err.c_str(); }
+
+extern "C" fsh_writer* fsh_writer_open(const char* prefix, const fsh_bin_config* cfg)
+{
+    if (!prefix || !cfg) return nullptr;
+    if (cfg->params.quality_method == FSB_QUA_QVZ) { g_err = "QVZ (-q3) bin files carry a codebook computed by fastore_pack code: not supported by this writer"; return nullptr; }
+    fsh_writer* w = new fsh_writer();
+    w->cfg = *cfg;
+    static const char* ext[4] = {".bmeta", ".bdna", ".bqua", ".bhead"};
+    for (int s = 0; s < 4; ++s)
+    {
+        if (s == 3 && !cfg->params.reads_have_headers) continue;
+        w->f[s] = std::fopen((std::string(prefix) + ext[s]).c_str(), "wb");
+        if (!w->f[s]) { g_err = std::string("cannot create ") + prefix + ext[s]; for (FILE* g : w->f) if (g) std::fclose(g); delete w; return nullptr; }
+        std::setvbuf(w->f[s], nullptr, _IOFBF, 8u << 20);
+    }
+    // the 40-byte header is written last (BinFile.cpp:283-284); skip it
+    static const uint8_t zeros[40] = {0};
+    w->put(0, zeros, 40);
+    return w;
+}
+
+// Titles of one parsed chunk -> header field statistics (Stats.cpp:90-169).
+extern "C" int fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const fsb_record* records, uint64_t n)
+{
+    if (!w || (!text && n) || (!records && n)) return FSB_ERR_PARAM;
+    if (!w->cfg.params.reads_have_headers) return FSB_OK;
+    static const char seps[] = " ./:#+";
+    for (uint64_t r = 0; r < n; ++r)
+    {
+        const char* head = (const char*)text + records[r].head_off;
+        const uint32_t hl = records[r].head_len;
+        uint32_t field_no = 0, start = 0;
+        for (uint32_t i = 0; i <= hl; ++i)
+        {
+            if (i != hl && !std::memchr(seps, head[i], 6)) continue;
+            const char* fs = head + start;
+            const uint32_t flen = i - start;
+            uint64_t v;
+            const bool numeric = is_num(fs, flen, v);
+            if (w->fields.size() < field_no + 1)
+            {
+                w->fields.emplace_back();
+                HeadField& f = w->fields.back();
+                f.is_const = true;
+                f.is_numeric = numeric;
+                if (numeric) f.min_value = f.max_value = v;
+                else { f.min_value = f.max_value = flen; f.values.insert(std::string(fs, flen)); }
+                if (i != hl) f.separator = head[i];
+            }
+            else
+            {
+                HeadField& f = w->fields[field_no];
+                if (numeric)
+                {
+                    f.min_value = std::min(f.min_value, v);
+                    f.max_value = std::max(f.max_value, v);
+                    f.is_const &= (f.min_value == f.max_value);
+                }
+                else
+                {
+                    f.values.insert(std::string(fs, flen));
+                    f.is_const &= f.values.size() == 1;
+                }
+            }
+            start = i + 1;
+            field_no++;
+        }
+    }
+    return FSB_OK;
+}
+
+// BinFileWriter::WriteNextBlock for a MultiSignatureType block (BinFile.cpp:85-153).
+extern "C" int fsh_writer_add_block(fsh_writer* w, const fsb_block* b)
+{
+    if (!w || !b) return FSB_ERR_PARAM;
+    const bool heads = w->cfg.params.reads_have_headers != 0;
+    uint64_t off[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < b->n_bins; ++i)
+    {
+        const fsb_bin_descriptor& d = b->bins[i];
+        w->records += d.records_count;
+        BinInfo& bi = w->bins[(uint32_t)d.signature];
+        BlockMeta m{d.meta_size, d.dna_size, d.qua_size, d.head_size, d.records_count, d.raw_dna_size, d.raw_head_size, w->pos[0], w->pos[1], w->pos[2], 0};
+        bi.total_meta += d.meta_size; bi.total_dna += d.dna_size; bi.total_qua += d.qua_size;
+        bi.total_raw_dna += d.raw_dna_size; bi.total_records += d.records_count;
+        bool ok = w->put(0, b->meta + off[0], d.meta_size) && w->put(1, b->dna + off[1], d.dna_size) && w->put(2, b->qua + off[2], d.qua_size);
+        off[0] += d.meta_size; off[1] += d.dna_size; off[2] += d.qua_size;
+        if (heads)
+        {
+            m.head_off = w->pos[3];
+            bi.total_raw_head += d.raw_head_size; bi.total_head += d.head_size;
+            ok = ok && w->put(3, b->head + off[3], d.head_size);
+            off[3] += d.head_size;
+        }
+        if (!ok) { g_err = "write failed"; return FSB_ERR_STATE; }
+        bi.blocks.push_back(m);
+    }
+    if (off[0] != b->meta_size || off[1] != b->dna_size || off[2] != b->qua_size || (heads && off[3] != b->head_size))
+    {
+        g_err = "block descriptors do not add up to the stream sizes";
+        return FSB_ERR_INPUT;
+    }
+    return FSB_OK;
+}
+
+namespace {
+
+struct ByteSink
+{
+    std::vector<uint8_t> v;
+    void u8(uint8_t x) { v.push_back(x); }
+    void be16(uint32_t x) { u8((uint8_t)(x >> 8)); u8((uint8_t)x); }
+    void be64(uint64_t x) { for (int i = 7; i >= 0; --i) u8((uint8_t)(x >> (8 * i))); }
+    void raw(const void* p, size_t n) { const uint8_t* q = (const uint8_t*)p; v.insert(v.end(), q, q + n); }
+};
+
+// the 88 bytes of BinModuleConfig (Params.h:167-193; offsets measured with the reference headers)
+void dump_config(const fsh_bin_config& c, uint8_t (&o)[88])
+{
+    std::memset(o, 0, 88);
+    const fsb_params& p = c.params;
+    o[0] = p.paired_end ? 1 : 0;                     // archiveType.readType
+    o[1] = p.quality_offset;                         // archiveType.qualityOffset
+    o[2] = p.reads_have_headers ? 1 : 0;             // archiveType.readsHaveHeaders
+    std::memcpy(o + 4, &c.min_block_bin_size, 4);    // catParams.minBlockBinSize
+    o[8] = p.signature_len; o[9] = p.skip_zone_len; o[10] = p.signature_mask_cutoff_bits;
+    std::memcpy(o + 11, p.dna_symbol_order, 5);      // minimizer.dnaSymbolOrder
+    o[16] = 0; o[17] = 6;                            // minFilter: filterLowQualitySignatures = false, lowQualityThreshold = 6
+    o[24] = p.quality_method; o[25] = p.binary_threshold;
+    o[32] = c.verbose ? 1 : 0; o[33] = c.verbose ? 1 : 0;   // qvzOpts.verbose, .stats (main.cpp:175-176, 236)
+    o[35] = 2;                                       // qvzOpts.distortion = DISTORTION_MSE (main.cpp:177)
+    const double D = 1.0;                            // qvzOpts.D (main.cpp:178)
+    std::memcpy(o + 56, &D, 8);
+    o[64] = c.keep_comments ? 1 : 0;                 // headParams.preserveComments
+    std::memcpy(o + 72, &c.fastq_block_size, 8);
+    const uint32_t level = 0;                        // binningLevel
+    std::memcpy(o + 80, &level, 4);
+    o[84] = 0;                                       // binningType = BIN_RECORDS
+}
+
+} // namespace
+
+// BinFileWriter::FinishCompress + WriteFileFooter + WriteFileHeader (BinFile.cpp:225-462).
+extern "C" int fsh_writer_close(fsh_writer* w)
+{
+    if (!w) return FSB_ERR_PARAM;
+    const fsb_params& p = w->cfg.params;
+    const bool heads = p.reads_have_headers != 0;
+    const uint64_t footer_offset = w->pos[0];
+    ByteSink s;
+    uint8_t cfg88[88];
+    dump_config(w->cfg, cfg88);
+    s.raw(cfg88, 88);
+    {   // occupancy bitmap: 4^k + 1 bits, MSB first, padded to a byte (BinFile.cpp:326-343)
+        const uint64_t nbits = (1ull << (2 * p.signature_len)) + 1;
+        std::vector<uint8_t> bm((nbits + 7) / 8, 0);
+        for (const auto& kv : w->bins) bm[kv.first >> 3] |= (uint8_t)(0x80u >> (kv.first & 7));
+        s.raw(bm.data(), bm.size());
+    }
+    for (const auto& kv : w->bins)
+    {
+        const BinInfo& b = kv.second;
+        s.be64(b.total_meta); s.be64(b.total_dna); s.be64(b.total_qua); s.be64(b.total_raw_dna); s.be64(b.total_records);
+        if (heads) { s.be64(b.total_head); s.be64(b.total_raw_head); }
+        s.be64(b.blocks.size());
+        s.raw(b.blocks.data(), b.blocks.size() * sizeof(BlockMeta));
+    }
+    if (heads)
+    {
+        s.u8((uint8_t)w->fields.size());
+        for (const HeadField& f : w->fields)
+        {
+            s.u8(f.is_numeric); s.u8(f.is_const); s.u8((uint8_t)f.separator);
+            if (f.is_numeric)
+            {
+                s.be64(f.min_value);
+                if (!f.is_const) s.be64(f.max_value);
+            }
+            else
+            {
+                if (!f.is_const) s.be16((uint32_t)f.values.size());
+                for (const std::string& v : f.values) { s.u8((uint8_t)v.size()); s.raw(v.data(), v.size()); }
+            }
+        }
+        if (p.paired_end)
+        {   // the last numeric field spanning exactly 1..2 tells the mates apart (BinFile.cpp:436-455)
+            uint32_t idx = 0;
+            for (int32_t i = (int32_t)w->fields.size() - 1; i >= 0; --i)
+                if (w->fields[i].is_numeric && w->fields[i].min_value == 1 && w->fields[i].max_value == 2) { idx = (uint32_t)i; break; }
+            s.u8((uint8_t)idx);
+        }
+    }
+    bool ok = w->put(0, s.v.data(), s.v.size());
+    // header: footerOffset, recordsCount, blockCount (= distinct bins), footerSize, usesHeaderStream, 7 reserved (BinFile.h:106-118)
+    uint8_t hdr[40] = {0};
+    const uint64_t h64[4] = {footer_offset, w->records, (uint64_t)w->bins.size(), (uint64_t)s.v.size()};
+    std::memcpy(hdr, h64, 32);
+    hdr[32] = heads ? 1 : 0;
+    ok = ok && std::fseek(w->f[0], 0, SEEK_SET) == 0 && std::fwrite(hdr, 1, 40, w->f[0]) == 40;
+    for (FILE* f : w->f) if (f && std::fclose(f) != 0) ok = false;
+    delete w;
+    if (!ok) { g_err = "write failed"; return FSB_ERR_STATE; }
+    return FSB_OK;
+}

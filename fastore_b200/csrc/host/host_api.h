@@ -4,6 +4,8 @@
  *
  *   fsh_parse_*   FASTQ record parser  -> record table for the C ABI   (mirrors FastqParser.cpp:118-165)
  *   fsh_cut_*     FASTQ chunk cutter                                   (mirrors FastqStream.cpp:15-256)
+ *   fsh_reader_*  FASTQ chunk reader (SE / PE with read-id re-synchronisation) (FastqStream.cpp:44-256)
+ *   fsh_writer_*  bin-file writer: .bmeta / .bdna / .bqua / .bhead          (BinFile.cpp:47-462, Stats.cpp:63-170)
  *   fsh_synth_*   seeded synthetic FASTQ generator used by tests and bench.py
  */
 #ifndef FASTORE_HOST_API_H
@@ -60,6 +62,49 @@ uint64_t fsh_max_records(const uint8_t* text, uint64_t size);
  * byte of the record that begins the *next* chunk.
  */
 uint64_t fsh_cut_position(const uint8_t* buf, uint64_t size, uint64_t window);
+
+/* ---- chunk reader ---------------------------------------------------------------------------- */
+
+/*
+ * Reads FASTQ files chunk by chunk exactly like IFastqStreamReaderSE/PE::ReadNextChunk
+ * (FastqStream.cpp:44-101, 104-228): a buffer of `block_size` bytes per file is filled (carried
+ * tail first, then the files one after the other), cut at the first record start after
+ * block_size - window (window = 8 KiB SE, 1 MiB PE; FastqStream.h:99,142), in PE mode both cuts are
+ * re-synchronised on the numeric read id of the next title (FastqStream.cpp:231-256); the chunk
+ * loses its final line end, the rest is carried over.  Chunk boundaries define block boundaries,
+ * so they must be the reference's.
+ */
+typedef struct fsh_reader fsh_reader;
+fsh_reader* fsh_reader_open(const char* const* files1, uint32_t n1, const char* const* files2, uint32_t n2, uint64_t block_size);
+/* buf1 / buf2: block_size bytes each (buf2 unused for SE).  Returns 1 (chunk delivered), 0 (end of input), -1 (I/O error). */
+int  fsh_reader_next(fsh_reader* r, uint8_t* buf1, uint64_t* size1, uint8_t* buf2, uint64_t* size2);
+void fsh_reader_close(fsh_reader* r);
+
+/* ---- bin-file writer -------------------------------------------------------------------------- */
+
+/* The fields of BinModuleConfig (Params.h:167-193) that are not binning parameters of the device path. */
+typedef struct fsh_bin_config {
+    fsb_params params;
+    uint32_t min_block_bin_size;   /* -m, CategorizerParameters::minBlockBinSize (8) */
+    uint8_t  keep_comments;        /* !-C, HeadersCompressionParams::preserveComments */
+    uint8_t  verbose;              /* -v (sets qvzOpts.verbose / stats in the dumped parameters, main.cpp:236) */
+    uint8_t  reserved[2];
+    uint64_t fastq_block_size;     /* -b in bytes */
+} fsh_bin_config;
+
+/*
+ * Writes <prefix>.bmeta / .bdna / .bqua [/ .bhead] byte for byte like BinFileWriter
+ * (StartCompress / WriteNextBlock / FinishCompress / WriteFileFooter, BinFile.cpp:47-462), except
+ * that the never-initialised padding bytes of the 88-byte parameter dump are written as zeros.
+ * QVZ (-q3) footers carry a codebook computed by fastore_pack code and are not supported here.
+ */
+typedef struct fsh_writer fsh_writer;
+fsh_writer* fsh_writer_open(const char* prefix, const fsh_bin_config* cfg);
+/* FastqRawBlockStats::Update for the titles of one parsed chunk (mate 1, and mate 2 in PE mode): Stats.cpp:90-169 */
+int  fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const fsb_record* records, uint64_t n_records);
+int  fsh_writer_add_block(fsh_writer* w, const fsb_block* block);          /* WriteNextBlock */
+int  fsh_writer_close(fsh_writer* w);                                      /* FinishCompress; frees w */
+const char* fsh_last_error(void);
 
 /* ---- synthetic FASTQ --------------------------------------------------------------------------*/
 
