@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path (K1 signature -> stable sort -> layout scans -> K4 pack) over
+A "step" is one pass of the hot path (K1 ingest -> stable sort -> layout scans -> K4 place) over
 one batch of synthetic FASTQ chunks.  Workload at N=1: BASELINE.json configs[1] -- 10 M synthetic
 150 bp paired-end reads (pairs), lossless binning parameters (-z -H -q0 -p8 -s0), cut into chunks of
 the size the reference's `-b256` chunk cutter produces.  At N>1 every rank bins its own 10 M-pair
@@ -271,12 +271,10 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from fastore_b200 import sharding
+
     def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, device="cuda")
 
     stream = torch.cuda.Stream()
     g = GpuBinner(params, device=local, stream=stream.cuda_stream, profile=True)
@@ -336,8 +334,15 @@ def run_b200_arm(args):
     peak, peak_src = load_peaks()
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     dom_ms = stage_ms[dom] / max(runs, 1)
+    traffic = None
+    try:                                               # dram__bytes_read + write per pair of the dominant kernel, from the committed ncu capture
+        tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        if dom in tj["bytes_per_pair"]:
+            traffic = tj["bytes_per_pair"][dom] * n_pairs
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": alg_bytes / (dom_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": alg_bytes / (dom_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "frac": alg_bytes / (dom_ms / 1e3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes,
             "whole_path_achieved": alg_bytes / (ms_per_step / 1e3) / 1e9,
             "whole_path_frac": alg_bytes / (ms_per_step / 1e3) / 1e9 / peak,
