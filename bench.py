@@ -249,6 +249,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from fastore_b200 import _native as N

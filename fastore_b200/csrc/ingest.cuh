@@ -42,6 +42,7 @@ template <int NW> constexpr uint32_t win_slot_bytes() { return ((win_pieces<NW>(
 struct IngestPlan
 {
     uint32_t warps;          // warps per block
+    uint32_t stg_stride;     // words per record in the slot staging: G.words + 4, so that the lanes' stores spread over the banks
     uint32_t head_pieces;    // 16-byte pieces per title window incl. the guard piece (0: no titles)
     uint32_t off_head, off_staging, total_bytes;
 };
@@ -51,6 +52,7 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
 {
     IngestPlan pl{};
     pl.head_pieces = P.has_headers ? ((15u + max_head + 15u) >> 4) + 1u : 0u;
+    pl.stg_stride = G.words + 4u;
     const uint32_t recs = P.paired ? 16u : 32u;                      // records per warp
     for (pl.warps = 4; ; pl.warps >>= 1)
     {
@@ -60,31 +62,25 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
         o += pl.warps * recs * pl.head_pieces * 16u;
         o += 32;                                                     // back pad: forward readers run up to 19 bytes past a window
         pl.off_staging = o;
-        o += pl.warps * recs * G.words * 4u;
+        o += pl.warps * recs * pl.stg_stride * 4u;
         pl.total_bytes = o;
         if (o <= 56u * 1024u || pl.warps == 1) break;
     }
     return pl;
 }
 
-// A warp copies the aligned windows around its 32 lanes' spans: LPM lanes per span so that
-// consecutive lanes request consecutive 16-byte pieces.
+// Every lane copies the aligned window around its own span, one 16-byte piece per step.  (Spreading a
+// span over several lanes would coalesce the requests, but costs two shuffles and an index
+// computation per piece; K1 is bound by the integer pipe, not by the load path, and every line is
+// still fetched from HBM exactly once.)
 template <int NW>
-__device__ __forceinline__ void gather_windows(uint8_t* warp_slots, uint32_t piece0, uint32_t npieces, const uint8_t* text0, const uint8_t* text1, bool paired)
+__device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece0, uint32_t npieces, const uint8_t* text)
 {
-    constexpr uint32_t PW = win_pieces<NW>(), SB = win_slot_bytes<NW>();
-    constexpr int LPM = PW <= 16 ? 16 : 32, PER_IT = 32 / LPM;
-    const unsigned lane = threadIdx.x & 31;
-#pragma unroll 4
-    for (int it = 0; it < 32 / PER_IT; ++it)
-    {
-        const int src = it * PER_IT + (int)(lane / LPM);
-        const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, piece0, src);
-        const uint32_t np = __shfl_sync(0xFFFFFFFFu, npieces, src);
-        const unsigned j = lane % LPM;
-        const uint8_t* base = (paired && (src & 1)) ? text1 : text0;
-        if (j < np) cp_async16(warp_slots + (size_t)src * SB + 16u + 16u * j, base + ((uint64_t)(p0 + j) << 4));
-    }
+    constexpr uint32_t PW = win_pieces<NW>();
+    const uint8_t* src = text + (piece0 << 4);
+#pragma unroll
+    for (uint32_t j = 0; j < PW; ++j)
+        if (j < npieces) cp_async16(my_window + 16u + 16u * j, src + 16u * j);
 }
 
 // K1.  NW = ceil(longest read of the batch / 32).
@@ -103,7 +99,7 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
     const uint32_t recs_per_warp = P.paired ? 16u : 32u;
     uint8_t* wslots = smem + 16 + (size_t)warp * 32 * SB;
     uint8_t* hslots = smem + pl.off_head + (size_t)warp * recs_per_warp * pl.head_pieces * 16u;
-    uint32_t* stg = reinterpret_cast<uint32_t*>(smem + pl.off_staging) + (size_t)warp * recs_per_warp * G.words;
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smem + pl.off_staging) + (size_t)warp * recs_per_warp * pl.stg_stride;
 
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
     const uint64_t g0 = ((uint64_t)blockIdx.x * pl.warps + warp) * 32;             // first mate of this warp
@@ -115,7 +111,8 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
     const uint32_t lrec = P.paired ? (lane >> 1) : lane;                            // record index inside the warp
 
     uint32_t L = 0, a_seq = 0, a_qua = 0, a_head = 0, H = 0, ch = 0;
-    uint32_t seq_p0 = 0, seq_np = 0, qua_p0 = 0, qua_np = 0, head_p0 = 0, head_np = 0;
+    uint64_t seq_p0 = 0, qua_p0 = 0;
+    uint32_t seq_np = 0, qua_np = 0, head_p0 = 0, head_np = 0;
     if (live)
     {
         ch = find_chunk(B, i);
@@ -123,8 +120,8 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
         const uint64_t tb = (m ? B.chunk_text_base[1] : B.chunk_text_base[0])[ch];
         L = r.seq_len;
         const uint64_t so = tb + r.seq_off, qo = tb + r.qua_off;
-        a_seq = (uint32_t)(so & 15u); seq_p0 = (uint32_t)(so >> 4); seq_np = (a_seq + L + 15u) >> 4;
-        a_qua = (uint32_t)(qo & 15u); qua_p0 = (uint32_t)(qo >> 4); qua_np = (a_qua + L + 15u) >> 4;
+        a_seq = (uint32_t)(so & 15u); seq_p0 = so >> 4; seq_np = (a_seq + L + 15u) >> 4;
+        a_qua = (uint32_t)(qo & 15u); qua_p0 = qo >> 4; qua_np = (a_qua + L + 15u) >> 4;
         if (m == 0 && P.has_headers)
         {
             const uint64_t ho = tb + r.head_off;
@@ -133,7 +130,9 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
         }
     }
     // ---- stage the sequences and the titles; clear the slot staging meanwhile ------------------------------
-    gather_windows<NW>(wslots, seq_p0, seq_np, B.text[0], B.text[1], P.paired != 0);
+    uint8_t* my_window = wslots + (size_t)lane * SB;
+    const uint8_t* my_text = m ? B.text[1] : B.text[0];
+    gather_window<NW>(my_window, seq_p0, seq_np, my_text);
     if (pl.head_pieces)
     {
         const uint32_t hp = pl.head_pieces - 1u, step = P.paired ? 2u : 1u;
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
     for (int j = 0; j < NW; ++j) { Hp.w[j] = 0; Lp.w[j] = 0; Np.w[j] = 0; }
     if (live) mate_planes<NW>(win_words + 4 + (a_seq >> 2), 8u * (a_seq & 3u), L, Hp, Lp, Np);
     __syncwarp();                                                 // every lane is done with its sequence window
-    gather_windows<NW>(wslots, qua_p0, qua_np, B.text[0], B.text[1], P.paired != 0);
+    gather_window<NW>(my_window, qua_p0, qua_np, my_text);
     cp_async_commit();
 
     // ---- signature -------------------------------------------------------------------------------------------
@@ -188,7 +187,7 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
     const uint32_t lenA = roleB ? Lother : L, lenB = P.paired ? (roleB ? L : Lother) : 0u;
     const bool plainA = (inf & FSB_INFO_PLAIN_A) != 0;
     const uint32_t sfx = nbin ? 0u : P.k;
-    uint32_t* my_slot = stg + (size_t)lrec * G.words;
+    uint32_t* my_slot = stg + (size_t)lrec * pl.stg_stride;
 
     // ---- DNA of this mate in the stored orientation (StoreDna), straight from the planes ----------------------------
     SegEmit ed = seg_open(my_slot, 0, 0), eh = ed, eq = ed;
@@ -231,11 +230,16 @@ __global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P
     {
         const uint64_t rec0 = P.paired ? (g0 >> 1) : g0;
         const uint64_t nrec = min((uint64_t)recs_per_warp, B.n_records - rec0);
-        const uint4* sv = reinterpret_cast<const uint4*>(stg);
         uint4* gv = reinterpret_cast<uint4*>(slots + rec0 * G.words);
-        const uint32_t nvec = (uint32_t)nrec * (G.words / 4);
-#pragma unroll 4
-        for (uint32_t j = lane; j < nvec; j += 32) gv[j] = sv[j];
+        const uint32_t vpr = G.words >> 2, nvec = (uint32_t)nrec * vpr;            // 16-byte vectors per record / in all
+        uint32_t rec = lane / vpr, piece = lane - rec * vpr;                        // staging keeps 4 pad words per record
+        const uint32_t drec = 32u / vpr, dpiece = 32u - drec * vpr;
+        for (uint32_t j = lane; j < nvec; j += 32)
+        {
+            gv[j] = *reinterpret_cast<const uint4*>(stg + (size_t)rec * pl.stg_stride + 4u * piece);
+            rec += drec; piece += dpiece;
+            if (piece >= vpr) { piece -= vpr; rec += 1; }
+        }
     }
 }
 

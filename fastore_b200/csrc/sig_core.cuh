@@ -103,20 +103,46 @@ FSB_HD void candidate_masks(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm,
     Cr = bv_andn(bv_andn(bv_range<NW>((int32_t)P.s + 1, (int32_t)L - (int32_t)k + 1), badR), Nw);
 }
 
-// Radix descent, forward strand.  D tracks the candidates shifted onto the symbol under test.
 // One bit step of the descent: keep the candidates whose key bit is 0 if there are any.  `plane`
-// holds the key bit (inv = false) or its complement (inv = true) at the candidates' positions.
-// Written so that a step is NW and-nots, an OR tree, one compare and NW three-input logic ops.
-template <int NW>
-FSB_HD uint32_t descend_step(BV<NW>& D, const BV<NW>& plane, bool inv)
+// holds the key bit (INV = false) or its complement (INV = true) at the candidates' positions.
+// A step is NW and-nots into an OR tree, one compare and NW three-input logic ops; the mask form is
+// spelled out as LOP3s because, left to itself, the compiler turns it into a select per word.
+FSB_HD uint32_t mask_nonzero(uint32_t o)                         // o != 0 ? 0xFFFFFFFF : 0
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("set.ne.u32.u32 %0, %1, 0;" : "=r"(r) : "r"(o));
+    return r;
+#else
+    return o ? 0xFFFFFFFFu : 0u;
+#endif
+}
+template <bool INV> FSB_HD uint32_t drop_ones(uint32_t d, uint32_t am, uint32_t plane)     // d & ~(am & key bit)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    if (INV) asm("lop3.b32 %0, %1, %2, %3, 0xB0;" : "=r"(r) : "r"(d), "r"(am), "r"(plane));      // a & ~(b & ~c)
+    else asm("lop3.b32 %0, %1, %2, %3, 0x70;" : "=r"(r) : "r"(d), "r"(am), "r"(plane));          // a & ~(b & c)
+    return r;
+#else
+    return d & ~(am & (INV ? ~plane : plane));
+#endif
+}
+template <int NW, bool INV>
+FSB_HD uint32_t descend_step_t(BV<NW>& D, const BV<NW>& plane)
 {
     uint32_t o = 0;
 #pragma unroll
-    for (int j = 0; j < NW; ++j) o |= D.w[j] & (inv ? plane.w[j] : ~plane.w[j]);
-    const uint32_t am = o ? 0xFFFFFFFFu : 0u;                   // any candidate with a 0 bit: drop those with a 1 bit
+    for (int j = 0; j < NW; ++j) o |= D.w[j] & (INV ? plane.w[j] : ~plane.w[j]);
+    const uint32_t am = mask_nonzero(o);                        // any candidate with a 0 bit: drop those with a 1 bit
 #pragma unroll
-    for (int j = 0; j < NW; ++j) D.w[j] &= ~(am & (inv ? ~plane.w[j] : plane.w[j]));
-    return o ? 0u : 1u;
+    for (int j = 0; j < NW; ++j) D.w[j] = drop_ones<INV>(D.w[j], am, plane.w[j]);
+    return am + 1u;                                             // 0 if a candidate had a 0 bit, else 1
+}
+template <int NW>
+FSB_HD uint32_t descend_step(BV<NW>& D, const BV<NW>& plane, bool inv)
+{
+    return inv ? descend_step_t<NW, true>(D, plane) : descend_step_t<NW, false>(D, plane);
 }
 
 // Radix descent, forward strand.  D tracks the candidates shifted onto the symbol under test.

@@ -47,3 +47,17 @@ def test_reference_decoder_reads_our_files(tmp_path, paired):
     BF.decode_with_reference(tmp_path / "ours", outs, paired)
     for src, dec in zip(files, outs):
         assert sorted(BF.fastq_records(src)) == sorted(BF.fastq_records(dec))
+
+
+@pytest.mark.gpu
+def test_cli_on_all_gpus_is_byte_identical(tmp_path):
+    """Chunk i -> GPU i mod G with an ordered writer turn: the files do not depend on the number of GPUs."""
+    from fastore_b200 import _native as N
+    G = N.cuda_lib().fsb_device_count()
+    if G < 2:
+        pytest.skip("needs at least 2 GPUs")
+    files = BF.write_fastq(tmp_path, "mg", 40000, 150, True, 220)
+    flags = dict(paired=True, b=2)
+    BF.run_reference_bin(files, tmp_path / "ref", flags)
+    BF.run_cli(files, tmp_path / "ours", flags, gpus=G)
+    BF.assert_bin_files_equal(tmp_path / "ours", tmp_path / "ref", True)
