@@ -96,25 +96,27 @@ FSB_HD uint32_t card_head(uint64_t c) { return (uint32_t)(c >> 28) & 0xFFu; }
 // ---- the per-record slot K1 writes and K4 gathers -----------------------------------------------------------
 // One slot per record (pair) in input order, 128-byte aligned so that a gather by sorted index only
 // touches lines it uses completely.  It holds the record's contribution to the quality, title and
-// DNA streams exactly as they will appear in the output (stored orientation, MSB-first), each
-// region starting at bit 0 of a 16-byte aligned word offset:
-//   [0, qw)            quality of stored mate A then B      (lenA + lenB) * q bits
-//   [qw, qw + hw)      title: 8 bits headLen + 7 bits/char   (mate-1 title)
-//   [qw + hw, words)   DNA of mate A without the signature, then mate B, 2 or 3 bits per symbol
+// DNA streams exactly as they will appear in the output (stored orientation, MSB-first):
+//   [0, wqa)          quality of stored mate A, from bit 0       lenA * q bits
+//   [wqa, 2 wqa)      quality of stored mate B (PE), from bit 0  lenB * q bits
+//   [qw, qw + tw)     title (8 bits headLen + 7 bits/char of the mate-1 title) immediately followed by
+//                     the DNA of mate A without the signature, then mate B, 2 or 3 bits per symbol
+// wqa is a multiple of 4 words, so both quality regions are 16-byte aligned; qw = mates * wqa.
 struct SlotGeom
 {
-    uint32_t qw, hw, dw;     // region sizes in 32-bit words, multiples of 4
+    uint32_t wqa;            // words of one mate's quality region (multiple of 4)
+    uint32_t qw, tw;         // words of the quality regions together / of the title + DNA region
     uint32_t words;          // slot stride in words, multiple of 32 (128 bytes)
 };
 inline SlotGeom make_slot_geom(const DeviceParams& P, uint32_t max_len, uint32_t max_head)
 {
     SlotGeom g{};
     const uint32_t mates = P.paired ? 2u : 1u;
-    auto up4 = [](uint32_t bits) { return (((bits + 31u) >> 5) + 3u) & ~3u; };
-    g.qw = up4(mates * max_len * P.qua_bits);
-    g.hw = P.has_headers ? up4(8u + 7u * (max_head ? max_head - 1u : 0u)) : 0u;
-    g.dw = up4(mates * max_len * 3u);
-    g.words = (g.qw + g.hw + g.dw + 31u) & ~31u;
+    auto words = [](uint32_t bits) { return (bits + 31u) >> 5; };
+    g.wqa = (words(max_len * P.qua_bits) + 3u) & ~3u;
+    g.qw = mates * g.wqa;
+    g.tw = words((P.has_headers ? 8u + 7u * (max_head ? max_head - 1u : 0u) : 0u) + mates * max_len * 3u);
+    g.words = (g.qw + g.tw + 31u) & ~31u;
     return g;
 }
 
@@ -167,6 +169,17 @@ FSB_HD uint32_t bswap32(uint32_t x)
     return __builtin_bswap32(x);
 #endif
 }
+FSB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel)     // result byte i = pool[(sel >> 4i) & 7], pool = x (0..3), y (4..7)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t pool = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
 FSB_HD uint32_t bit_length_u32(uint32_t x) { return x ? 32u - clz32(x) : 0u; }     // Utils.h:235-243 for x < 2^31
 
 // ---- bit vectors of 32*NW positions: position p is bit (p & 31) of word (p >> 5) -----------------
@@ -205,18 +218,32 @@ template <int NW> FSB_HD uint32_t bv_popc(const BV<NW>& a) { uint32_t o = 0;
 #pragma unroll
     for (int j = 0; j < NW; ++j) o += popc32(a.w[j]); return o; }
 
+// bits [0, hi) of one word for any hi (negative: none, 32 and more: all).  The device form leans on
+// shl.b32 clamping shift counts above 31 (the result is 0).
+FSB_HD uint32_t below_mask(int32_t hi)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(0xFFFFFFFFu), "r"((uint32_t)max(hi, 0)));
+    return ~r;
+#else
+    return hi <= 0 ? 0u : (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u));
+#endif
+}
 // bits [a, b) set (a, b may be negative or beyond the vector)
 template <int NW> FSB_HD BV<NW> bv_range(int32_t a, int32_t b)
 {
     BV<NW> r;
 #pragma unroll
-    for (int j = 0; j < NW; ++j)
-    {
-        const int32_t lo = a - 32 * j, hi = b - 32 * j;
-        const uint32_t mlo = lo <= 0 ? 0u : (lo >= 32 ? 0xFFFFFFFFu : ((1u << lo) - 1u));   // bits below a
-        const uint32_t mhi = hi <= 0 ? 0u : (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u));   // bits below b
-        r.w[j] = mhi & ~mlo;
-    }
+    for (int j = 0; j < NW; ++j) r.w[j] = below_mask(b - 32 * j) & ~below_mask(a - 32 * j);
+    return r;
+}
+// bits [0, b) set
+template <int NW> FSB_HD BV<NW> bv_below(int32_t b)
+{
+    BV<NW> r;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) r.w[j] = below_mask(b - 32 * j);
     return r;
 }
 // r[p] = OR of x[p .. p + width), width in [1, 32]

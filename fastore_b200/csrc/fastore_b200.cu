@@ -173,7 +173,13 @@ cudaError_t launch_ingest_q(const BatchView& B, const DeviceParams& P, const Slo
     cudaError_t e = cudaFuncSetAttribute(ingest_kernel<NW, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
     if (e != cudaSuccess) return e;
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
-    const unsigned blocks = (unsigned)((n_mates + pl.warps * 32 - 1) / (pl.warps * 32));
+    // persistent warps: as many blocks as fit on the device at once, each warp strides over the warp batches
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ingest_kernel<NW, Q>, (int)(pl.warps * 32), pl.total_bytes)) != cudaSuccess) return e;
+    const uint64_t need = (n_mates + pl.warps * 32 - 1) / (pl.warps * 32);
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
     ingest_kernel<NW, Q><<<blocks, pl.warps * 32, pl.total_bytes, st>>>(B, P, G, pl, keys, cards, slots, sig, info);
     return cudaGetLastError();
 }

@@ -32,214 +32,360 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t shared_addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t shared_addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(shared_addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int NW> constexpr uint32_t win_pieces() { return 2 * NW + 1; }      // 16-byte pieces of the aligned window around L <= 32 NW bytes
-// + one guard piece in front; an odd number of pieces per window keeps the lanes' windows on different banks
-template <int NW> constexpr uint32_t win_slot_bytes() { return ((win_pieces<NW>() + 1) | 1u) * 16; }
+// An odd number of pieces per window keeps the lanes' windows on different banks.  A lane's pieces
+// start 16 bytes into its window slot, i.e. they end 16 bytes into the next lane's slot: what a
+// reversed reader sees when it looks 4 bytes below its first piece is the previous lane's last
+// piece (or the front pad), which is harmless.
+template <int NW> constexpr uint32_t win_slot_bytes() { return win_pieces<NW>() * 16; }
+
+constexpr uint32_t kSmemChunkTable = 32;     // chunk tables of batches with at most this many chunks are kept in shared memory
+#ifndef FSB_K1_WARPS
+#define FSB_K1_WARPS 8
+#endif
+#ifndef FSB_K1_MINBLOCKS
+#define FSB_K1_MINBLOCKS 3
+#endif
+constexpr uint32_t kIngestMaxWarps = FSB_K1_WARPS;      // warps per block (launch bound)
 
 struct IngestPlan
 {
     uint32_t warps;          // warps per block
-    uint32_t stg_stride;     // words per record in the slot staging: G.words + 4, so that the lanes' stores spread over the banks
+    uint32_t stg_stride;     // words per record in the title + DNA staging (a multiple of 4, not of 8: the lanes' stores spread over the banks)
     uint32_t head_pieces;    // 16-byte pieces per title window incl. the guard piece (0: no titles)
-    uint32_t off_head, off_staging, total_bytes;
+    uint32_t off_head, off_staging, off_lut, off_chunks, total_bytes;
+    uint32_t blocks_per_sm;
 };
 
+// the bit-spreading tables of pack_core.cuh; every block copies them into shared memory
+__device__ const SpreadLut g_spread_lut = SpreadLut();
+
+// Shared memory of a block of `warps` warps:
+//   sequence / quality windows   32 per warp; once the qualities are packed they also stage the slots' quality regions
+//   title windows                one per record
+//   title + DNA staging          one region of G.tw words per record
+//   spreading tables, chunk tables
 template <int NW>
-inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uint32_t max_head)
+inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t smem_per_sm = 227u * 1024u)
 {
-    IngestPlan pl{};
-    pl.head_pieces = P.has_headers ? ((15u + max_head + 15u) >> 4) + 1u : 0u;
-    pl.stg_stride = G.words + 4u;
+    IngestPlan best{};
+    uint32_t best_warps_per_sm = 0;
     const uint32_t recs = P.paired ? 16u : 32u;                      // records per warp
-    for (pl.warps = 4; ; pl.warps >>= 1)
+    for (uint32_t warps = kIngestMaxWarps; warps >= 1; warps >>= 1)
     {
+        IngestPlan pl{};
+        pl.warps = warps;
+        pl.head_pieces = P.has_headers ? ((15u + max_head + 15u) >> 4) + 1u : 0u;
+        pl.stg_stride = (G.tw + 3u) & ~3u;
+        if ((pl.stg_stride & 7u) == 0) pl.stg_stride += 4u;
         uint32_t o = 16;                                             // front pad: reversed readers may look 4 bytes below a window
-        o += pl.warps * 32u * win_slot_bytes<NW>();
+        o += warps * 32u * win_slot_bytes<NW>() + 16u;               // the last lane's pieces end 16 bytes past its slot
         pl.off_head = o;
-        o += pl.warps * recs * pl.head_pieces * 16u;
+        o += warps * recs * pl.head_pieces * 16u;
         o += 32;                                                     // back pad: forward readers run up to 19 bytes past a window
         pl.off_staging = o;
-        o += pl.warps * recs * pl.stg_stride * 4u;
+        o += warps * recs * pl.stg_stride * 4u;
+        o = (o + 15u) & ~15u;
+        pl.off_lut = o;
+        o += (uint32_t)sizeof(SpreadLut);
+        pl.off_chunks = o;
+        o += (3u * kSmemChunkTable + 1u) * 8u;
         pl.total_bytes = o;
-        if (o <= 56u * 1024u || pl.warps == 1) break;
+        pl.blocks_per_sm = std::min(std::min(smem_per_sm / (o + 1024u), 2048u / (warps * 32u)), 32u);
+        const uint32_t wps = pl.blocks_per_sm * warps;
+        if (wps > best_warps_per_sm) { best = pl; best_warps_per_sm = wps; }
     }
-    return pl;
+    return best;
 }
 
 // Every lane copies the aligned window around its own span, one 16-byte piece per step.  (Spreading a
 // span over several lanes would coalesce the requests, but costs two shuffles and an index
-// computation per piece; K1 is bound by the integer pipe, not by the load path, and every line is
-// still fetched from HBM exactly once.)
+// computation per piece; and every line is still fetched from HBM exactly once.)
 template <int NW>
 __device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece0, uint32_t npieces, const uint8_t* text)
 {
-    constexpr uint32_t PW = win_pieces<NW>();
     const uint8_t* src = text + (piece0 << 4);
-#pragma unroll
-    for (uint32_t j = 0; j < PW; ++j)
-        if (j < npieces) cp_async16(my_window + 16u + 16u * j, src + 16u * j);
+    uint8_t* dst = my_window + 16u;
+    npieces = min(npieces, win_pieces<NW>());
+#pragma unroll 1
+    for (uint32_t j = 0; j < npieces; ++j) cp_async16(dst + 16u * j, src + 16u * j);
+}
+
+// What a lane knows about its mate of one warp batch before the text arrives: the record table
+// entry as loaded (nothing is derived from it before it is needed, so the load stays in flight).
+struct MateMeta
+{
+    uint4 rec;               // fsb_record: head_off, seq_off, qua_off, seq_len | head_len << 16
+    uint64_t text_base;      // of the mate's chunk inside text[m]
+    uint32_t ch;
+    bool live;
+};
+
+// The chunk tables: first record of every chunk and the chunks' text offsets (shared-memory copies for small batches).
+struct ChunkTables
+{
+    const uint64_t* first;                // [n_chunks + 1]
+    const uint64_t* text_base[2];         // [n_chunks]
+    uint32_t n_chunks;
+};
+__device__ __forceinline__ uint32_t chunk_of(const ChunkTables& T, uint64_t i)
+{
+    uint32_t lo = 0, hi = T.n_chunks;      // invariant: first[lo] <= i < first[hi]
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (T.first[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 // K1.  NW = ceil(longest read of the batch / 32).
 //   keys[i]  = chunk : signature            cards[i] = card_make(...)  (core.cuh)
 //   slots    = [n_records][G.words] words   sig_out / info_out: optional per-read output (parity tests)
 // Q = quality bits per symbol (6, 3 or 1).
+//
+// Persistent warps: a warp walks over warp batches of 32 mates (stride = warps of the grid); the record
+// table entries of the next batch are loaded while the signature search of the current one runs, and
+// its sequence / title windows are requested as soon as the current quality regions have left.
 template <int NW, int Q>
-__global__ void __launch_bounds__(128) ingest_kernel(BatchView B, DeviceParams P, SlotGeom G, IngestPlan pl, uint32_t* __restrict__ keys,
-                                                      unsigned long long* __restrict__ cards, uint32_t* __restrict__ slots,
-                                                      uint32_t* __restrict__ sig_out, uint32_t* __restrict__ info_out)
+__global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest_kernel(BatchView B, DeviceParams P, SlotGeom G, IngestPlan pl, uint32_t* __restrict__ keys,
+                                                                      unsigned long long* __restrict__ cards, uint32_t* __restrict__ slots,
+                                                                      uint32_t* __restrict__ sig_out, uint32_t* __restrict__ info_out)
 {
     constexpr uint32_t SB = win_slot_bytes<NW>();
     extern __shared__ uint4 ingest_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(ingest_smem);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t recs_per_warp = P.paired ? 16u : 32u;
-    uint8_t* wslots = smem + 16 + (size_t)warp * 32 * SB;
+    uint8_t* warp_windows = smem + (size_t)warp * 32 * SB;
+    uint8_t* my_window = warp_windows + (size_t)lane * SB;                            // pieces at + 16
     uint8_t* hslots = smem + pl.off_head + (size_t)warp * recs_per_warp * pl.head_pieces * 16u;
     uint32_t* stg = reinterpret_cast<uint32_t*>(smem + pl.off_staging) + (size_t)warp * recs_per_warp * pl.stg_stride;
 
+    // ---- once per block: the spreading tables and the chunk tables ---------------------------------------------------
+    ChunkTables T;
+    T.n_chunks = B.n_chunks; T.first = B.chunk_first_rec; T.text_base[0] = B.chunk_text_base[0]; T.text_base[1] = B.chunk_text_base[1];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(g_spread_lut.v);
+        uint4* dst = reinterpret_cast<uint4*>(smem + pl.off_lut);
+        for (uint32_t j = threadIdx.x; j < sizeof(SpreadLut) / 16u; j += blockDim.x) dst[j] = src[j];
+        if (B.n_chunks <= kSmemChunkTable)
+        {
+            uint64_t* ct = reinterpret_cast<uint64_t*>(smem + pl.off_chunks);
+            for (uint32_t j = threadIdx.x; j <= B.n_chunks; j += blockDim.x) ct[j] = B.chunk_first_rec[j];
+            for (uint32_t j = threadIdx.x; j < B.n_chunks; j += blockDim.x)
+            {
+                ct[kSmemChunkTable + 1u + j] = B.chunk_text_base[0][j];
+                ct[2u * kSmemChunkTable + 1u + j] = P.paired ? B.chunk_text_base[1][j] : 0ull;
+            }
+            T.first = ct; T.text_base[0] = ct + kSmemChunkTable + 1u; T.text_base[1] = ct + 2u * kSmemChunkTable + 1u;
+        }
+    }
+    __syncthreads();
+    const LutShared lut{(uint32_t)__cvta_generic_to_shared(smem + pl.off_lut)};
+
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
-    const uint64_t g0 = ((uint64_t)blockIdx.x * pl.warps + warp) * 32;             // first mate of this warp
-    if (g0 >= n_mates) return;                                                     // whole warp out of range (no block-wide barriers below)
-    const uint64_t g = g0 + lane;
-    const bool live = g < n_mates;
-    const uint64_t i = P.paired ? (g >> 1) : g;                                     // record (pair) index
-    const unsigned m = P.paired ? (unsigned)(g & 1) : 0u;
-    const uint32_t lrec = P.paired ? (lane >> 1) : lane;                            // record index inside the warp
-
-    uint32_t L = 0, a_seq = 0, a_qua = 0, a_head = 0, H = 0, ch = 0;
-    uint64_t seq_p0 = 0, qua_p0 = 0;
-    uint32_t seq_np = 0, qua_np = 0, head_p0 = 0, head_np = 0;
-    if (live)
-    {
-        ch = find_chunk(B, i);
-        const fsb_record r = (m ? B.rec[1] : B.rec[0])[i];
-        const uint64_t tb = (m ? B.chunk_text_base[1] : B.chunk_text_base[0])[ch];
-        L = r.seq_len;
-        const uint64_t so = tb + r.seq_off, qo = tb + r.qua_off;
-        a_seq = (uint32_t)(so & 15u); seq_p0 = so >> 4; seq_np = (a_seq + L + 15u) >> 4;
-        a_qua = (uint32_t)(qo & 15u); qua_p0 = qo >> 4; qua_np = (a_qua + L + 15u) >> 4;
-        if (m == 0 && P.has_headers)
-        {
-            const uint64_t ho = tb + r.head_off;
-            H = r.head_len;
-            a_head = (uint32_t)(ho & 15u); head_p0 = (uint32_t)(ho >> 4); head_np = (a_head + H + 15u) >> 4;
-        }
-    }
-    // ---- stage the sequences and the titles; clear the slot staging meanwhile ------------------------------
-    uint8_t* my_window = wslots + (size_t)lane * SB;
+    const uint64_t n_wb = (n_mates + 31u) >> 5;                                       // warp batches
+    const uint64_t wb_stride = (uint64_t)gridDim.x * pl.warps;
+    uint64_t wb = (uint64_t)blockIdx.x * pl.warps + warp;
+    if (wb >= n_wb) return;                                                           // (no block-wide barriers below)
+    const unsigned m = P.paired ? (lane & 1u) : 0u;
+    const uint32_t lrec = P.paired ? (lane >> 1) : lane;                              // record index inside the warp
     const uint8_t* my_text = m ? B.text[1] : B.text[0];
-    gather_window<NW>(my_window, seq_p0, seq_np, my_text);
-    if (pl.head_pieces)
-    {
-        const uint32_t hp = pl.head_pieces - 1u, step = P.paired ? 2u : 1u;
-        for (uint32_t base = 0; base < recs_per_warp * hp; base += 32)           // uniform trip count: the shuffles need every lane
-        {
-            const uint32_t idx = base + lane;
-            const uint32_t rec = min(idx / hp, recs_per_warp - 1u), j = idx - rec * hp;
-            const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, head_p0, rec * step);
-            const uint32_t np = __shfl_sync(0xFFFFFFFFu, head_np, rec * step);
-            if (j < np && j < hp) cp_async16(hslots + (size_t)rec * pl.head_pieces * 16u + 16u + 16u * j, B.text[0] + ((uint64_t)(p0 + j) << 4));
-        }
-    }
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncwarp();
+    const uint32_t* win_words = reinterpret_cast<const uint32_t*>(my_window);
+    uint32_t* my_stage = stg + (size_t)lrec * pl.stg_stride;
 
-    // ---- bit planes of the sequence; from here on the windows belong to the qualities -------------------------
-    const uint32_t* win_words = reinterpret_cast<const uint32_t*>(wslots + (size_t)lane * SB);
-    BV<NW> Hp, Lp, Np;
+    auto load_meta = [&](uint64_t batch) -> MateMeta
+    {
+        MateMeta mm{};
+        const uint64_t g = batch * 32u + lane;
+        mm.live = g < n_mates;
+        if (mm.live)
+        {
+            const uint64_t i = P.paired ? (g >> 1) : g;
+            mm.rec = *reinterpret_cast<const uint4*>((m ? B.rec[1] : B.rec[0]) + i);
+            mm.ch = chunk_of(T, i);
+            mm.text_base = (m ? T.text_base[1] : T.text_base[0])[mm.ch];
+        }
+        return mm;
+    };
+    // the sequence windows and the title windows of one batch
+    auto gather_seq_and_titles = [&](const MateMeta& mm)
+    {
+        const uint64_t seq_at = mm.text_base + mm.rec.y;
+        const uint32_t L = mm.rec.w & 0xFFFFu, H = (m == 0 && P.has_headers) ? ((mm.rec.w >> 16) & 0xFFu) : 0u;
+        gather_window<NW>(my_window, seq_at >> 4, mm.live ? ((uint32_t)(seq_at & 15u) + L + 15u) >> 4 : 0u, my_text);
+        if (mm.live && H)
+        {   // the lane of mate 1 copies the pieces of its record's title
+            const uint64_t head_at = mm.text_base + mm.rec.x;
+            const uint32_t np = min(((uint32_t)(head_at & 15u) + H + 15u) >> 4, pl.head_pieces - 1u);
+            const uint8_t* src = B.text[0] + ((head_at >> 4) << 4);
+            uint8_t* dst = hslots + (size_t)lrec * pl.head_pieces * 16u + 16u;
+#pragma unroll 1
+            for (uint32_t j = 0; j < np; ++j) cp_async16(dst + 16u * j, src + 16u * j);
+        }
+        cp_async_commit();
+    };
+    MateMeta cur = load_meta(wb);
+    gather_seq_and_titles(cur);
+    for (;;)
+    {
+        const uint64_t wb_next = wb + wb_stride;
+        const bool more = wb_next < n_wb;                                             // warp uniform
+        const bool live = cur.live;
+        const uint32_t L = cur.rec.w & 0xFFFFu, H = (m == 0 && P.has_headers) ? ((cur.rec.w >> 16) & 0xFFu) : 0u;
+        const uint64_t i = P.paired ? ((wb * 32u + lane) >> 1) : (wb * 32u + lane);   // record (pair) index
+        const uint64_t rec0 = P.paired ? (wb * 16u) : (wb * 32u);
+        const uint32_t nrec = (uint32_t)min((uint64_t)recs_per_warp, B.n_records - rec0);
+        const uint64_t seq_at = cur.text_base + cur.rec.y, qua_at = cur.text_base + cur.rec.z;
+        const uint32_t a_seq = (uint32_t)(seq_at & 15u), a_qua = (uint32_t)(qua_at & 15u), a_head = (uint32_t)((cur.text_base + cur.rec.x) & 15u);
+        cp_async_wait_all();
+        __syncwarp();
+
+        // ---- bit planes of the sequence; from here on the windows belong to the qualities ----------------------------
+        BV<NW> Hp, Lp, Np;
 #pragma unroll
-    for (int j = 0; j < NW; ++j) { Hp.w[j] = 0; Lp.w[j] = 0; Np.w[j] = 0; }
-    if (live) mate_planes<NW>(win_words + 4 + (a_seq >> 2), 8u * (a_seq & 3u), L, Hp, Lp, Np);
-    __syncwarp();                                                 // every lane is done with its sequence window
-    gather_window<NW>(my_window, qua_p0, qua_np, my_text);
-    cp_async_commit();
+        for (int j = 0; j < NW; ++j) { Hp.w[j] = 0; Lp.w[j] = 0; Np.w[j] = 0; }
+        if (live) mate_planes<NW>(win_words + 4 + (a_seq >> 2), 8u * (a_seq & 3u), L, Hp, Lp, Np);
+        __syncwarp();                                                 // every lane is done with its sequence window
+        gather_window<NW>(my_window, qua_at >> 4, live ? (a_qua + L + 15u) >> 4 : 0u, my_text);
+        cp_async_commit();
+        MateMeta nxt{};
+        if (more) nxt = load_meta(wb_next);                           // in flight during the signature search
 
-    // ---- signature -------------------------------------------------------------------------------------------
-    StrandMin f, r;
-    uint32_t nN = 0;
-    f.sig = r.sig = P.nbin; f.pos = r.pos = 0;
-    if (live) plane_minimizers<NW>(Hp, Lp, Np, L, P, f, r, nN);
-    uint32_t sig, inf;
-    if (!P.paired) select_se(f, r, nN, P, sig, inf);
-    else
-    {
-        // lanes 2i and 2i+1 exchange their results: the even lane holds f1 = FM(m1), r2 = FM(rc(m1));
-        // the odd lane f2 = FM(m2), r1 = FM(rc(m2))
-        StrandMin of, orv;
-        of.sig = __shfl_xor_sync(0xFFFFFFFFu, f.sig, 1); of.pos = __shfl_xor_sync(0xFFFFFFFFu, f.pos, 1);
-        orv.sig = __shfl_xor_sync(0xFFFFFFFFu, r.sig, 1); orv.pos = __shfl_xor_sync(0xFFFFFFFFu, r.pos, 1);
-        const uint32_t onN = __shfl_xor_sync(0xFFFFFFFFu, nN, 1);
-        select_pe(f, of, orv, r, nN, onN, P, sig, inf);          // meaningful on even lanes only
-        sig = __shfl_sync(0xFFFFFFFFu, sig, lane & ~1u);
-        inf = __shfl_sync(0xFFFFFFFFu, inf, lane & ~1u);
-    }
-    const uint32_t Lother = P.paired ? __shfl_xor_sync(0xFFFFFFFFu, L, 1) : 0u;
-    const bool nbin = sig == P.nbin;
-    const bool rev = (inf & FSB_INFO_REVERSE) != 0, swp = (inf & FSB_INFO_SWAPPED) != 0;
-    // stored pair: forward [m1|m2]; reversed [rc(m2)|rc(m1)]; a swap exchanges the halves
-    const bool a_is_m2 = P.paired && (rev != swp);
-    const bool roleB = P.paired && ((m == 1) != a_is_m2);
-    const uint32_t lenA = roleB ? Lother : L, lenB = P.paired ? (roleB ? L : Lother) : 0u;
-    const bool plainA = (inf & FSB_INFO_PLAIN_A) != 0;
-    const uint32_t sfx = nbin ? 0u : P.k;
-    uint32_t* my_slot = stg + (size_t)lrec * pl.stg_stride;
-
-    // ---- DNA of this mate in the stored orientation (StoreDna), straight from the planes ----------------------------
-    SegEmit ed = seg_open(my_slot, 0, 0), eh = ed, eq = ed;
-    if (live)
-    {
-        const uint32_t cut_len = roleB ? 0u : sfx, cut_pos = (roleB || nbin) ? 0u : (inf & FSB_INFO_POS_MASK);
-        const uint32_t off = 32u * (G.qw + G.hw) + (roleB ? (lenA - sfx) * (plainA ? 2u : 3u) : 0u);
-        ed = seg_open(my_slot, off, (L - cut_len) * (nN == 0 ? 2u : 3u));
-        pack_dna_planes<NW>(Hp, Lp, Np, L, rev, nN == 0, cut_pos, cut_len, ed);
-    }
-    // ---- title, key and card --------------------------------------------------------------------------------------
-    if (live && m == 0)
-    {
-        if (P.has_headers)
+        // ---- signature ------------------------------------------------------------------------------------------------
+        StrandMin f, r;
+        uint32_t nN = 0;
+        f.sig = r.sig = P.nbin; f.pos = r.pos = 0;
+        if (live) plane_minimizers<NW>(Hp, Lp, Np, L, P, f, r, nN);
+        uint32_t sig, inf;
+        if (!P.paired) select_se(f, r, nN, P, sig, inf);
+        else
         {
-            eh = seg_open(my_slot, 32u * G.qw, 8u + 7u * (H ? H - 1u : 0u));
-            pack_head(reinterpret_cast<const uint32_t*>(hslots + (size_t)lrec * pl.head_pieces * 16u), 16u + a_head, H, eh);
-            seg_finish(eh, false);
+            // lanes 2i and 2i+1 exchange their results: the even lane holds f1 = FM(m1), r2 = FM(rc(m1));
+            // the odd lane f2 = FM(m2), r1 = FM(rc(m2))
+            StrandMin of, orv;
+            of.sig = __shfl_xor_sync(0xFFFFFFFFu, f.sig, 1); of.pos = __shfl_xor_sync(0xFFFFFFFFu, f.pos, 1);
+            orv.sig = __shfl_xor_sync(0xFFFFFFFFu, r.sig, 1); orv.pos = __shfl_xor_sync(0xFFFFFFFFu, r.pos, 1);
+            const uint32_t onN = __shfl_xor_sync(0xFFFFFFFFu, nN, 1);
+            select_pe(f, of, orv, r, nN, onN, P, sig, inf);          // meaningful on even lanes only
+            sig = __shfl_sync(0xFFFFFFFFu, sig, lane & ~1u);
+            inf = __shfl_sync(0xFFFFFFFFu, inf, lane & ~1u);
         }
-        keys[i] = (ch << P.key_bits) | sig;
-        cards[i] = card_make((uint32_t)i, inf, lenA, lenB, H);
-        if (sig_out) { sig_out[i] = sig; info_out[i] = inf; }
-    }
-    cp_async_wait_all();
-    __syncwarp();
+        const uint32_t Lother = P.paired ? __shfl_xor_sync(0xFFFFFFFFu, L, 1) : 0u;
+        const uint32_t Hrec = P.paired ? __shfl_sync(0xFFFFFFFFu, H, lane & ~1u) : H;          // the record's title length (mate 1)
+        const bool nbin = sig == P.nbin;
+        const bool rev = (inf & FSB_INFO_REVERSE) != 0, swp = (inf & FSB_INFO_SWAPPED) != 0;
+        // stored pair: forward [m1|m2]; reversed [rc(m2)|rc(m1)]; a swap exchanges the halves
+        const bool a_is_m2 = P.paired && (rev != swp);
+        const bool roleB = P.paired && ((m == 1) != a_is_m2);
+        const uint32_t lenA = roleB ? Lother : L, lenB = P.paired ? (roleB ? L : Lother) : 0u;
+        const bool plainA = (inf & FSB_INFO_PLAIN_A) != 0;
+        const uint32_t sfx = nbin ? 0u : P.k;
+        const uint32_t head_bits = P.has_headers ? 8u + 7u * (Hrec ? Hrec - 1u : 0u) : 0u;
 
-    // ---- quality of this mate in the stored orientation (StoreQuality) --------------------------------------------
-    if (live)
-    {
-        eq = seg_open(my_slot, roleB ? lenA * Q : 0u, L * Q);
-        pack_quality<Q>(reader_open(win_words, 16u + a_qua, L, rev), L, P, eq);
-    }
-    // word 0 of every segment: the mates A first, then the mates B merge into what A has stored
-    if (live && !roleB) { seg_finish(ed, false); seg_finish(eq, false); }
-    __syncwarp();
-    if (live && roleB) { seg_finish(ed, true); seg_finish(eq, true); }
-    __syncwarp();
-
-    // ---- the warp's slots leave as one contiguous block -------------------------------------------------------------
-    {
-        const uint64_t rec0 = P.paired ? (g0 >> 1) : g0;
-        const uint64_t nrec = min((uint64_t)recs_per_warp, B.n_records - rec0);
-        uint4* gv = reinterpret_cast<uint4*>(slots + rec0 * G.words);
-        const uint32_t vpr = G.words >> 2, nvec = (uint32_t)nrec * vpr;            // 16-byte vectors per record / in all
-        uint32_t rec = lane / vpr, piece = lane - rec * vpr;                        // staging keeps 4 pad words per record
-        const uint32_t drec = 32u / vpr, dpiece = 32u - drec * vpr;
-        for (uint32_t j = lane; j < nvec; j += 32)
+        // ---- DNA of this mate in the stored orientation (StoreDna), straight from the planes: it follows the title ----------
+        SegEmit ed = seg_open(my_stage, 0, 0);
+        if (live)
         {
-            gv[j] = *reinterpret_cast<const uint4*>(stg + (size_t)rec * pl.stg_stride + 4u * piece);
-            rec += drec; piece += dpiece;
-            if (piece >= vpr) { piece -= vpr; rec += 1; }
+            const uint32_t cut_len = roleB ? 0u : sfx, cut_pos = (roleB || nbin) ? 0u : (inf & FSB_INFO_POS_MASK);
+            const uint32_t off = head_bits + (roleB ? (lenA - sfx) * (plainA ? 2u : 3u) : 0u);
+            ed = seg_open(my_stage, off, (L - cut_len) * (nN == 0 ? 2u : 3u));
+            pack_dna_planes<NW>(Hp, Lp, Np, L, rev, nN == 0, cut_pos, cut_len, lut, ed);
         }
+        // ---- title, key and card --------------------------------------------------------------------------------------
+        if (live && m == 0)
+        {
+            if (P.has_headers)
+            {
+                SegEmit eh = seg_open(my_stage, 0, head_bits);
+                pack_head(reinterpret_cast<const uint32_t*>(hslots + (size_t)lrec * pl.head_pieces * 16u), 16u + a_head, H, eh);
+                seg_finish(eh, false);
+            }
+            keys[i] = (cur.ch << P.key_bits) | sig;
+            cards[i] = card_make((uint32_t)i, inf, lenA, lenB, H);
+            if (sig_out) { sig_out[i] = sig; info_out[i] = inf; }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+
+        // ---- quality of this mate in the stored orientation (StoreQuality), packed in place in its window; the
+        //      windows' packed streams then go to the mates' quality regions of the slots: 8 lanes per mate, four
+        //      stream words each (the regions are 16-byte aligned) ------------------------------------------------------
+        {
+            uint32_t desc = 0;                                        // base | reversed << 8 | mate B << 9 | stream words << 10
+            if (live)
+            {
+                const PackedAt at = pack_quality_inplace<Q>(reinterpret_cast<uint32_t*>(my_window), 16u + a_qua, L, rev, P);
+                desc = at.base | (rev ? 0x100u : 0u) | (roleB ? 0x200u : 0u) | (at.nwords << 10);
+            }
+            __syncwarp();
+            const uint32_t sub = lane >> 3, k0 = 4u * (lane & 7u);
+            const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(warp_windows) + sub * SB;
+            uint32_t* const batch_slots = slots + rec0 * G.words;     // 32-bit word indices from here on
+            const uint32_t rec_words = P.paired ? (G.words >> 1) : G.words;      // slot words per mate index
+#pragma unroll 1
+            for (uint32_t t0 = 0; t0 < 32u; t0 += 4)
+            {                                                         // mate t0 + sub of the warp batch
+                const uint32_t d = __shfl_sync(0xFFFFFFFFu, desc, t0 + sub);
+                const uint32_t nw = d >> 10;
+                const int32_t step = (d & 0x100u) ? -4 : 4;           // bytes from one stream word to the next
+                uint32_t sa = win_s + t0 * SB + 4u * (d & 0xFFu) + (uint32_t)(step * (int32_t)k0);
+                uint32_t di = ((t0 + sub) & (P.paired ? ~1u : ~0u)) * rec_words + ((d & 0x200u) ? G.wqa : 0u) + k0;
+#pragma unroll 1
+                for (uint32_t k = k0; k < nw; k += 32)                // one round unless a mate is longer than 170 bases
+                {
+                    uint4 v;
+                    v.x = lds32(sa); v.y = lds32(sa + step); v.z = lds32(sa + 2 * step); v.w = lds32(sa + 3 * step);
+                    *reinterpret_cast<uint4*>(batch_slots + di) = v;
+                    sa += 32 * step; di += 32;
+                }
+            }
+        }
+        __syncwarp();
+        __syncwarp();                                                 // windows and title windows are free again
+        if (more) gather_seq_and_titles(nxt);
+        // word 0 of the DNA segments: mate A merges into the title's last word, then mate B into A's
+        if (live && !roleB) seg_finish(ed, true);
+        __syncwarp();
+        if (live && roleB) seg_finish(ed, true);
+        __syncwarp();
+        {   // the title + DNA regions: 8 lanes per record, one 16-byte vector each per step
+            const uint32_t nvec = (G.tw + 3u) >> 2, sub = lane >> 3, l8 = lane & 7u;
+            uint32_t sa = (uint32_t)__cvta_generic_to_shared(stg) + 16u * l8 + sub * pl.stg_stride * 4u;
+            uint32_t* const batch_slots = slots + rec0 * G.words;
+            uint32_t di = sub * G.words + G.qw + 4u * l8;
+#pragma unroll 1
+            for (uint32_t r = sub; r < nrec; r += 4)
+            {
+#pragma unroll 1
+                for (uint32_t v = l8; v < nvec; v += 8) *reinterpret_cast<uint4*>(batch_slots + di + 4u * (v - l8)) = lds128(sa + 16u * (v - l8));
+                sa += 16u * pl.stg_stride; di += 4u * G.words;
+            }
+        }
+        if (!more) break;
+        __syncwarp();                                                 // the staging is rewritten by the next batch
+        cur = nxt; wb = wb_next;
     }
 }
 

@@ -18,17 +18,6 @@
 namespace fsb {
 
 // ---- word-level helpers with host equivalents ----------------------------------------------------------
-FSB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel)     // result byte i = pool[(sel >> 4i) & 7], pool = x (0..3), y (4..7)
-{
-#if defined(__CUDA_ARCH__)
-    return __byte_perm(x, y, sel);
-#else
-    const uint64_t pool = ((uint64_t)y << 32) | x;
-    uint32_t r = 0;
-    for (int i = 0; i < 4; ++i) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
-    return r;
-#endif
-}
 FSB_HD void or_word(uint32_t* p, uint32_t v)
 {
 #if defined(__CUDA_ARCH__)
@@ -73,6 +62,15 @@ FSB_HD void seg_push(SegEmit& e, uint32_t x)                  // next 32 bits of
     e.prev = x;
     if (e.idx == 0) e.v0 = v;
     else if (e.idx <= e.last) e.w[e.idx] = v;
+    e.idx++;
+}
+// the same for a word the caller knows to be neither word 0 nor (GUARD = false) past the segment's end
+template <bool GUARD>
+FSB_HD void seg_push_inner(SegEmit& e, uint32_t x)
+{
+    const uint32_t v = funnel_r(x, e.prev, e.phi);
+    e.prev = x;
+    if (!GUARD || e.idx <= e.last) e.w[e.idx] = v;
     e.idx++;
 }
 FSB_HD void seg_close(SegEmit& e) { if (e.idx <= e.last) seg_push(e, 0u); }     // the bits of the last stream word that spilled over
@@ -158,8 +156,8 @@ FSB_HD uint32_t gather4x6(uint32_t x)
 template <int Q>
 FSB_HD uint32_t quality4(uint32_t b, uint32_t off4 /* offset * 0x01010101 */, uint32_t thr4 /* threshold * 0x01010101 */)
 {
+    if (Q == 6) return gather4x6((b | 0x80808080u) - off4);             // (q - offset) & 63: the borrow guard bit 7 is masked off
     const uint32_t d = ((b | 0x80808080u) - off4) ^ 0x80808080u;        // per byte (q - offset) mod 256, no borrow between bytes
-    if (Q == 6) return gather4x6(d);                                      // c & 63
     if (Q == 1)
     {   // c >= binaryThreshold on the unsigned difference: a "negative" difference is large
         const uint32_t ge = ((((d | 0x80808080u) - thr4) | d) >> 7) & 0x01010101u;
@@ -179,6 +177,43 @@ FSB_HD uint32_t quality4(uint32_t b, uint32_t off4 /* offset * 0x01010101 */, ui
 }
 
 // ---- K4: move one prepacked segment to its final bit position ------------------------------------------------
+// `nbits` bits starting at bit `sbit` of src[] (MSB-first: bit 0 = most significant bit of src[0]) go
+// to bit offset `off` of `words`.  Interior words are plain stores; the first and the last word --
+// shared with the neighbouring segments -- are ORed into the zero-initialised buffer.  May read one
+// word past the segment's last source word.
+FSB_HD void shift_copy(const uint32_t* src, uint32_t sbit, uint32_t nbits, uint32_t* words, uint32_t off)
+{
+    if (nbits == 0) return;
+    const uint32_t phi = off & 31u;
+    uint32_t* w = words + (off >> 5);
+    const uint32_t end = phi + nbits;
+    const uint32_t last = (end - 1u) >> 5;                       // index of the last output word
+    const uint32_t tailbits = end - 32u * last;                  // 1..32 valid bits in it
+    const uint32_t lastmask = tailbits >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> tailbits);
+    // output word j holds the source bits [S + 32 j, S + 32 j + 32), S = sbit - phi >= -31
+    const int32_t S = (int32_t)sbit - (int32_t)phi;
+    const int32_t q = S >> 5;                                     // floor: -1 when the first word starts with bits of the neighbour
+    const uint32_t r = (uint32_t)S & 31u;
+    const uint32_t* p = src + q + 1;                              // output word j = (p[j - 1] : p[j]) << r
+    uint32_t a = q >= 0 ? src[q] : 0u;
+    uint32_t b = p[0];
+    uint32_t v = funnel_l(b, a, r) & (0xFFFFFFFFu >> phi);
+    a = b;
+    if (last == 0) { or_word(w, v & lastmask); return; }
+    or_word(w, v);
+    uint32_t j = 1;
+    for (; j + 4u <= last; j += 4)                                // words strictly inside the segment
+    {
+        const uint32_t x0 = p[j], x1 = p[j + 1], x2 = p[j + 2], x3 = p[j + 3];
+        w[j] = funnel_l(x0, a, r); w[j + 1] = funnel_l(x1, x0, r); w[j + 2] = funnel_l(x2, x1, r); w[j + 3] = funnel_l(x3, x2, r);
+        a = x3;
+    }
+    for (; j < last; ++j) { b = p[j]; w[j] = funnel_l(b, a, r); a = b; }
+    b = p[last];
+    or_word(w + last, funnel_l(b, a, r) & lastmask);
+}
+
+// ---- K4: the same for a 16-byte aligned source whose segment starts at bit 0 (vector loads) ------------------------
 // `src` (16-byte aligned) holds `nbits` bits starting at bit 0 of src[0], MSB-first; they go to bit
 // offset `off` of `words`.  Interior words are plain stores, the first and the last word -- shared
 // with the neighbouring segments -- are ORed into the zero-initialised buffer.  Reads whole groups
@@ -192,7 +227,7 @@ FSB_HD void load4(const uint32_t* p, uint32_t (&x)[4])
     for (int u = 0; u < 4; ++u) x[u] = p[u];
 #endif
 }
-FSB_HD void shift_copy(const uint32_t* src, uint32_t nbits, uint32_t* words, uint32_t off)
+FSB_HD void shift_copy_aligned(const uint32_t* src, uint32_t nbits, uint32_t* words, uint32_t off)
 {
     if (nbits == 0) return;
     const uint32_t phi = off & 31u;
@@ -234,40 +269,60 @@ FSB_HD void shift_copy(const uint32_t* src, uint32_t nbits, uint32_t* words, uin
 }
 
 // ---- quality stream of one stored mate (StoreQuality, FastqPacker.cpp:205-269) -------------------------------
-// 32 symbols -> Q stream words per round; a rolled loop (the kernel's code has to fit the
-// instruction cache).  Symbols past `len` inside the last round code to unspecified bits.
+// Packed in place: 32 symbols -> Q stream words per round, written over source bytes the reader has
+// already consumed.  A forward reader moves up through its window, so the stream words go upwards
+// from the word its first byte lies in (a round reads 32 bytes and writes 4 Q <= 24); a reversed
+// reader moves down from the mate's end, so they go downwards from the word holding the end.
+// Stream word k ends up at w[base + dir * k].  Symbols past `len` inside the last round code to
+// unspecified bits; words past the stream's end are not written.
+struct PackedAt { uint32_t base; int32_t dir; uint32_t nwords; };
+
 template <int Q>
-FSB_HD void pack_quality(SymReader rd, uint32_t len, const DeviceParams& P, SegEmit& e)
+FSB_HD PackedAt pack_quality_inplace(uint32_t* w, uint32_t addr, uint32_t len, bool rev, const DeviceParams& P)
 {
     const uint32_t off4 = P.qua_offset * 0x01010101u, thr4 = P.qua_threshold * 0x01010101u;
+    PackedAt at;
+    at.base = rev ? (addr + len) >> 2 : addr >> 2;
+    at.dir = rev ? -1 : 1;
+    at.nwords = (len * Q + 31u) >> 5;
+    SymReader rd = reader_open(w, addr, len, rev);
+    uint32_t* out = w + at.base;
+    uint32_t room = at.nwords;                                   // words still to be written
     const uint32_t rounds = (len + 31u) >> 5;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (uint32_t j = 0; j < rounds; ++j)
     {
-        uint32_t t[8];
+        uint32_t t[8], v[Q];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t[u] = quality4<Q>(reader_next(rd), off4, thr4);
-        if (Q == 6)
+        if constexpr (Q == 6)
         {   // 24 bits per group of four symbols: whole bytes, so the words are byte permutations
-            seg_push(e, byte_perm(t[1], t[0], 0x6542u));                 // t0[23:0] t1[23:16]
-            seg_push(e, byte_perm(t[2], t[1], 0x5421u));                 // t1[15:0] t2[23:8]
-            seg_push(e, byte_perm(t[3], t[2], 0x4210u));                 // t2[7:0]  t3[23:0]
-            seg_push(e, byte_perm(t[5], t[4], 0x6542u));
-            seg_push(e, byte_perm(t[6], t[5], 0x5421u));
-            seg_push(e, byte_perm(t[7], t[6], 0x4210u));
+            v[0] = byte_perm(t[1], t[0], 0x6542u);               // t0[23:0] t1[23:16]
+            v[1] = byte_perm(t[2], t[1], 0x5421u);               // t1[15:0] t2[23:8]
+            v[2] = byte_perm(t[3], t[2], 0x4210u);               // t2[7:0]  t3[23:0]
+            v[3] = byte_perm(t[5], t[4], 0x6542u);
+            v[4] = byte_perm(t[6], t[5], 0x5421u);
+            v[5] = byte_perm(t[7], t[6], 0x4210u);
         }
-        else if (Q == 3)
+        else if constexpr (Q == 3)
         {
-            seg_push(e, (t[0] << 20) | (t[1] << 8) | (t[2] >> 4));
-            seg_push(e, (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8));
-            seg_push(e, (t[5] << 24) | (t[6] << 12) | t[7]);
+            v[0] = (t[0] << 20) | (t[1] << 8) | (t[2] >> 4);
+            v[1] = (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8);
+            v[2] = (t[5] << 24) | (t[6] << 12) | t[7];
         }
         else
-            seg_push(e, (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7]);
+            v[0] = (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7];
+#pragma unroll
+        for (int u = 0; u < Q; ++u)
+        {
+            if ((uint32_t)u < room) *out = v[u];
+            out += at.dir;
+        }
+        room = room > (uint32_t)Q ? room - Q : 0u;
     }
-    seg_close(e);
+    return at;
 }
 
 // ---- DNA stream of one stored mate straight from K1's bit planes -----------------------------------------------
@@ -347,107 +402,112 @@ FSB_HD void cut_planes(MsbPlanes<NW>& o, uint32_t cut_pos, uint32_t cut_len)
     }
 }
 
-// [a15 .. a0 | b15 .. b0] -> a15 b15 a14 b14 .. a0 b0
-FSB_HD uint32_t shuffle16(uint32_t x)
+// Bit-spreading tables: entry b of the first holds the bits of byte b at stride 2 (bit i -> bit 2i),
+// entry 256 + b at stride 3 (bit i -> bit 3i).  The kernels keep a copy in shared memory; one
+// lookup per plane byte replaces a shift-and-mask network per symbol group.
+struct SpreadLut
 {
-    uint32_t t;
-    t = (x ^ (x >> 8)) & 0x0000FF00u; x = x ^ t ^ (t << 8);
-    t = (x ^ (x >> 4)) & 0x00F000F0u; x = x ^ t ^ (t << 4);
-    t = (x ^ (x >> 2)) & 0x0C0C0C0Cu; x = x ^ t ^ (t << 2);
-    t = (x ^ (x >> 1)) & 0x22222222u; x = x ^ t ^ (t << 1);
-    return x;
-}
-// ten 2-bit fields (field f at bits 2f) -> stride 3 (field f at bits 3f); ten 1-bit fields -> bit 3f
-FSB_HD uint32_t spread_2to3(uint32_t x)
+    uint32_t v[512];
+    constexpr SpreadLut() : v()
+    {
+        for (uint32_t b = 0; b < 256; ++b)
+        {
+            uint32_t s2 = 0, s3 = 0;
+            for (uint32_t i = 0; i < 8; ++i)
+                if (b & (1u << i)) { s2 |= 1u << (2 * i); s3 |= 1u << (3 * i); }
+            v[b] = s2; v[256 + b] = s3;
+        }
+    }
+};
+// LUT accessors: a plain pointer (host emulation) or a 32-bit shared-memory address (K1)
+struct LutPtr
 {
-    uint32_t t;
-    t = x << 8; x = (x & ~0x0F000000u) | (t & 0x0F000000u);
-    t = x << 4; x = (x & ~0x000FF000u) | (t & 0x000FF000u);
-    t = x << 2; x = (x & ~0x003C03C0u) | (t & 0x003C03C0u);
-    t = x << 1; x = (x & ~0x18618618u) | (t & 0x18618618u);
-    return x & 0x1B6DB6DBu;
-}
-FSB_HD uint32_t spread_1to3(uint32_t x)
+    const uint32_t* t;
+    FSB_HD uint32_t at(uint32_t tab, uint32_t byte) const { return t[tab + byte]; }
+};
+#if defined(__CUDACC__)
+struct LutShared
 {
-    uint32_t t;
-    t = x << 16; x = (x & ~0x03000000u) | (t & 0x03000000u);
-    t = x << 8;  x = (x & ~0x0000F000u) | (t & 0x0000F000u);
-    t = x << 4;  x = (x & ~0x000C00C0u) | (t & 0x000C00C0u);
-    t = x << 2;  x = (x & ~0x08208208u) | (t & 0x08208208u);
-    return x & 0x09249249u;
+    uint32_t base;           // shared-window address of the table
+    __device__ __forceinline__ uint32_t at(uint32_t tab, uint32_t byte) const
+    {
+        uint32_t addr, v;
+        asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(byte), "r"(base + 4u * tab));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        return v;
+    }
+};
+#endif
+FSB_HD uint32_t byte_of(uint32_t x, int b)                         // byte b of x, zero extended (pool bytes 4..7 are zero)
+{
+    return byte_perm(x, 0u, b == 0 ? 0x4440u : b == 1 ? 0x4441u : b == 2 ? 0x4442u : 0x4443u);
 }
 
-// 2-bit stream words D[0 .. 2 NW) (+ one zero word) of the planes
-template <int NW>
-FSB_HD void planes_to_2bit(const MsbPlanes<NW>& o, uint32_t (&D)[2 * NW + 1])
-{
-#pragma unroll
-    for (int j = 0; j < NW; ++j)
-    {
-        D[2 * j] = shuffle16(byte_perm(o.l[j], o.h[j], 0x7632u));          // [h.hi16 | l.hi16]
-        D[2 * j + 1] = shuffle16(byte_perm(o.l[j], o.h[j], 0x5410u));      // [h.lo16 | l.lo16]
-    }
-    D[2 * NW] = 0;
-}
-// 3-bit stream words E[0 .. 3 NW) from the 2-bit stream and the N plane, ten symbols at a time
-template <int NW>
-FSB_HD void expand_to_3bit(const uint32_t (&D)[2 * NW + 1], const MsbPlanes<NW>& o, uint32_t (&E)[3 * NW])
-{
-#pragma unroll
-    for (int j = 0; j < 3 * NW; ++j) E[j] = 0;
-    constexpr int NCH = (32 * NW + 9) / 10;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-    {
-        const int wd = (20 * c) >> 5, sd = (20 * c) & 31, wn = (10 * c) >> 5, sn = (10 * c) & 31;
-        const uint32_t e = funnel_l(wd + 1 <= 2 * NW ? D[wd + 1] : 0u, D[wd], sd) >> 12;                 // symbols 10c .. 10c+9, two bits each
-        const uint32_t n = funnel_l(o.n[wn + 1 <= NW ? wn + 1 : NW], o.n[wn], sn) >> 22;                   // their N flags
-        const uint32_t t30 = spread_2to3(e) | (spread_1to3(n) << 2);                                       // 30 stream bits
-        const int wo = (30 * c) >> 5, so = (30 * c) & 31;                                                   // they start at bit 30c
-        const uint32_t top = t30 << 2;                                                                      // left-aligned
-        if (wo < 3 * NW) E[wo] |= top >> so;
-        if (so > 2 && wo + 1 < 3 * NW) E[wo + 1] |= top << (32 - so);
-    }
-}
-
-// the whole DNA segment of one stored mate
-template <int NW>
+// the whole DNA segment of one stored mate.  The loops over the plane words stay rolled (see
+// ascii_to_planes): each round codes word 0 of the planes, then the planes move down one word.
+template <int NW, class LUT>
 FSB_HD void pack_dna_planes(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, bool rev, bool plain,
-                            uint32_t cut_pos, uint32_t cut_len, SegEmit& e)
+                            uint32_t cut_pos, uint32_t cut_len, const LUT& lut, SegEmit& e)
 {
     MsbPlanes<NW> o;
     stored_planes<NW>(H, Lo, Nm, L, rev, o);
     if (cut_len) cut_planes<NW>(o, cut_pos, cut_len);
-    uint32_t D[2 * NW + 1];
-    planes_to_2bit<NW>(o, D);
     if (plain)
-    {
+    {   // 2 bits per symbol: hi and lo interleaved, 16 symbols per stream word
+#pragma unroll 1
+        for (int j = 0; j < NW; ++j)
+        {
+            uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 2 * NW; ++j) seg_push(e, D[j]);
+            for (int b = 0; b < 4; ++b) v[b] = 2u * lut.at(0, byte_of(o.h[0], b)) + lut.at(0, byte_of(o.l[0], b));
+            seg_push(e, (v[3] << 16) + v[2]);
+            seg_push(e, (v[1] << 16) + v[0]);
+#pragma unroll
+            for (int i = 0; i + 1 < NW; ++i) { o.h[i] = o.h[i + 1]; o.l[i] = o.l[i + 1]; }
+        }
     }
     else
-    {
-        uint32_t E[3 * NW];
-        expand_to_3bit<NW>(D, o, E);
+    {   // 3 bits per symbol (N, hi, lo): 8 symbols -> 24 bits, four groups -> three stream words
+#pragma unroll 1
+        for (int j = 0; j < NW; ++j)
+        {
+            uint32_t t[4];
 #pragma unroll
-        for (int j = 0; j < 3 * NW; ++j) seg_push(e, E[j]);
+            for (int b = 0; b < 4; ++b)
+                t[b] = 4u * lut.at(256, byte_of(o.n[0], 3 - b)) + 2u * lut.at(256, byte_of(o.h[0], 3 - b)) + lut.at(256, byte_of(o.l[0], 3 - b));
+            seg_push(e, byte_perm(t[1], t[0], 0x6542u));                 // t0[23:0] t1[23:16]
+            seg_push(e, byte_perm(t[2], t[1], 0x5421u));                 // t1[15:0] t2[23:8]
+            seg_push(e, byte_perm(t[3], t[2], 0x4210u));                 // t2[7:0]  t3[23:0]
+#pragma unroll
+            for (int i = 0; i + 1 < NW; ++i) { o.h[i] = o.h[i + 1]; o.l[i] = o.l[i + 1]; o.n[i] = o.n[i + 1]; }
+        }
     }
     seg_close(e);
 }
 
-// ---- title (StoreHeader, FastqPacker.cpp:272-287): 8 bits headLen, then 7 bits per char after '@' ---------
+// one 7-bit value per byte -> 28 bits, first symbol on top
+FSB_HD uint32_t gather4x7(uint32_t x)
+{
+    const uint32_t c = ((x & 0x7F007F00u) >> 1) | (x & 0x007F007Fu);
+    return ((c & 0x3FFF0000u) >> 2) | (c & 0x00003FFFu);
+}
+// Four characters per step; `hold` keeps the n < 32 stream bits not yet pushed, left aligned.
 FSB_HD void pack_head(const uint32_t* w, uint32_t addr, uint32_t H, SegEmit& e)
 {
-    uint64_t acc = H & 0xFFu;
-    uint32_t n = 8;
-    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(w) + addr;
-    for (uint32_t i = 1; i < H; ++i)
+    uint32_t hold = (H & 0xFFu) << 24, n = 8;
+    if (H > 1u)
     {
-        acc = (acc << 7) | (uint64_t)(bytes[i] & 0x7Fu);
-        n += 7;
-        if (n >= 32) { seg_push(e, (uint32_t)(acc >> (n - 32))); n -= 32; }
+        SymReader rd = reader_open(w, addr + 1u, H - 1u, false);
+        const uint32_t groups = (H + 2u) >> 2;                    // ceil((H - 1) / 4); characters past the title code to unspecified bits
+        for (uint32_t g = 0; g < groups; ++g)
+        {
+            const uint32_t c = gather4x7(reader_next(rd)) << 4;   // 28 bits, left aligned
+            const uint32_t word = hold | (c >> n);
+            if (n >= 4u) { seg_push(e, word); hold = c << (32u - n); n -= 4u; }
+            else { hold = word; n += 28u; }
+        }
     }
-    if (n) seg_push(e, (uint32_t)(acc << (32 - n)));
+    if (n) seg_push(e, hold);
     seg_close(e);
 }
 

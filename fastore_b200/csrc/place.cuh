@@ -8,7 +8,7 @@
 // input order.  Bins are laid out back to back in the sorted order, so the T consecutive sorted
 // records a block owns cover one contiguous bit range of every stream.  A block
 //   1. looks up its records (sorted key + card, bin, bit offsets from the layout scans);
-//   2. gathers their slots -- whole, fully used 128-byte lines -- into shared memory with cp.async;
+//   2. gathers their slots -- whole 128-byte lines -- into shared memory with cp.async;
 //   3. funnel-shifts every segment to its bit phase into per-stream staging buffers (one thread per
 //      (record, segment); the record's meta fields and the 17-bit bin headers are produced here);
 //   4. writes the staging buffers out with coalesced 16-byte stores; only the first / last word of a
@@ -102,7 +102,7 @@ __device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_
 __device__ __forceinline__ uint32_t staging_bit(uint64_t off, uint64_t tile_b0) { return (uint32_t)(off - (((tile_b0 >> 5) & ~3ull) << 5)); }
 
 // ---- shared-memory plan, computed on the host from the batch statistics --------------------------------------
-constexpr uint32_t kPlaceRoles = 4;          // quality first half, quality second half, DNA, title + meta
+constexpr uint32_t kPlaceRoles = 4;          // quality of mate A, quality of mate B, DNA, title + meta
 
 struct PlacePlan
 {
@@ -120,21 +120,22 @@ struct RecPlan
     uint32_t nbits[4];
     uint32_t meta_val;
     uint32_t bin_header;     // 0, or 0x80000000 | the bin's 17 header bits when the record opens its bin
-    uint32_t need[2];        // which 16-byte pieces of the slot hold bits of this record (bit p of the 64-bit mask)
+    uint32_t qa_bits;        // quality bits of stored mate A (mate B's follow in the stream)
 };
 
 inline PlacePlan make_place_plan(const DeviceParams& P, const SlotGeom& G, uint32_t max_len, uint32_t max_head)
 {
     PlacePlan pl{};
     const uint32_t mates = P.paired ? 2u : 1u;
-    pl.slot_stride = G.words + 4u;
+    pl.slot_stride = (G.qw + G.tw + 3u) & ~3u;
+    if ((pl.slot_stride & 7u) == 0) pl.slot_stride += 4u;
     for (pl.T = 64; ; pl.T >>= 1)
     {
         pl.threads = kPlaceRoles * pl.T;
         uint32_t o = 0;
         pl.off_plan = o; o += pl.T * (uint32_t)sizeof(RecPlan);
         o = (o + 15u) & ~15u;
-        pl.off_slots = o; o += pl.T * pl.slot_stride * 4u + 16u;                       // + slack: shift_copy reads whole groups of four words
+        pl.off_slots = o; o += pl.T * pl.slot_stride * 4u + 16u;                       // + slack: shift_copy may read one word past a segment
         pl.off_staging[0] = o; o += staging_words(pl.T, 28u + 17u) * 4u;
         pl.off_staging[1] = o; o += staging_words(pl.T, mates * max_len * 3u + 7u) * 4u;
         pl.off_staging[2] = o; o += staging_words(pl.T, mates * max_len * P.qua_bits + 7u) * 4u;
@@ -223,11 +224,7 @@ __global__ void __launch_bounds__(256) place_kernel(PlaceArgs a, PlacePlan pl)
             uint32_t mbits;
             rp.meta_val = meta_fields(P, nbin, info, lenA, lenB, bmin, bmax, mbits);
             rp.bin_header = (i == start) ? (0x80000000u | ((bmin & 0xFFu) << 9) | ((bmax & 0xFFu) << 1)) : 0u;   // PackToBin (FastqPacker.cpp:581-583)
-            // used pieces: [0, uq) of the quality region, [qp, qp + uh) of the title region, [qp + hp, .. + ud) of the DNA region
-            const uint32_t uq = (rb.qua + 127u) >> 7, uh = (rb.head + 127u) >> 7, ud = (rb.dna + 127u) >> 7;
-            const uint32_t qp = G.qw >> 2, hp = G.hw >> 2;
-            const unsigned long long m = (uq >= 64u ? ~0ull : ((1ull << uq) - 1ull)) | (((1ull << uh) - 1ull) << qp) | (((1ull << ud) - 1ull) << (qp + hp));
-            rp.need[0] = (uint32_t)m; rp.need[1] = (uint32_t)(m >> 32);
+            rp.qa_bits = lenA * P.qua_bits;
         }
     }
     {
@@ -240,23 +237,22 @@ __global__ void __launch_bounds__(256) place_kernel(PlaceArgs a, PlacePlan pl)
         if (role == 0)
         {
             RecPlan& q = plan[t];
-            q.rec = rp.rec; q.meta_val = rp.meta_val; q.bin_header = rp.bin_header; q.need[0] = rp.need[0]; q.need[1] = rp.need[1];
+            q.rec = rp.rec; q.meta_val = rp.meta_val; q.bin_header = rp.bin_header; q.qa_bits = rp.qa_bits;
             q.nbits[0] = rp.nbits[0]; q.nbits[1] = rp.nbits[1]; q.nbits[2] = rp.nbits[2]; q.nbits[3] = rp.nbits[3];
         }
         plan[t].loc[role] = staging_bit(off, tb0[role]);
     }
     __syncthreads();
 
-    // ---- 2. gather the slots: one warp per record, lane p copies 16-byte piece p (and p + 32) ---------------------------
+    // ---- 2. gather the slots: one warp per record, lane p copies 16-byte piece p, p + 32, .. ------------------------------------
     {
-        const uint32_t npieces = G.words >> 2;
+        const uint32_t npieces = (G.qw + G.tw + 3u) >> 2;
         for (uint32_t r = warp; r < ntile; r += nwarps)
         {
-            const RecPlan& q = plan[r];
-            const uint4* src = reinterpret_cast<const uint4*>(a.slots) + (uint64_t)q.rec * npieces;
-            uint32_t* dst = slot_buf + (size_t)r * pl.slot_stride;
-            if ((q.need[0] >> lane) & 1u) cp_async16(dst + 4u * lane, src + lane);
-            if (npieces > 32u && ((q.need[1] >> lane) & 1u)) cp_async16(dst + 4u * (lane + 32u), src + lane + 32u);
+            const uint4* src = reinterpret_cast<const uint4*>(a.slots + (uint64_t)plan[r].rec * G.words) + lane;
+            uint32_t* dst = slot_buf + (size_t)r * pl.slot_stride + 4u * lane;
+#pragma unroll 1
+            for (uint32_t pc = lane; pc < npieces; pc += 32) { cp_async16(dst, src); dst += 128; src += 32; }
         }
         cp_async_commit();
         cp_async_wait_all();
@@ -269,16 +265,14 @@ __global__ void __launch_bounds__(256) place_kernel(PlaceArgs a, PlacePlan pl)
         {
             const RecPlan& q = plan[t];
             const uint32_t* slot = slot_buf + (size_t)t * pl.slot_stride;
-            const uint32_t nq = q.nbits[2];
-            const uint32_t half = (((((nq + 31u) >> 5) + 1u) >> 1) + 3u) & ~3u;            // words of the first half, a multiple of 4
-            if (role == 0) shift_copy(slot, min(nq, 32u * half), stg[2], q.loc[2]);
-            else if (role == 1) { if (nq > 32u * half) shift_copy(slot + half, nq - 32u * half, stg[2], q.loc[2] + 32u * half); }
-            else if (role == 2) shift_copy(slot + G.qw + G.hw, q.nbits[1], stg[1], q.loc[1]);
+            if (role == 0) shift_copy_aligned(slot, q.qa_bits, stg[2], q.loc[2]);
+            else if (role == 1) shift_copy_aligned(slot + G.wqa, q.nbits[2] - q.qa_bits, stg[2], q.loc[2] + q.qa_bits);
+            else if (role == 2) shift_copy(slot + G.qw, q.nbits[3], q.nbits[1], stg[1], q.loc[1]);      // the DNA follows the title
             else
             {
                 if (q.bin_header) or_bits(stg[0], q.loc[0] - 17u, q.bin_header & 0x1FFFFu, 17);
                 or_bits(stg[0], q.loc[0], q.meta_val, q.nbits[0]);
-                if (P.has_headers) shift_copy(slot + G.qw, q.nbits[3], stg[3], q.loc[3]);
+                if (P.has_headers) shift_copy_aligned(slot + G.qw, q.nbits[3], stg[3], q.loc[3]);
             }
         }
     }

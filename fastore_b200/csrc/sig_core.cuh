@@ -42,30 +42,38 @@ constexpr uint32_t kGatherBit3 = (1u << 21) | (1u << 14) | (1u << 7) | (1u << 0)
 //   hi plane = ASCII bit 2 (A 0x41, C 0x43 -> 0;  G 0x47, T 0x54 -> 1)
 //   lo plane = ASCII bit 1 ^ bit 2 (A 0, C 1, G 1^1 = 0, T 0^1 = 1)
 //   N  plane = ASCII bit 3 ('N' = 0x4E is the only symbol of the alphabet with it)
+// The loop over the plane words is kept rolled (K1 is bound by instruction fetch, not by issue
+// slots): every round produces the next word of each plane, and the planes move through their
+// registers like a shift register, so no register array is indexed dynamically.
 template <int NW>
 FSB_HD void ascii_to_planes(const uint32_t* w, uint32_t bshift, BV<NW>& H, BV<NW>& Lo, BV<NW>& Nm)
 {
     uint32_t prev = w[0];
+    const uint32_t* p = w + 1;
 #pragma unroll
+    for (int i = 0; i < NW; ++i) { H.w[i] = 0; Lo.w[i] = 0; Nm.w[i] = 0; }
+#pragma unroll 1
     for (int j = 0; j < NW; ++j)
     {
         uint32_t h = 0, b1 = 0, n = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
         {
-            const uint32_t a = w[8 * j + 2 * q + 1], b = w[8 * j + 2 * q + 2];
+            const uint32_t a = p[2 * q], b = p[2 * q + 1];
             const uint32_t w0 = funnel_r(prev, a, bshift);      // bases 32j + 8q .. +3
             const uint32_t w1 = funnel_r(a, b, bshift);         // bases 32j + 8q + 4 .. +7
             prev = b;
-            const uint32_t s = w1 << 4;
-            const uint32_t xh = (w0 & 0x04040404u) | (s & 0x40404040u);
-            const uint32_t x1 = (w0 & 0x02020202u) | (s & 0x20202020u);
-            const uint32_t xn = (w0 & 0x08080808u) | (s & 0x80808080u);
-            h |= ((xh * kGatherBit2) >> 24) << (8 * q);
-            b1 |= ((x1 * kGatherBit1) >> 24) << (8 * q);
-            n |= ((xn * kGatherBit3) >> 24) << (8 * q);
+            // ASCII bits 1..3 of eight bases in one word: the first four in the low nibbles, the next four in the high ones
+            const uint32_t t = (w0 & 0x0E0E0E0Eu) | ((w1 * 16u) & 0xE0E0E0E0u);
+            // the gathered byte enters at the top, the earlier ones move down: after four steps byte q holds bases 8q .. 8q+7
+            h = byte_perm(h, (t & 0x44444444u) * kGatherBit2, 0x7321u);
+            b1 = byte_perm(b1, (t & 0x22222222u) * kGatherBit1, 0x7321u);
+            n = byte_perm(n, (t & 0x88888888u) * kGatherBit3, 0x7321u);
         }
-        H.w[j] = h; Lo.w[j] = b1 ^ h; Nm.w[j] = n;
+        p += 8;
+#pragma unroll
+        for (int i = 0; i + 1 < NW; ++i) { H.w[i] = H.w[i + 1]; Lo.w[i] = Lo.w[i + 1]; Nm.w[i] = Nm.w[i + 1]; }
+        H.w[NW - 1] = h; Lo.w[NW - 1] = b1 ^ h; Nm.w[NW - 1] = n;
     }
 }
 
@@ -99,7 +107,7 @@ FSB_HD void candidate_masks(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm,
         for (int j = 0; j < NW; ++j) badR.w[j] |= ~sh.w[j];
     }
     const int32_t lim = (int32_t)L - (int32_t)k - (int32_t)P.s;  // FindMinimizer scans i < L - k - s
-    Cf = bv_andn(bv_andn(bv_range<NW>(0, lim), badF), Nw);
+    Cf = bv_andn(bv_andn(bv_below<NW>(lim), badF), Nw);
     Cr = bv_andn(bv_andn(bv_range<NW>((int32_t)P.s + 1, (int32_t)L - (int32_t)k + 1), badR), Nw);
 }
 
@@ -137,7 +145,7 @@ FSB_HD uint32_t descend_step_t(BV<NW>& D, const BV<NW>& plane)
     const uint32_t am = mask_nonzero(o);                        // any candidate with a 0 bit: drop those with a 1 bit
 #pragma unroll
     for (int j = 0; j < NW; ++j) D.w[j] = drop_ones<INV>(D.w[j], am, plane.w[j]);
-    return am + 1u;                                             // 0 if a candidate had a 0 bit, else 1
+    return am;                                                  // all ones if a candidate had a 0 bit (the key bit is 0), else 0
 }
 template <int NW>
 FSB_HD uint32_t descend_step(BV<NW>& D, const BV<NW>& plane, bool inv)
@@ -153,11 +161,11 @@ FSB_HD StrandMin descend_forward(BV<NW> D, const BV<NW>& H, const BV<NW>& Lo, co
     for (uint32_t d = 0; d < P.k; ++d)
     {
         if (d) D = bv_shl(D, 1);
-        m = 2 * m + descend_step<NW>(D, H, false);
+        m = 2 * m + descend_step<NW>(D, H, false);                // accumulates -(key bit == 0); the ones are added at the end
         m = 2 * m + descend_step<NW>(D, Lo, false);
     }
     StrandMin r;
-    r.sig = m;
+    r.sig = m + P.kmer_mask;
     r.pos = bv_lowest(D) - (P.k - 1);
     return r;
 }
@@ -176,7 +184,7 @@ FSB_HD StrandMin descend_reverse(const BV<NW>& C, const BV<NW>& H, const BV<NW>&
         m = 2 * m + descend_step<NW>(D, Lo, true);
     }
     StrandMin r;
-    r.sig = m;
+    r.sig = m + P.kmer_mask;
     r.pos = L - P.k - bv_highest(D);
     return r;
 }
@@ -203,7 +211,7 @@ template <int NW>
 FSB_HD void mate_planes(const uint32_t* words, uint32_t bshift, uint32_t L, BV<NW>& H, BV<NW>& Lo, BV<NW>& Nm)
 {
     ascii_to_planes<NW>(words, bshift, H, Lo, Nm);
-    Nm = bv_and(Nm, bv_range<NW>(0, (int32_t)L));
+    Nm = bv_and(Nm, bv_below<NW>((int32_t)L));
 }
 template <int NW>
 FSB_HD void mate_minimizers(const uint32_t* words, uint32_t bshift, uint32_t L, const DeviceParams& P,

@@ -112,26 +112,31 @@ struct Slot
     }
 };
 
-// What K1 (ingest.cuh) does for one stored mate: code its DNA and quality bits into the record's slot.
-// `merge`: the mate is stored second (B), its segments start where mate A's end.
+// What K1 (ingest.cuh) does for one stored mate: code its DNA bits into the title + DNA region of the
+// record's slot and its quality bits into the mate's quality region.
+// `roleB`: the mate is stored second, its DNA starts where mate A's ends.
 template <int NW>
 void prepack_mate(const DeviceParams& P, const SlotGeom& G, const Slot& seq, const Slot& qua, uint32_t len, bool rev, bool plain, uint32_t cut_pos, uint32_t cut_len,
-                  uint32_t* slot, uint32_t dna_off, uint32_t qua_off, bool merge)
+                  uint32_t* slot, uint32_t dna_off, bool roleB)
 {
     // K1 derives the DNA from the bit planes it built for the signature search
     BV<NW> H, Lo, Nm;
     mate_planes<NW>(seq.w.data() + (seq.addr >> 2), 8u * (seq.addr & 3u), len, H, Lo, Nm);
-    SegEmit ed = seg_open(slot, 32u * (G.qw + G.hw) + dna_off, (len - cut_len) * (plain ? 2u : 3u));
-    pack_dna_planes<NW>(H, Lo, Nm, len, rev, plain, cut_pos, cut_len, ed);
-    SegEmit eq = seg_open(slot, qua_off, len * P.qua_bits);
-    const SymReader rq = reader_open(qua.w.data(), qua.addr, len, rev);
+    SegEmit ed = seg_open(slot + G.qw, dna_off, (len - cut_len) * (plain ? 2u : 3u));
+    static const SpreadLut tables;
+    pack_dna_planes<NW>(H, Lo, Nm, len, rev, plain, cut_pos, cut_len, LutPtr{tables.v}, ed);
+    seg_finish(ed, true);
+    // the quality is packed in place in (a copy of) its window, then moved to the mate's quality region
+    std::vector<uint32_t> win(qua.w);
+    PackedAt at;
     switch (P.qua_bits)
     {
-    case 6: pack_quality<6>(rq, len, P, eq); break;
-    case 3: pack_quality<3>(rq, len, P, eq); break;
-    default: pack_quality<1>(rq, len, P, eq); break;
+    case 6: at = pack_quality_inplace<6>(win.data(), qua.addr, len, rev, P); break;
+    case 3: at = pack_quality_inplace<3>(win.data(), qua.addr, len, rev, P); break;
+    default: at = pack_quality_inplace<1>(win.data(), qua.addr, len, rev, P); break;
     }
-    seg_finish(ed, merge); seg_finish(eq, merge);
+    uint32_t* dst = slot + (roleB ? G.wqa : 0u);
+    for (uint32_t k = 0; k < at.nwords; ++k) dst[k] = win[(int64_t)at.base + (int64_t)at.dir * k];
 }
 
 template <int NW>
@@ -195,26 +200,27 @@ int run_pack(const DeviceParams& P, const fsb_chunk* ch, const uint32_t* sig, co
             quaA.fill(ch->text[ma], ch->text_size[ma], ra.qua_off, ra.seq_len);
             const uint32_t sfx = nbin ? 0u : P.k, mpos = inf & FSB_INFO_POS_MASK;
             const bool plainA = (inf & FSB_INFO_PLAIN_A) != 0, plainB = (inf & FSB_INFO_PLAIN_B) != 0;
-            // ---- K1: the record's slot ----
+            // ---- K1: the record's slot (title first: the DNA segments merge into the word the title ends in) ----
             std::fill(slot.begin(), slot.end(), 0xDEADBEEFu);      // the slot staging is never cleared
+            const fsb_record& r1 = ch->records[0][r];
+            const uint32_t H = P.has_headers ? r1.head_len : 0u;
+            const uint32_t head_bits = P.has_headers ? 8u + 7u * (H ? H - 1u : 0u) : 0u;
+            if (P.has_headers)
+            {
+                head.fill(ch->text[0], ch->text_size[0], r1.head_off, r1.head_len);
+                SegEmit eh = seg_open(slot.data() + G.qw, 0, head_bits);
+                pack_head(head.w.data(), head.addr, r1.head_len, eh);
+                seg_finish(eh, false);
+            }
             uint32_t lenB = 0;
-            prepack_mate<NW>(P, G, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, slot.data(), 0, 0, false);
+            prepack_mate<NW>(P, G, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, slot.data(), head_bits, false);
             if (pe)
             {
                 const fsb_record& rbm = ch->records[mb][r];
                 lenB = rbm.seq_len;
                 seqB.fill(ch->text[mb], ch->text_size[mb], rbm.seq_off, rbm.seq_len);
                 quaB.fill(ch->text[mb], ch->text_size[mb], rbm.qua_off, rbm.seq_len);
-                prepack_mate<NW>(P, G, seqB, quaB, rbm.seq_len, rev, plainB, 0, 0, slot.data(), (ra.seq_len - sfx) * (plainA ? 2u : 3u), ra.seq_len * P.qua_bits, true);
-            }
-            const fsb_record& r1 = ch->records[0][r];
-            const uint32_t H = P.has_headers ? r1.head_len : 0u;
-            if (P.has_headers)
-            {
-                head.fill(ch->text[0], ch->text_size[0], r1.head_off, r1.head_len);
-                SegEmit eh = seg_open(slot.data(), 32u * G.qw, 8u + 7u * (r1.head_len ? r1.head_len - 1u : 0u));
-                pack_head(head.w.data(), head.addr, r1.head_len, eh);
-                seg_finish(eh, false);
+                prepack_mate<NW>(P, G, seqB, quaB, rbm.seq_len, rev, plainB, 0, 0, slot.data(), head_bits + (ra.seq_len - sfx) * (plainA ? 2u : 3u), true);
             }
             // the card must survive the trip through the sort
             const uint64_t card = card_make(r, inf, ra.seq_len, lenB, H);
@@ -229,11 +235,11 @@ int run_pack(const DeviceParams& P, const fsb_chunk* ch, const uint32_t* sig, co
             const uint32_t mv = meta_fields(P, nbin, inf, ra.seq_len, lenB, bmin[b], bmax[b], mbits);
             if (mbits != rb.meta) return FSB_ERR_STATE;
             or_bits(words[0].data(), (uint32_t)off[0][i], mv, mbits);
-            const uint32_t nq = rb.qua, half = (((((nq + 31u) >> 5) + 1u) >> 1) + 3u) & ~3u;
-            shift_copy(slot.data(), std::min(nq, 32u * half), words[2].data(), (uint32_t)off[2][i]);
-            if (nq > 32u * half) shift_copy(slot.data() + half, nq - 32u * half, words[2].data(), (uint32_t)off[2][i] + 32u * half);
-            shift_copy(slot.data() + G.qw + G.hw, rb.dna, words[1].data(), (uint32_t)off[1][i]);
-            if (P.has_headers) shift_copy(slot.data() + G.qw, rb.head, words[3].data(), (uint32_t)off[3][i]);
+            const uint32_t qa = ra.seq_len * P.qua_bits;
+            shift_copy_aligned(slot.data(), qa, words[2].data(), (uint32_t)off[2][i]);
+            shift_copy_aligned(slot.data() + G.wqa, rb.qua - qa, words[2].data(), (uint32_t)off[2][i] + qa);
+            shift_copy(slot.data() + G.qw, rb.head, rb.dna, words[1].data(), (uint32_t)off[1][i]);
+            if (P.has_headers) shift_copy_aligned(slot.data() + G.qw, rb.head, words[3].data(), (uint32_t)off[3][i]);
         }
     }
     for (int s = 0; s < 4; ++s)
