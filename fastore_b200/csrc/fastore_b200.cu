@@ -122,7 +122,7 @@ struct fsb_ctx
 
     // intermediates, shared by all batches (the kernels of different batches run on one stream)
     DevBuf d_keys[2], d_cards[2], d_slots, d_counts, d_counts_scan, d_scan_tmp;
-    DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head;
+    DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head, d_tbase;
     DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4];
 
     // ---- profiling -----------------------------------------------------------------------------
@@ -192,17 +192,27 @@ cudaError_t launch_ingest(const BatchView& B, const DeviceParams& P, const SlotG
     return launch_ingest_q<NW, 1>(B, P, G, max_head, keys, cards, slots, sig, info, st);
 }
 
-cudaError_t launch_place(const PlaceArgs& pa, uint32_t max_len, uint32_t max_head, cudaStream_t st, int* launches)
+cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_len, uint32_t max_head, cudaStream_t st, int* launches)
 {
     const uint64_t n = pa.B.n_records;
     const PlacePlan pl = make_place_plan(pa.P, pa.G, max_len, max_head);
     const uint64_t tiles = (n + pl.T - 1) / pl.T;
+    // placement tables: tile ranges, then every record's position inside its tile
+    const unsigned grid_t = (unsigned)((4 * (tiles + 1) + 255) / 256);
+    tile_base_kernel<<<grid_t, 256, 0, st>>>(pa, pl.T, tiles, pm.tbase);
+    placement_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pa, pl.T, pm);
     // only the words two tiles share have to be zero before K4 runs
-    zero_boundary_words_kernel<<<dim3((unsigned)((tiles + 255) / 256), 4), 256, 0, st>>>(pa, pl.T);
+    zero_boundary_words_kernel<<<grid_t, 256, 0, st>>>(pa.O, tiles, pm.tbase);
     cudaError_t e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
     if (e != cudaSuccess) return e;
-    place_kernel<<<(unsigned)tiles, pl.threads, pl.total_bytes, st>>>(pa, pl);
-    *launches += 2;
+    // persistent blocks: as many as fit on the device at once
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel, (int)pl.threads, pl.total_bytes)) != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
+    place_kernel<<<blocks, pl.threads, pl.total_bytes, st>>>(pa, pl, pm, tiles);
+    *launches += 4;
     return cudaGetLastError();
 }
 
@@ -364,6 +374,7 @@ int stage_complete(fsb_ctx* c, Batch& b)
     const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(n, ncounts), nbm) + 1;
     CUDA_TRY(c, ensure_shared(c, c->d_scan_tmp, 4 * (scan_num_tiles(max_scan_n) + 2) * 8));
     CUDA_TRY(c, ensure_shared(c, c->d_flags, (n + 1) * 4));
+    CUDA_TRY(c, ensure_shared(c, c->d_tbase, ((n + kPlaceTile - 1) / kPlaceTile + 2) * 4 * 8));
     CUDA_TRY(c, ensure_shared(c, c->d_flags_excl, (n + 2) * 4));
     CUDA_TRY(c, ensure_shared(c, c->d_bin_of, (n + 1) * 4));
     CUDA_TRY(c, ensure_shared(c, c->d_bin_start, (nbm + 2) * 4));
@@ -525,8 +536,11 @@ int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
     {
         PlaceArgs pa{B, P, b.geom, S, A, SC, BO, {{b.d_out[0].as<uint32_t>(), b.d_out[1].as<uint32_t>(), b.d_out[2].as<uint32_t>(), b.d_out[3].as<uint32_t>()}},
                      c->d_slots.as<uint32_t>(), nb_ptr};
+        // the per-read bit lengths and the bin flags are spent: their arrays take the placement tables
+        Placement pm{{c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(), c->d_bits[3].as<uint32_t>()},
+                     c->d_flags.as<uint32_t>(), c->d_tbase.as<unsigned long long>()};
         int place_launches = 0;
-        CUDA_TRY(c, launch_place(pa, b.max_len, b.max_head, st, &place_launches));
+        CUDA_TRY(c, launch_place(pa, pm, b.max_len, b.max_head, st, &place_launches));
         launches += place_launches;
     }
     if (ev)
@@ -693,7 +707,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
         if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);
     }
     DevBuf* dev[] = {&c->d_keys[0], &c->d_keys[1], &c->d_cards[0], &c->d_cards[1], &c->d_slots, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags,
-                     &c->d_flags_excl, &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
+                     &c->d_flags_excl, &c->d_tbase, &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
                      &c->d_bits[2], &c->d_bits[3], &c->d_P[0], &c->d_P[1], &c->d_P[2], &c->d_P[3], &c->d_bytes[0], &c->d_bytes[1],
                      &c->d_bytes[2], &c->d_bytes[3], &c->d_BO[0], &c->d_BO[1], &c->d_BO[2], &c->d_BO[3]};
     for (DevBuf* d : dev) d->release();

@@ -50,6 +50,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t shared_addr)
     return v;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int NW> constexpr uint32_t win_pieces() { return 2 * NW + 1; }      // 16-byte pieces of the aligned window around L <= 32 NW bytes
@@ -342,18 +343,22 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
             __syncwarp();
             const uint32_t sub = lane >> 3, k0 = 4u * (lane & 7u);
             const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(warp_windows) + sub * SB;
-            uint32_t* const batch_slots = slots + rec0 * G.words;     // 32-bit word indices from here on
+            uint32_t* batch_slots = slots + rec0 * G.words;           // 32-bit word indices from here on
             const uint32_t rec_words = P.paired ? (G.words >> 1) : G.words;      // slot words per mate index
+            uint32_t wsa = win_s, tt = sub, di0 = (sub & (P.paired ? ~1u : ~0u)) * rec_words + k0, k0p = k0;
+            // (opaque to the compiler: under register pressure it would otherwise rebuild these in every round)
+            asm volatile("" : "+r"(wsa), "+r"(tt), "+r"(di0), "+r"(k0p), "+l"(batch_slots));
 #pragma unroll 1
             for (uint32_t t0 = 0; t0 < 32u; t0 += 4)
             {                                                         // mate t0 + sub of the warp batch
-                const uint32_t d = __shfl_sync(0xFFFFFFFFu, desc, t0 + sub);
+                const uint32_t d = __shfl_sync(0xFFFFFFFFu, desc, tt);
                 const uint32_t nw = d >> 10;
                 const int32_t step = (d & 0x100u) ? -4 : 4;           // bytes from one stream word to the next
-                uint32_t sa = win_s + t0 * SB + 4u * (d & 0xFFu) + (uint32_t)(step * (int32_t)k0);
-                uint32_t di = ((t0 + sub) & (P.paired ? ~1u : ~0u)) * rec_words + ((d & 0x200u) ? G.wqa : 0u) + k0;
+                uint32_t sa = wsa + 4u * (d & 0xFFu) + (uint32_t)(step * (int32_t)k0p);
+                uint32_t di = di0 + ((d & 0x200u) ? G.wqa : 0u);
+                tt += 4; wsa += 4u * SB; di0 += 4u * rec_words;
 #pragma unroll 1
-                for (uint32_t k = k0; k < nw; k += 32)                // one round unless a mate is longer than 170 bases
+                for (uint32_t k = k0p; k < nw; k += 32)               // one round unless a mate is longer than 170 bases
                 {
                     uint4 v;
                     v.x = lds32(sa); v.y = lds32(sa + step); v.z = lds32(sa + 2 * step); v.w = lds32(sa + 3 * step);

@@ -102,20 +102,25 @@ __device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_
 __device__ __forceinline__ uint32_t staging_bit(uint64_t off, uint64_t tile_b0) { return (uint32_t)(off - (((tile_b0 >> 5) & ~3ull) << 5)); }
 
 // ---- shared-memory plan, computed on the host from the batch statistics --------------------------------------
+#ifndef FSB_K4_TILE
+#define FSB_K4_TILE 32
+#endif
+constexpr uint32_t kPlaceTile = FSB_K4_TILE;  // records per tile: one lane per record, one warp per role
 constexpr uint32_t kPlaceRoles = 4;          // quality of mate A, quality of mate B, DNA, title + meta
+static_assert(kPlaceTile == 32, "place_kernel maps the records of a tile onto the lanes of a warp");
 
 struct PlacePlan
 {
     uint32_t T;              // records per tile
     uint32_t threads;        // kPlaceRoles * T
     uint32_t slot_stride;    // words per slot in shared memory (odd number of 16-byte units: conflict-free 16-byte reads)
+    uint32_t slot_bytes;     // one buffer of T slots (there are two: the next tile's slots arrive while this one is placed)
     uint32_t off_plan, off_slots, off_staging[4], staging_bytes, total_bytes;
 };
 inline uint32_t staging_words(uint32_t T, uint32_t bits_per_record) { return ((T * bits_per_record + 31u) / 32u + 6u + 3u) & ~3u; }
 
 struct RecPlan
 {
-    uint32_t rec;            // record index (slot)
     uint32_t loc[4];         // bit offset of the record inside the tile's staging buffers (meta, dna, qua, head)
     uint32_t nbits[4];
     uint32_t meta_val;
@@ -129,142 +134,193 @@ inline PlacePlan make_place_plan(const DeviceParams& P, const SlotGeom& G, uint3
     const uint32_t mates = P.paired ? 2u : 1u;
     pl.slot_stride = (G.qw + G.tw + 3u) & ~3u;
     if ((pl.slot_stride & 7u) == 0) pl.slot_stride += 4u;
-    for (pl.T = 64; ; pl.T >>= 1)
-    {
-        pl.threads = kPlaceRoles * pl.T;
-        uint32_t o = 0;
-        pl.off_plan = o; o += pl.T * (uint32_t)sizeof(RecPlan);
-        o = (o + 15u) & ~15u;
-        pl.off_slots = o; o += pl.T * pl.slot_stride * 4u + 16u;                       // + slack: shift_copy may read one word past a segment
-        pl.off_staging[0] = o; o += staging_words(pl.T, 28u + 17u) * 4u;
-        pl.off_staging[1] = o; o += staging_words(pl.T, mates * max_len * 3u + 7u) * 4u;
-        pl.off_staging[2] = o; o += staging_words(pl.T, mates * max_len * P.qua_bits + 7u) * 4u;
-        pl.off_staging[3] = o; o += staging_words(pl.T, P.has_headers ? 8u + 7u * (max_head ? max_head - 1u : 0u) + 7u : 0u) * 4u;
-        pl.staging_bytes = o - pl.off_staging[0];
-        pl.total_bytes = o;
-        if (o <= 100u * 1024u || pl.T == 8) break;
-    }
+    pl.T = kPlaceTile;
+    pl.threads = kPlaceRoles * pl.T;
+    uint32_t o = 0;
+    pl.off_plan = o; o += pl.T * (uint32_t)sizeof(RecPlan);
+    o = (o + 15u) & ~15u;
+    pl.slot_bytes = pl.T * pl.slot_stride * 4u + 16u;                                   // + slack: shift_copy may read a few words past a segment
+    pl.off_slots = o; o += 2u * pl.slot_bytes;
+    pl.off_staging[0] = o; o += staging_words(pl.T, 28u + 17u) * 4u;
+    pl.off_staging[1] = o; o += staging_words(pl.T, mates * max_len * 3u + 7u) * 4u;
+    pl.off_staging[2] = o; o += staging_words(pl.T, mates * max_len * P.qua_bits + 7u) * 4u;
+    pl.off_staging[3] = o; o += staging_words(pl.T, P.has_headers ? 8u + 7u * (max_head ? max_head - 1u : 0u) + 7u : 0u) * 4u;
+    pl.staging_bytes = o - pl.off_staging[0];
+    pl.total_bytes = o;
     return pl;
+}
+
+// ---- placement tables -------------------------------------------------------------------------------------------
+// Everything K4 has to look up per record is worked out beforehand by two streaming kernels with
+// plenty of threads to hide the dependent loads (bin of the record -> start of the bin -> scans), so
+// that K4 itself only reads arrays indexed by the sorted position:
+//   tbase[tile][s]   first bit of the tile in stream s (the bin's first byte when its first record opens a bin);
+//                    entry [tiles] is the end of the stream
+//   loc[s][i]        bit offset of record i inside its tile's staging buffer of stream s
+//   binfo[i]         bin minLen | bin maxLen << 8 | record opens its bin << 16 | N-bin << 17
+struct Placement
+{
+    uint32_t* loc[4];
+    uint32_t* binfo;
+    unsigned long long* tbase;
+};
+
+__global__ void __launch_bounds__(256) tile_base_kernel(PlaceArgs a, uint32_t T, uint64_t tiles, unsigned long long* __restrict__ tbase)
+{
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (tile, stream)
+    if (x >= 4 * (tiles + 1)) return;
+    const uint64_t tile = x >> 2;
+    const int s = (int)(x & 3u);
+    const uint64_t i0 = tile * T, n = a.B.n_records;
+    unsigned long long b0 = 0;
+    if (!(s == 3 && !a.P.has_headers))
+    {
+        if (i0 < n)
+        {
+            const uint32_t bin = a.A.bin_of[i0];
+            const uint64_t start = a.A.bin_start[bin];
+            b0 = (i0 == start) ? 8ull * a.BO.B[s][bin] : stream_offset(a, s, i0, bin, start);
+        }
+        else b0 = 8ull * a.BO.B[s][*a.nb_ptr];
+    }
+    tbase[x] = b0;
+}
+
+__global__ void __launch_bounds__(256) placement_kernel(PlaceArgs a, uint32_t T, Placement pm)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.B.n_records) return;
+    const uint32_t bin = a.A.bin_of[i];
+    const uint64_t start = a.A.bin_start[bin];
+    const uint64_t tile = i / T;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+    {
+        uint32_t loc = 0;
+        if (!(s == 3 && !a.P.has_headers)) loc = staging_bit(stream_offset(a, s, i, bin, start), pm.tbase[4 * tile + s]);
+        pm.loc[s][i] = loc;
+    }
+    const bool nbin = (a.S.skeys[i] & ((1u << a.P.key_bits) - 1u)) == a.P.nbin;
+    pm.binfo[i] = (a.A.bin_min[bin] & 0xFFu) | ((a.A.bin_max[bin] & 0xFFu) << 8) | (i == start ? 0x10000u : 0u) | (nbin ? 0x20000u : 0u);
 }
 
 // ---- tile-boundary words ---------------------------------------------------------------------------------------
 // write_out merges the first / last word of a tile with atomicOr when it is shared with the
 // neighbouring tile; those words -- and only those -- must be zero beforehand (this replaces a
-// memset of the whole output).  blockIdx.y = stream.
-__global__ void __launch_bounds__(256) zero_boundary_words_kernel(PlaceArgs a, uint32_t T)
+// memset of the whole output).  One thread per (tile boundary, stream).
+__global__ void __launch_bounds__(256) zero_boundary_words_kernel(OutStreams O, uint64_t tiles, const unsigned long long* __restrict__ tbase)
 {
-    const int s = blockIdx.y;
-    const uint64_t n = a.B.n_records;
-    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t i0 = tile * T;
-    if (i0 >= n) return;
-    unsigned long long b0, b1;
-    tile_range(a, s, i0, T, b0, b1);
-    if (b0 & 31u) a.O.w[s][b0 >> 5] = 0;
-    if (i0 + T >= n && (b1 & 31u)) a.O.w[s][b1 >> 5] = 0;
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= 4 * (tiles + 1)) return;
+    const unsigned long long b = tbase[x];
+    if (b & 31u) O.w[x & 3u][b >> 5] = 0;
 }
 
 // ---- K4 --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) place_kernel(PlaceArgs a, PlacePlan pl)
+// Persistent blocks of four warps; warp = role (quality A, quality B, DNA, title + meta), lane = record of
+// the tile.  Per tile a thread needs three coalesced values (card, loc, binfo); they are loaded two tiles
+// ahead, the slot gather of the next tile is issued before the current tile is placed (two slot buffers),
+// so the long latencies overlap with the shifting and the write-out.
+struct TileRegs
+{
+    unsigned long long card;
+    uint32_t loc, binfo;
+    unsigned long long tb0, tb1;     // the tile's bit range in the thread's stream
+};
+
+__global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceArgs a, PlacePlan pl, Placement pm, uint64_t tiles)
 {
     extern __shared__ uint4 place_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(place_smem);
-    __shared__ unsigned long long tb0[4], tb1[4];
+    __shared__ unsigned long long tb0s[4], tb1s[4];
     const DeviceParams& P = a.P;
     const SlotGeom& G = a.G;
-    const uint32_t T = pl.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const uint64_t i0 = (uint64_t)blockIdx.x * T, n = a.B.n_records;
-    const uint32_t ntile = (uint32_t)min((uint64_t)T, n - i0);
+    constexpr uint32_t T = kPlaceTile;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, role = tid >> 5;
+    const uint64_t n = a.B.n_records;
     RecPlan* plan = reinterpret_cast<RecPlan*>(smem + pl.off_plan);
-    uint32_t* slot_buf = reinterpret_cast<uint32_t*>(smem + pl.off_slots);
     uint32_t* stg[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) stg[s] = reinterpret_cast<uint32_t*>(smem + pl.off_staging[s]);
+    const uint32_t npieces = (G.qw + G.tw + 3u) >> 2;
+    const uint32_t* my_loc = role == 0 ? pm.loc[0] : (role == 1 ? pm.loc[1] : (role == 2 ? pm.loc[2] : pm.loc[3]));
 
-    // ---- 1. look the tile's records up: thread (s, t) works out where record t goes in stream s ------------------
-    const uint32_t role = tid / T, t = tid - role * T;
-    uint64_t off = 0;
-    RecPlan rp{};
-    const bool live = t < ntile;
-    if (live)
+    auto load_tile = [&](uint64_t tile) -> TileRegs
     {
-        const int s = (int)role;
-        const uint64_t i = i0 + t;
-        const uint32_t key = a.S.skeys[i];
-        const uint64_t card = a.S.cards[i];
-        const bool nbin = (key & ((1u << P.key_bits) - 1u)) == P.nbin;
-        const uint32_t bin = a.A.bin_of[i];
-        const uint64_t start = a.A.bin_start[bin];
-        const uint32_t bmin = a.A.bin_min[bin], bmax = a.A.bin_max[bin];
-        const uint32_t info = card_info(card), lenA = card_lenA(card), lenB = card_lenB(card), H = card_head(card);
-        const bool has = !(s == 3 && !P.has_headers);
-        off = has ? stream_offset(a, s, i, bin, start) : 0ull;
-        if (t == 0)
-        {   // the tile's bit range in this stream (the first record's bin header belongs to the tile when it opens the bin)
-            tb0[s] = !has ? 0ull : ((i == start) ? 8ull * a.BO.B[s][bin] : off);
-            unsigned long long e = 0;
-            if (has)
+        TileRegs r{};
+        if (tile < tiles)
+        {
+            const uint64_t i = tile * T + lane;
+            if (i < n) { r.card = a.S.cards[i]; r.loc = my_loc[i]; r.binfo = pm.binfo[i]; }
+            r.tb0 = pm.tbase[4 * tile + role]; r.tb1 = pm.tbase[4 * tile + 4 + role];
+        }
+        return r;
+    };
+    // warp w fetches the slots of records w, w + 4, .. of the tile: lane p copies 16-byte piece p, p + 32, ..
+    auto gather = [&](uint64_t tile, const TileRegs& r, uint32_t buf)
+    {
+        if (tile < tiles)
+        {
+            const uint32_t ntile = (uint32_t)min((uint64_t)T, n - tile * T);
+            const uint32_t my_rec = card_rec(r.card);
+            uint32_t* sb = reinterpret_cast<uint32_t*>(smem + pl.off_slots + (size_t)buf * pl.slot_bytes);
+            for (uint32_t q = role; q < ntile; q += kPlaceRoles)
             {
-                const uint64_t in = i0 + T;
-                if (in < n)
-                {
-                    const uint32_t bin2 = a.A.bin_of[in];
-                    const uint64_t start2 = a.A.bin_start[bin2];
-                    e = (in == start2) ? 8ull * a.BO.B[s][bin2] : stream_offset(a, s, in, bin2, start2);
-                }
-                else e = 8ull * a.BO.B[s][*a.nb_ptr];
-            }
-            tb1[s] = e;
-        }
-        if (s == 0)
-        {
-            const ReadBits rb = read_bit_lengths(P, nbin, info, lenA, lenB, H, bmin, bmax);
-            rp.rec = card_rec(card);
-            rp.nbits[0] = rb.meta; rp.nbits[1] = rb.dna; rp.nbits[2] = rb.qua; rp.nbits[3] = rb.head;
-            uint32_t mbits;
-            rp.meta_val = meta_fields(P, nbin, info, lenA, lenB, bmin, bmax, mbits);
-            rp.bin_header = (i == start) ? (0x80000000u | ((bmin & 0xFFu) << 9) | ((bmax & 0xFFu) << 1)) : 0u;   // PackToBin (FastqPacker.cpp:581-583)
-            rp.qa_bits = lenA * P.qua_bits;
-        }
-    }
-    {
-        uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
-        for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    if (live)
-    {
-        if (role == 0)
-        {
-            RecPlan& q = plan[t];
-            q.rec = rp.rec; q.meta_val = rp.meta_val; q.bin_header = rp.bin_header; q.qa_bits = rp.qa_bits;
-            q.nbits[0] = rp.nbits[0]; q.nbits[1] = rp.nbits[1]; q.nbits[2] = rp.nbits[2]; q.nbits[3] = rp.nbits[3];
-        }
-        plan[t].loc[role] = staging_bit(off, tb0[role]);
-    }
-    __syncthreads();
-
-    // ---- 2. gather the slots: one warp per record, lane p copies 16-byte piece p, p + 32, .. ------------------------------------
-    {
-        const uint32_t npieces = (G.qw + G.tw + 3u) >> 2;
-        for (uint32_t r = warp; r < ntile; r += nwarps)
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(a.slots + (uint64_t)plan[r].rec * G.words) + lane;
-            uint32_t* dst = slot_buf + (size_t)r * pl.slot_stride + 4u * lane;
+                const uint32_t rec = __shfl_sync(0xFFFFFFFFu, my_rec, q);
+                const uint4* src = reinterpret_cast<const uint4*>(a.slots + (uint64_t)rec * G.words) + lane;
+                uint32_t* dst = sb + (size_t)q * pl.slot_stride + 4u * lane;
 #pragma unroll 1
-            for (uint32_t pc = lane; pc < npieces; pc += 32) { cp_async16(dst, src); dst += 128; src += 32; }
+                for (uint32_t pc = lane; pc < npieces; pc += 32) { cp_async16(dst, src); dst += 128; src += 32; }
+            }
         }
         cp_async_commit();
-        cp_async_wait_all();
-    }
-    __syncthreads();
+    };
 
-    // ---- 3. every (record, segment) to its bit phase ---------------------------------------------------------------------
+    uint64_t tile = blockIdx.x;
+    const uint64_t stride = gridDim.x;
+    TileRegs cur = load_tile(tile), nxt = load_tile(tile + stride);
+    uint32_t buf = 0;
+    gather(tile, cur, buf);
+    for (; tile < tiles; tile += stride)
     {
+        gather(tile + stride, nxt, buf ^ 1u);                         // in flight while this tile is placed
+        const TileRegs nn = load_tile(tile + 2 * stride);             // used in the next round
+        const uint64_t i0 = tile * T;
+        const uint32_t ntile = (uint32_t)min((uint64_t)T, n - i0);
+        const bool live = lane < ntile;
+        const uint32_t* slot_buf = reinterpret_cast<const uint32_t*>(smem + pl.off_slots + (size_t)buf * pl.slot_bytes);
+
+        // ---- 1. the tile's plan ------------------------------------------------------------------------------------------
+        {
+            uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
+            for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
+        }
+        if (lane == 0) { tb0s[role] = cur.tb0; tb1s[role] = cur.tb1; }
         if (live)
         {
-            const RecPlan& q = plan[t];
-            const uint32_t* slot = slot_buf + (size_t)t * pl.slot_stride;
+            RecPlan& q = plan[lane];
+            q.loc[role] = cur.loc;
+            if (role == 0)
+            {
+                const uint32_t bmin = cur.binfo & 0xFFu, bmax = (cur.binfo >> 8) & 0xFFu;
+                const bool nbin = (cur.binfo & 0x20000u) != 0;
+                const uint32_t info = card_info(cur.card), lenA = card_lenA(cur.card), lenB = card_lenB(cur.card), H = card_head(cur.card);
+                const ReadBits rb = read_bit_lengths(P, nbin, info, lenA, lenB, H, bmin, bmax);
+                q.nbits[0] = rb.meta; q.nbits[1] = rb.dna; q.nbits[2] = rb.qua; q.nbits[3] = rb.head;
+                uint32_t mbits;
+                q.meta_val = meta_fields(P, nbin, info, lenA, lenB, bmin, bmax, mbits);
+                q.bin_header = (cur.binfo & 0x10000u) ? (0x80000000u | (bmin << 9) | (bmax << 1)) : 0u;   // PackToBin (FastqPacker.cpp:581-583)
+                q.qa_bits = lenA * P.qua_bits;
+            }
+        }
+        cp_async_wait_group1();                                        // this tile's slots have arrived (the next tile's may still travel)
+        __syncthreads();
+
+        // ---- 2. every (record, segment) to its bit phase ---------------------------------------------------------------------
+        if (live)
+        {
+            const RecPlan& q = plan[lane];
+            const uint32_t* slot = slot_buf + (size_t)lane * pl.slot_stride;
             if (role == 0) shift_copy_aligned(slot, q.qa_bits, stg[2], q.loc[2]);
             else if (role == 1) shift_copy_aligned(slot + G.wqa, q.nbits[2] - q.qa_bits, stg[2], q.loc[2] + q.qa_bits);
             else if (role == 2) shift_copy(slot + G.qw, q.nbits[3], q.nbits[1], stg[1], q.loc[1]);      // the DNA follows the title
@@ -275,12 +331,15 @@ __global__ void __launch_bounds__(256) place_kernel(PlaceArgs a, PlacePlan pl)
                 if (P.has_headers) shift_copy_aligned(slot + G.qw, q.nbits[3], stg[3], q.loc[3]);
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- 4. out ------------------------------------------------------------------------------------------------------------
+        // ---- 3. out ------------------------------------------------------------------------------------------------------------
 #pragma unroll
-    for (int s = 0; s < 4; ++s) write_out(stg[s], a.O.w[s], tb0[s], tb1[s]);
+        for (int s = 0; s < 4; ++s) write_out(stg[s], a.O.w[s], tb0s[s], tb1s[s]);
+        __syncthreads();                                              // staging, plan and tile ranges are rewritten by the next round
+        cur = nxt; nxt = nn; buf ^= 1u;
+    }
+    cp_async_wait_all();
 }
 
 } // namespace fsb
