@@ -330,44 +330,13 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         cp_async_wait_all();
         __syncwarp();
 
-        // ---- quality of this mate in the stored orientation (StoreQuality), packed in place in its window; the
-        //      windows' packed streams then go to the mates' quality regions of the slots: 8 lanes per mate, four
-        //      stream words each (the regions are 16-byte aligned) ------------------------------------------------------
+        // ---- quality of this mate in the stored orientation (StoreQuality): every lane packs its mate's stream
+        //      and stores it as 16-byte vectors straight into the mate's quality region of the slot ---------------------
+        if (live)
         {
-            uint32_t desc = 0;                                        // base | reversed << 8 | mate B << 9 | stream words << 10
-            if (live)
-            {
-                const PackedAt at = pack_quality_inplace<Q>(reinterpret_cast<uint32_t*>(my_window), 16u + a_qua, L, rev, P);
-                desc = at.base | (rev ? 0x100u : 0u) | (roleB ? 0x200u : 0u) | (at.nwords << 10);
-            }
-            __syncwarp();
-            const uint32_t sub = lane >> 3, k0 = 4u * (lane & 7u);
-            const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(warp_windows) + sub * SB;
-            uint32_t* batch_slots = slots + rec0 * G.words;           // 32-bit word indices from here on
-            const uint32_t rec_words = P.paired ? (G.words >> 1) : G.words;      // slot words per mate index
-            uint32_t wsa = win_s, tt = sub, di0 = (sub & (P.paired ? ~1u : ~0u)) * rec_words + k0, k0p = k0;
-            // (opaque to the compiler: under register pressure it would otherwise rebuild these in every round)
-            asm volatile("" : "+r"(wsa), "+r"(tt), "+r"(di0), "+r"(k0p), "+l"(batch_slots));
-#pragma unroll 1
-            for (uint32_t t0 = 0; t0 < 32u; t0 += 4)
-            {                                                         // mate t0 + sub of the warp batch
-                const uint32_t d = __shfl_sync(0xFFFFFFFFu, desc, tt);
-                const uint32_t nw = d >> 10;
-                const int32_t step = (d & 0x100u) ? -4 : 4;           // bytes from one stream word to the next
-                uint32_t sa = wsa + 4u * (d & 0xFFu) + (uint32_t)(step * (int32_t)k0p);
-                uint32_t di = di0 + ((d & 0x200u) ? G.wqa : 0u);
-                tt += 4; wsa += 4u * SB; di0 += 4u * rec_words;
-#pragma unroll 1
-                for (uint32_t k = k0p; k < nw; k += 32)               // one round unless a mate is longer than 170 bases
-                {
-                    uint4 v;
-                    v.x = lds32(sa); v.y = lds32(sa + step); v.z = lds32(sa + 2 * step); v.w = lds32(sa + 3 * step);
-                    *reinterpret_cast<uint4*>(batch_slots + di) = v;
-                    sa += 32 * step; di += 32;
-                }
-            }
+            uint32_t* dst = slots + (rec0 + lrec) * G.words + (roleB ? G.wqa : 0u);
+            pack_quality_to<Q>(reader_open(win_words, 16u + a_qua, L, rev), L, P, dst);
         }
-        __syncwarp();
         __syncwarp();                                                 // windows and title windows are free again
         if (more) gather_seq_and_titles(nxt);
         // word 0 of the DNA segments: mate A merges into the title's last word, then mate B into A's

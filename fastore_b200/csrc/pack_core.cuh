@@ -269,60 +269,68 @@ FSB_HD void shift_copy_aligned(const uint32_t* src, uint32_t nbits, uint32_t* wo
 }
 
 // ---- quality stream of one stored mate (StoreQuality, FastqPacker.cpp:205-269) -------------------------------
-// Packed in place: 32 symbols -> Q stream words per round, written over source bytes the reader has
-// already consumed.  A forward reader moves up through its window, so the stream words go upwards
-// from the word its first byte lies in (a round reads 32 bytes and writes 4 Q <= 24); a reversed
-// reader moves down from the mate's end, so they go downwards from the word holding the end.
-// Stream word k ends up at w[base + dir * k].  Symbols past `len` inside the last round code to
-// unspecified bits; words past the stream's end are not written.
-struct PackedAt { uint32_t base; int32_t dir; uint32_t nwords; };
-
-template <int Q>
-FSB_HD PackedAt pack_quality_inplace(uint32_t* w, uint32_t addr, uint32_t len, bool rev, const DeviceParams& P)
+// 32 symbols -> Q stream words per round; rounds are taken R at a time so that a step yields whole
+// 16-byte vectors (12, 12 or 4 words), which go straight to the mate's quality region `dst` (16-byte
+// aligned, in the record's slot in global memory): every lane stores its own vectors, no staging.
+// Symbols past `len` inside the last round code to unspecified bits; rounds past the mate's end
+// yield zero words; vectors past the stream's end are not written.
+FSB_HD void store4(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+#else
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
+template <int Q>
+FSB_HD void pack_quality_to(SymReader rd, uint32_t len, const DeviceParams& P, uint32_t* dst)
+{
+    constexpr int R = (Q == 6) ? 2 : 4;                          // rounds per step
     const uint32_t off4 = P.qua_offset * 0x01010101u, thr4 = P.qua_threshold * 0x01010101u;
-    PackedAt at;
-    at.base = rev ? (addr + len) >> 2 : addr >> 2;
-    at.dir = rev ? -1 : 1;
-    at.nwords = (len * Q + 31u) >> 5;
-    SymReader rd = reader_open(w, addr, len, rev);
-    uint32_t* out = w + at.base;
-    uint32_t room = at.nwords;                                   // words still to be written
-    const uint32_t rounds = (len + 31u) >> 5;
+    const uint32_t nwords = (len * Q + 31u) >> 5;
+    uint32_t done = 0;                                           // symbols / words handled so far
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (uint32_t j = 0; j < rounds; ++j)
+    for (uint32_t w0 = 0; w0 < nwords; w0 += R * Q, done += 32u * R)
     {
-        uint32_t t[8], v[Q];
+        uint32_t v[R * Q];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = quality4<Q>(reader_next(rd), off4, thr4);
-        if constexpr (Q == 6)
-        {   // 24 bits per group of four symbols: whole bytes, so the words are byte permutations
-            v[0] = byte_perm(t[1], t[0], 0x6542u);               // t0[23:0] t1[23:16]
-            v[1] = byte_perm(t[2], t[1], 0x5421u);               // t1[15:0] t2[23:8]
-            v[2] = byte_perm(t[3], t[2], 0x4210u);               // t2[7:0]  t3[23:0]
-            v[3] = byte_perm(t[5], t[4], 0x6542u);
-            v[4] = byte_perm(t[6], t[5], 0x5421u);
-            v[5] = byte_perm(t[7], t[6], 0x4210u);
-        }
-        else if constexpr (Q == 3)
+        for (int r = 0; r < R; ++r)
         {
-            v[0] = (t[0] << 20) | (t[1] << 8) | (t[2] >> 4);
-            v[1] = (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8);
-            v[2] = (t[5] << 24) | (t[6] << 12) | t[7];
-        }
-        else
-            v[0] = (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7];
+            if (r == 0 || done + 32u * r < len)
+            {
+                uint32_t t[8];
 #pragma unroll
-        for (int u = 0; u < Q; ++u)
-        {
-            if ((uint32_t)u < room) *out = v[u];
-            out += at.dir;
+                for (int u = 0; u < 8; ++u) t[u] = quality4<Q>(reader_next(rd), off4, thr4);
+                if constexpr (Q == 6)
+                {   // 24 bits per group of four symbols: whole bytes, so the words are byte permutations
+                    v[Q * r + 0] = byte_perm(t[1], t[0], 0x6542u);       // t0[23:0] t1[23:16]
+                    v[Q * r + 1] = byte_perm(t[2], t[1], 0x5421u);       // t1[15:0] t2[23:8]
+                    v[Q * r + 2] = byte_perm(t[3], t[2], 0x4210u);       // t2[7:0]  t3[23:0]
+                    v[Q * r + 3] = byte_perm(t[5], t[4], 0x6542u);
+                    v[Q * r + 4] = byte_perm(t[6], t[5], 0x5421u);
+                    v[Q * r + 5] = byte_perm(t[7], t[6], 0x4210u);
+                }
+                else if constexpr (Q == 3)
+                {
+                    v[Q * r + 0] = (t[0] << 20) | (t[1] << 8) | (t[2] >> 4);
+                    v[Q * r + 1] = (t[2] << 28) | (t[3] << 16) | (t[4] << 4) | (t[5] >> 8);
+                    v[Q * r + 2] = (t[5] << 24) | (t[6] << 12) | t[7];
+                }
+                else
+                    v[Q * r] = (t[0] << 28) | (t[1] << 24) | (t[2] << 20) | (t[3] << 16) | (t[4] << 12) | (t[5] << 8) | (t[6] << 4) | t[7];
+            }
+            else
+            {
+#pragma unroll
+                for (int u = 0; u < Q; ++u) v[Q * r + u] = 0;
+            }
         }
-        room = room > (uint32_t)Q ? room - Q : 0u;
+#pragma unroll
+        for (int g = 0; g < R * Q / 4; ++g)
+            if (w0 + 4u * g < nwords) store4(dst + w0 + 4 * g, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     }
-    return at;
 }
 
 // ---- DNA stream of one stored mate straight from K1's bit planes -----------------------------------------------
@@ -443,8 +451,11 @@ FSB_HD uint32_t byte_of(uint32_t x, int b)                         // byte b of 
     return byte_perm(x, 0u, b == 0 ? 0x4440u : b == 1 ? 0x4441u : b == 2 ? 0x4442u : 0x4443u);
 }
 
-// the whole DNA segment of one stored mate.  The loops over the plane words stay rolled (see
-// ascii_to_planes): each round codes word 0 of the planes, then the planes move down one word.
+// the whole DNA segment of one stored mate.  The loop over the plane words stays rolled (see
+// ascii_to_planes): each round codes word 0 of the planes, then the planes move down one word.  Mates
+// with and without 'N' run the same round -- a warp nearly always holds both kinds: they differ in the
+// table they look up (bits spread to stride 2 or 3; the N plane of a plain mate is empty and adds
+// nothing) and in how the four symbol groups of a round (16 or 24 bits each) make up stream words.
 template <int NW, class LUT>
 FSB_HD void pack_dna_planes(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, bool rev, bool plain,
                             uint32_t cut_pos, uint32_t cut_len, const LUT& lut, SegEmit& e)
@@ -452,35 +463,22 @@ FSB_HD void pack_dna_planes(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm,
     MsbPlanes<NW> o;
     stored_planes<NW>(H, Lo, Nm, L, rev, o);
     if (cut_len) cut_planes<NW>(o, cut_pos, cut_len);
-    if (plain)
-    {   // 2 bits per symbol: hi and lo interleaved, 16 symbols per stream word
+    const uint32_t tab = plain ? 0u : 256u;
+#if defined(__CUDA_ARCH__)
 #pragma unroll 1
-        for (int j = 0; j < NW; ++j)
-        {
-            uint32_t v[4];
+#endif
+    for (int j = 0; j < NW; ++j)
+    {
+        uint32_t t[4];                                               // symbols 8b .. 8b+7 of the round, first group in t[0]
 #pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = 2u * lut.at(0, byte_of(o.h[0], b)) + lut.at(0, byte_of(o.l[0], b));
-            seg_push(e, (v[3] << 16) + v[2]);
-            seg_push(e, (v[1] << 16) + v[0]);
+        for (int b = 0; b < 4; ++b)
+            t[b] = 4u * lut.at(tab, byte_of(o.n[0], 3 - b)) + 2u * lut.at(tab, byte_of(o.h[0], 3 - b)) + lut.at(tab, byte_of(o.l[0], 3 - b));
+        // 2 bits per symbol: two words of two 16-bit groups; 3 bits: three words out of four 24-bit groups
+        seg_push(e, plain ? (t[0] << 16) + t[1] : byte_perm(t[1], t[0], 0x6542u));          // t0[23:0] t1[23:16]
+        seg_push(e, plain ? (t[2] << 16) + t[3] : byte_perm(t[2], t[1], 0x5421u));          // t1[15:0] t2[23:8]
+        if (!plain) seg_push(e, byte_perm(t[3], t[2], 0x4210u));                            // t2[7:0]  t3[23:0]
 #pragma unroll
-            for (int i = 0; i + 1 < NW; ++i) { o.h[i] = o.h[i + 1]; o.l[i] = o.l[i + 1]; }
-        }
-    }
-    else
-    {   // 3 bits per symbol (N, hi, lo): 8 symbols -> 24 bits, four groups -> three stream words
-#pragma unroll 1
-        for (int j = 0; j < NW; ++j)
-        {
-            uint32_t t[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                t[b] = 4u * lut.at(256, byte_of(o.n[0], 3 - b)) + 2u * lut.at(256, byte_of(o.h[0], 3 - b)) + lut.at(256, byte_of(o.l[0], 3 - b));
-            seg_push(e, byte_perm(t[1], t[0], 0x6542u));                 // t0[23:0] t1[23:16]
-            seg_push(e, byte_perm(t[2], t[1], 0x5421u));                 // t1[15:0] t2[23:8]
-            seg_push(e, byte_perm(t[3], t[2], 0x4210u));                 // t2[7:0]  t3[23:0]
-#pragma unroll
-            for (int i = 0; i + 1 < NW; ++i) { o.h[i] = o.h[i + 1]; o.l[i] = o.l[i + 1]; o.n[i] = o.n[i + 1]; }
-        }
+        for (int i = 0; i + 1 < NW; ++i) { o.h[i] = o.h[i + 1]; o.l[i] = o.l[i + 1]; o.n[i] = o.n[i + 1]; }
     }
     seg_close(e);
 }

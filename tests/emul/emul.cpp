@@ -126,17 +126,15 @@ void prepack_mate(const DeviceParams& P, const SlotGeom& G, const Slot& seq, con
     static const SpreadLut tables;
     pack_dna_planes<NW>(H, Lo, Nm, len, rev, plain, cut_pos, cut_len, LutPtr{tables.v}, ed);
     seg_finish(ed, true);
-    // the quality is packed in place in (a copy of) its window, then moved to the mate's quality region
-    std::vector<uint32_t> win(qua.w);
-    PackedAt at;
+    // the quality goes straight to the mate's quality region
+    const SymReader rq = reader_open(qua.w.data(), qua.addr, len, rev);
+    uint32_t* dst = slot + (roleB ? G.wqa : 0u);
     switch (P.qua_bits)
     {
-    case 6: at = pack_quality_inplace<6>(win.data(), qua.addr, len, rev, P); break;
-    case 3: at = pack_quality_inplace<3>(win.data(), qua.addr, len, rev, P); break;
-    default: at = pack_quality_inplace<1>(win.data(), qua.addr, len, rev, P); break;
+    case 6: pack_quality_to<6>(rq, len, P, dst); break;
+    case 3: pack_quality_to<3>(rq, len, P, dst); break;
+    default: pack_quality_to<1>(rq, len, P, dst); break;
     }
-    uint32_t* dst = slot + (roleB ? G.wqa : 0u);
-    for (uint32_t k = 0; k < at.nwords; ++k) dst[k] = win[(int64_t)at.base + (int64_t)at.dir * k];
 }
 
 template <int NW>
