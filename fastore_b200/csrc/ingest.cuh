@@ -32,6 +32,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
 {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -65,7 +69,7 @@ constexpr uint32_t kSmemChunkTable = 32;     // chunk tables of batches with at 
 #define FSB_K1_WARPS 8
 #endif
 #ifndef FSB_K1_MINBLOCKS
-#define FSB_K1_MINBLOCKS 3
+#define FSB_K1_MINBLOCKS 2
 #endif
 constexpr uint32_t kIngestMaxWarps = FSB_K1_WARPS;      // warps per block (launch bound)
 

@@ -145,13 +145,25 @@ FSB_HD uint32_t gather4x3(uint32_t v)
 }
 // one bit per byte (bit 0) -> 4 bits, first symbol on top
 FSB_HD uint32_t gather4x1(uint32_t f) { return (f * 0x10204080u) >> 28; }
-// one 6-bit value per byte -> 24 bits, first symbol on top
+// one 6-bit value per byte -> 24 bits, first symbol on top.  K1 is bound by the integer ALU pipe, so the
+// two merge steps are written as multiply-adds (they issue on the other pipe): the odd bytes move down
+// two bits as the high half of a product with 2^30, the upper 12-bit pair moves down four bits by
+// subtracting 61440 times itself.
+FSB_HD uint32_t mul_hi_add(uint32_t a, uint32_t b, uint32_t c)        // high word of a * b, plus c
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32) + c;
+#endif
+}
 FSB_HD uint32_t gather4x6(uint32_t x)
 {
-    const uint32_t c = ((x & 0x3F003F00u) >> 2) | (x & 0x003F003Fu);
-    return ((c & 0x0FFF0000u) >> 4) | (c & 0x00000FFFu);
+    const uint32_t c = mul_hi_add(x & 0x3F003F00u, 0x40000000u, x & 0x003F003Fu);      // [s0 s1] at bit 16, [s2 s3] at bit 0
+    return (c >> 16) * 0xFFFF1000u + c;                                                  // c - 61440 * (c >> 16)
 }
-
 // StoreQuality (FastqPacker.cpp:205-269): four quality bytes -> four values of P.qua_bits bits.
 template <int Q>
 FSB_HD uint32_t quality4(uint32_t b, uint32_t off4 /* offset * 0x01010101 */, uint32_t thr4 /* threshold * 0x01010101 */)

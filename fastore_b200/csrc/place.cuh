@@ -263,14 +263,18 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         {
             const uint32_t ntile = (uint32_t)min((uint64_t)T, n - tile * T);
             const uint32_t my_rec = card_rec(r.card);
-            uint32_t* sb = reinterpret_cast<uint32_t*>(smem + pl.off_slots + (size_t)buf * pl.slot_bytes);
+            uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem + pl.off_slots + (size_t)buf * pl.slot_bytes) + 16u * lane + role * pl.slot_stride * 4u;
+            const uint4* const slots4 = reinterpret_cast<const uint4*>(a.slots) + lane;
+            const uint32_t pieces_per_slot = G.words >> 2;
+#pragma unroll 1
             for (uint32_t q = role; q < ntile; q += kPlaceRoles)
             {
                 const uint32_t rec = __shfl_sync(0xFFFFFFFFu, my_rec, q);
-                const uint4* src = reinterpret_cast<const uint4*>(a.slots + (uint64_t)rec * G.words) + lane;
-                uint32_t* dst = sb + (size_t)q * pl.slot_stride + 4u * lane;
+                const uint4* src = slots4 + (uint64_t)rec * pieces_per_slot;
+                if (lane < npieces) cp_async16_s(sa, src);
 #pragma unroll 1
-                for (uint32_t pc = lane; pc < npieces; pc += 32) { cp_async16(dst, src); dst += 128; src += 32; }
+                for (uint32_t pc = lane + 32u; pc < npieces; pc += 32) cp_async16_s(sa + 16u * (pc - lane), src + (pc - lane));
+                sa += kPlaceRoles * pl.slot_stride * 4u;
             }
         }
         cp_async_commit();

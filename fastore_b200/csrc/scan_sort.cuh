@@ -92,30 +92,26 @@ __global__ void __launch_bounds__(1024) scan_small(OUT* __restrict__ data, uint6
     if (threadIdx.x == 0) data[n] = carry;
 }
 
+template <typename T> __device__ __forceinline__ void load_items(const T* __restrict__ src, uint64_t base, uint64_t n, T (&v)[kScanItems]);
+template <typename T> __device__ __forceinline__ void store_items(T* __restrict__ dst, uint64_t base, uint64_t n, const T (&v)[kScanItems]);
+
 template <typename IN, typename OUT>
 __global__ void __launch_bounds__(kScanThreads) scan_apply(const IN* __restrict__ in, uint64_t n, const OUT* __restrict__ tile_offsets,
                                                             OUT* __restrict__ out)
 {
     __shared__ OUT sm[kScanThreads / 32 + 1];
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    OUT v[kScanItems];
+    IN v[kScanItems];
+    load_items<IN>(in, base, n, v);
     OUT s = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-    {
-        const uint64_t idx = base + i;
-        v[i] = idx < n ? (OUT)in[idx] : OUT(0);
-        s += v[i];
-    }
+    for (int i = 0; i < kScanItems; ++i) s += (OUT)v[i];
     OUT total;
     OUT ex = block_exclusive_scan<OUT, kScanThreads>(s, total, sm) + tile_offsets[blockIdx.x];
+    OUT o[kScanItems];
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-    {
-        const uint64_t idx = base + i;
-        if (idx < n) out[idx] = ex;
-        ex += v[i];
-    }
+    for (int i = 0; i < kScanItems; ++i) { o[i] = ex; ex += (OUT)v[i]; }
+    store_items<OUT>(out, base, n, o);
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) out[n] = tile_offsets[gridDim.x];
 }
 
@@ -161,6 +157,51 @@ __global__ void __launch_bounds__(1024) scan4_small(OUT* __restrict__ data, uint
     if (threadIdx.x == 0) d[n] = carry;
 }
 
+// a thread's kScanItems consecutive items, with 16-byte accesses where the tile is complete and the arrays are aligned
+template <typename T>
+__device__ __forceinline__ void load_items(const T* __restrict__ src, uint64_t base, uint64_t n, T (&v)[kScanItems])
+{
+    constexpr int PER = 16 / (int)sizeof(T);
+    if (base + kScanItems <= n && (reinterpret_cast<uintptr_t>(src + base) & 15u) == 0)
+    {
+        const uint4* p = reinterpret_cast<const uint4*>(src + base);
+#pragma unroll
+        for (int i = 0; i < kScanItems / PER; ++i)
+        {
+            const uint4 q = p[i];
+            if constexpr (sizeof(T) == 4) { v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+            else { v[2 * i] = ((T)q.y << 32) | q.x; v[2 * i + 1] = ((T)q.w << 32) | q.z; }
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) v[i] = base + i < n ? src[base + i] : T(0);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store_items(T* __restrict__ dst, uint64_t base, uint64_t n, const T (&v)[kScanItems])
+{
+    constexpr int PER = 16 / (int)sizeof(T);
+    if (base + kScanItems <= n && (reinterpret_cast<uintptr_t>(dst + base) & 15u) == 0)
+    {
+        uint4* p = reinterpret_cast<uint4*>(dst + base);
+#pragma unroll
+        for (int i = 0; i < kScanItems / PER; ++i)
+        {
+            uint4 q;
+            if constexpr (sizeof(T) == 4) { q.x = v[4 * i]; q.y = v[4 * i + 1]; q.z = v[4 * i + 2]; q.w = v[4 * i + 3]; }
+            else { q.x = (uint32_t)v[2 * i]; q.y = (uint32_t)(v[2 * i] >> 32); q.z = (uint32_t)v[2 * i + 1]; q.w = (uint32_t)(v[2 * i + 1] >> 32); }
+            p[i] = q;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) if (base + i < n) dst[base + i] = v[i];
+    }
+}
+
 template <typename IN, typename OUT>
 __global__ void __launch_bounds__(kScanThreads) scan4_apply(Ptr4<const IN> in, uint64_t n, const OUT* __restrict__ tile_offsets, uint64_t tiles_stride,
                                                              Ptr4<OUT> out)
@@ -170,24 +211,17 @@ __global__ void __launch_bounds__(kScanThreads) scan4_apply(Ptr4<const IN> in, u
     OUT* __restrict__ dst = pick4(out, blockIdx.y);
     const OUT* toff = tile_offsets + blockIdx.y * tiles_stride;
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    OUT v[kScanItems];
+    IN v[kScanItems];
+    load_items<IN>(src, base, n, v);
     OUT s = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-    {
-        const uint64_t idx = base + i;
-        v[i] = idx < n ? (OUT)src[idx] : OUT(0);
-        s += v[i];
-    }
+    for (int i = 0; i < kScanItems; ++i) s += (OUT)v[i];
     OUT total;
     OUT ex = block_exclusive_scan<OUT, kScanThreads>(s, total, sm) + toff[blockIdx.x];
+    OUT o[kScanItems];
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-    {
-        const uint64_t idx = base + i;
-        if (idx < n) dst[idx] = ex;
-        ex += v[i];
-    }
+    for (int i = 0; i < kScanItems; ++i) { o[i] = ex; ex += (OUT)v[i]; }
+    store_items<OUT>(dst, base, n, o);
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) dst[n] = toff[gridDim.x];
 }
 
