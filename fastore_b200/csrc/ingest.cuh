@@ -64,7 +64,6 @@ template <int NW> constexpr uint32_t win_pieces() { return 2 * NW + 1; }      //
 // piece (or the front pad), which is harmless.
 template <int NW> constexpr uint32_t win_slot_bytes() { return win_pieces<NW>() * 16; }
 
-constexpr uint32_t kSmemChunkTable = 32;     // chunk tables of batches with at most this many chunks are kept in shared memory
 #ifndef FSB_K1_WARPS
 #define FSB_K1_WARPS 8
 #endif
@@ -76,7 +75,7 @@ constexpr uint32_t kIngestMaxWarps = FSB_K1_WARPS;      // warps per block (laun
 struct IngestPlan
 {
     uint32_t warps;          // warps per block
-    uint32_t stg_stride;     // words per record in the title + DNA staging (a multiple of 4, not of 8: the lanes' stores spread over the banks)
+    uint32_t stg_stride;     // words per record in the slot staging: the slot's used words rounded up to 4, an odd number of 16-byte units
     uint32_t head_pieces;    // 16-byte pieces per title window incl. the guard piece (0: no titles)
     uint32_t off_head, off_staging, off_lut, off_chunks, total_bytes;
     uint32_t blocks_per_sm;
@@ -88,7 +87,7 @@ __device__ const SpreadLut g_spread_lut = SpreadLut();
 // Shared memory of a block of `warps` warps:
 //   sequence / quality windows   32 per warp; once the qualities are packed they also stage the slots' quality regions
 //   title windows                one per record
-//   title + DNA staging          one region of G.tw words per record
+//   slot staging                 one slot per record (quality regions, title + DNA region): the slots leave as whole lines
 //   spreading tables, chunk tables
 template <int NW>
 inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t smem_per_sm = 227u * 1024u)
@@ -101,7 +100,7 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
         IngestPlan pl{};
         pl.warps = warps;
         pl.head_pieces = P.has_headers ? ((15u + max_head + 15u) >> 4) + 1u : 0u;
-        pl.stg_stride = (G.tw + 3u) & ~3u;
+        pl.stg_stride = (G.qw + G.tw + 3u) & ~3u;
         if ((pl.stg_stride & 7u) == 0) pl.stg_stride += 4u;
         uint32_t o = 16;                                             // front pad: reversed readers may look 4 bytes below a window
         o += warps * 32u * win_slot_bytes<NW>() + 16u;               // the last lane's pieces end 16 bytes past its slot
@@ -114,7 +113,6 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
         pl.off_lut = o;
         o += (uint32_t)sizeof(SpreadLut);
         pl.off_chunks = o;
-        o += (3u * kSmemChunkTable + 1u) * 8u;
         pl.total_bytes = o;
         pl.blocks_per_sm = std::min(std::min(smem_per_sm / (o + 1024u), 2048u / (warps * 32u)), 32u);
         const uint32_t wps = pl.blocks_per_sm * warps;
@@ -126,6 +124,9 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
 // Every lane copies the aligned window around its own span, one 16-byte piece per step.  (Spreading a
 // span over several lanes would coalesce the requests, but costs two shuffles and an index
 // computation per piece; and every line is still fetched from HBM exactly once.)
+// Every lane copies the aligned window around its own span, 16-byte pieces, four per round.  (Copying a window
+// with the neighbouring lane, so that the two halves of a 32-byte sector leave in one instruction, halves the L2
+// requests but does not change the kernel's time; measured, round 1.)
 template <int NW>
 __device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece0, uint32_t npieces, const uint8_t* text)
 {
@@ -133,7 +134,14 @@ __device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece
     uint8_t* dst = my_window + 16u;
     npieces = min(npieces, win_pieces<NW>());
 #pragma unroll 1
-    for (uint32_t j = 0; j < npieces; ++j) cp_async16(dst + 16u * j, src + 16u * j);
+    for (uint32_t j = 0; j < npieces; j += 4)
+    {
+        cp_async16(dst, src);
+        if (j + 1u < npieces) cp_async16(dst + 16u, src + 16u);
+        if (j + 2u < npieces) cp_async16(dst + 32u, src + 32u);
+        if (j + 3u < npieces) cp_async16(dst + 48u, src + 48u);
+        dst += 64u; src += 64u;
+    }
 }
 
 // What a lane knows about its mate of one warp batch before the text arrives: the record table
@@ -187,26 +195,25 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
     uint8_t* hslots = smem + pl.off_head + (size_t)warp * recs_per_warp * pl.head_pieces * 16u;
     uint32_t* stg = reinterpret_cast<uint32_t*>(smem + pl.off_staging) + (size_t)warp * recs_per_warp * pl.stg_stride;
 
-    // ---- once per block: the spreading tables and the chunk tables ---------------------------------------------------
-    ChunkTables T;
-    T.n_chunks = B.n_chunks; T.first = B.chunk_first_rec; T.text_base[0] = B.chunk_text_base[0]; T.text_base[1] = B.chunk_text_base[1];
+    // ---- once per block: the spreading tables ------------------------------------------------------------------------
     {
         const uint4* src = reinterpret_cast<const uint4*>(g_spread_lut.v);
         uint4* dst = reinterpret_cast<uint4*>(smem + pl.off_lut);
         for (uint32_t j = threadIdx.x; j < sizeof(SpreadLut) / 16u; j += blockDim.x) dst[j] = src[j];
-        if (B.n_chunks <= kSmemChunkTable)
-        {
-            uint64_t* ct = reinterpret_cast<uint64_t*>(smem + pl.off_chunks);
-            for (uint32_t j = threadIdx.x; j <= B.n_chunks; j += blockDim.x) ct[j] = B.chunk_first_rec[j];
-            for (uint32_t j = threadIdx.x; j < B.n_chunks; j += blockDim.x)
-            {
-                ct[kSmemChunkTable + 1u + j] = B.chunk_text_base[0][j];
-                ct[2u * kSmemChunkTable + 1u + j] = P.paired ? B.chunk_text_base[1][j] : 0ull;
-            }
-            T.first = ct; T.text_base[0] = ct + kSmemChunkTable + 1u; T.text_base[1] = ct + 2u * kSmemChunkTable + 1u;
-        }
     }
     __syncthreads();
+    // ---- the chunk tables: with at most 32 chunks lane c keeps chunk c's first record and text offsets in registers
+    //      for the whole kernel, and a record's chunk is a ballot away; larger batches search the tables in global memory
+    ChunkTables T;
+    T.n_chunks = B.n_chunks; T.first = B.chunk_first_rec; T.text_base[0] = B.chunk_text_base[0]; T.text_base[1] = B.chunk_text_base[1];
+    const bool chunks_in_lanes = B.n_chunks <= 32u;
+    uint64_t c_first = ~0ull, c_tb0 = 0, c_tb1 = 0;
+    if (chunks_in_lanes && lane < B.n_chunks)
+    {
+        c_first = B.chunk_first_rec[lane];
+        c_tb0 = B.chunk_text_base[0][lane];
+        c_tb1 = P.paired ? B.chunk_text_base[1][lane] : 0ull;
+    }
     const LutShared lut{(uint32_t)__cvta_generic_to_shared(smem + pl.off_lut)};
 
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
@@ -229,6 +236,25 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         {
             const uint64_t i = P.paired ? (g >> 1) : g;
             mm.rec = *reinterpret_cast<const uint4*>((m ? B.rec[1] : B.rec[0]) + i);
+        }
+        if (chunks_in_lanes)
+        {   // chunk of the batch's first record by ballot; the lanes' records lie in it or (rarely) in later chunks
+            const uint64_t i0 = P.paired ? (batch * 16u) : (batch * 32u);
+            const uint32_t ch0 = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, c_first <= i0)) - 1u;
+            const uint64_t i = P.paired ? (g >> 1) : g;
+            uint32_t ch = ch0;
+            for (uint32_t c = ch0 + 1u; c < B.n_chunks; ++c)       // warp uniform trip count: until no lane moves on
+            {
+                const uint64_t f = __shfl_sync(0xFFFFFFFFu, c_first, c);
+                if (!__any_sync(0xFFFFFFFFu, mm.live && f <= i)) break;
+                if (mm.live && f <= i) ch = c;
+            }
+            const uint64_t tb0 = __shfl_sync(0xFFFFFFFFu, c_tb0, ch), tb1 = __shfl_sync(0xFFFFFFFFu, c_tb1, ch);
+            mm.ch = ch; mm.text_base = m ? tb1 : tb0;
+        }
+        else if (mm.live)
+        {
+            const uint64_t i = P.paired ? (g >> 1) : g;
             mm.ch = chunk_of(T, i);
             mm.text_base = (m ? T.text_base[1] : T.text_base[0])[mm.ch];
         }
@@ -282,7 +308,9 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         StrandMin f, r;
         uint32_t nN = 0;
         f.sig = r.sig = P.nbin; f.pos = r.pos = 0;
+#ifndef FSB_EXP_NOCOMPUTE
         if (live) plane_minimizers<NW>(Hp, Lp, Np, L, P, f, r, nN);
+#endif
         uint32_t sig, inf;
         if (!P.paired) select_se(f, r, nN, P, sig, inf);
         else
@@ -310,20 +338,22 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         const uint32_t head_bits = P.has_headers ? 8u + 7u * (Hrec ? Hrec - 1u : 0u) : 0u;
 
         // ---- DNA of this mate in the stored orientation (StoreDna), straight from the planes: it follows the title ----------
-        SegEmit ed = seg_open(my_stage, 0, 0);
+        SegEmit ed = seg_open(my_stage + G.qw, 0, 0);
         if (live)
         {
             const uint32_t cut_len = roleB ? 0u : sfx, cut_pos = (roleB || nbin) ? 0u : (inf & FSB_INFO_POS_MASK);
             const uint32_t off = head_bits + (roleB ? (lenA - sfx) * (plainA ? 2u : 3u) : 0u);
-            ed = seg_open(my_stage, off, (L - cut_len) * (nN == 0 ? 2u : 3u));
+            ed = seg_open(my_stage + G.qw, off, (L - cut_len) * (nN == 0 ? 2u : 3u));
+#ifndef FSB_EXP_NOCOMPUTE
             pack_dna_planes<NW>(Hp, Lp, Np, L, rev, nN == 0, cut_pos, cut_len, lut, ed);
+#endif
         }
         // ---- title, key and card --------------------------------------------------------------------------------------
         if (live && m == 0)
         {
             if (P.has_headers)
             {
-                SegEmit eh = seg_open(my_stage, 0, head_bits);
+                SegEmit eh = seg_open(my_stage + G.qw, 0, head_bits);
                 pack_head(reinterpret_cast<const uint32_t*>(hslots + (size_t)lrec * pl.head_pieces * 16u), 16u + a_head, H, eh);
                 seg_finish(eh, false);
             }
@@ -334,13 +364,9 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         cp_async_wait_all();
         __syncwarp();
 
-        // ---- quality of this mate in the stored orientation (StoreQuality): every lane packs its mate's stream
-        //      and stores it as 16-byte vectors straight into the mate's quality region of the slot ---------------------
-        if (live)
-        {
-            uint32_t* dst = slots + (rec0 + lrec) * G.words + (roleB ? G.wqa : 0u);
-            pack_quality_to<Q>(reader_open(win_words, 16u + a_qua, L, rev), L, P, dst);
-        }
+        // ---- quality of this mate in the stored orientation (StoreQuality): every lane packs its mate's stream as
+        //      16-byte vectors into the mate's quality region of the staged slot ----------------------------------------
+        if (live) pack_quality_to<Q>(reader_open(win_words, 16u + a_qua, L, rev), L, P, my_stage + (roleB ? G.wqa : 0u));
         __syncwarp();                                                 // windows and title windows are free again
         if (more) gather_seq_and_titles(nxt);
         // word 0 of the DNA segments: mate A merges into the title's last word, then mate B into A's
@@ -348,11 +374,11 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         __syncwarp();
         if (live && roleB) seg_finish(ed, true);
         __syncwarp();
-        {   // the title + DNA regions: 8 lanes per record, one 16-byte vector each per step
-            const uint32_t nvec = (G.tw + 3u) >> 2, sub = lane >> 3, l8 = lane & 7u;
+        {   // the warp's slots leave as whole lines: 8 lanes per record, one 16-byte vector each per step
+            const uint32_t nvec = (G.qw + G.tw + 3u) >> 2, sub = lane >> 3, l8 = lane & 7u;
             uint32_t sa = (uint32_t)__cvta_generic_to_shared(stg) + 16u * l8 + sub * pl.stg_stride * 4u;
             uint32_t* const batch_slots = slots + rec0 * G.words;
-            uint32_t di = sub * G.words + G.qw + 4u * l8;
+            uint32_t di = sub * G.words + 4u * l8;
 #pragma unroll 1
             for (uint32_t r = sub; r < nrec; r += 4)
             {

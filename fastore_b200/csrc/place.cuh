@@ -65,36 +65,63 @@ __device__ __forceinline__ void tile_range(const PlaceArgs& a, int s, uint64_t i
     else b1 = 8ull * a.BO.B[s][*a.nb_ptr];
 }
 
+#ifndef FSB_K4_TILE
+#define FSB_K4_TILE 32
+#endif
+constexpr uint32_t kPlaceTile = FSB_K4_TILE;  // records per tile: one lane per record, one warp per role
+constexpr uint32_t kPlaceRoles = 4;          // quality of mate A, quality of mate B, DNA, title + meta
+constexpr uint32_t kPlaceThreads = 128;     // kPlaceRoles * kPlaceTile
+static_assert(kPlaceTile == 32, "place_kernel maps the records of a tile onto the lanes of a warp");
+
+
 // Write a tile's staging buffer to its stream.  Staging word j is stream word base + j with base a
 // multiple of 4 (16-byte aligned), so whole groups of four go out as vector stores; the few words
 // at both ends are handled one by one, and the first / last word are merged with atomicOr when
-// they are shared with the neighbouring tile.
-__device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_words, uint64_t b0, uint64_t b1)
+// they are shared with the neighbouring tile.  The ranges are worked out once per tile and stream
+// (one thread) and read from shared memory by everybody.
+struct WritePlan
 {
-    if (b1 <= b0) return;
-    const uint32_t tid = threadIdx.x;
-    const uint64_t base = (b0 >> 5) & ~3ull;
-    const uint32_t ws = (uint32_t)((b0 >> 5) - base), we = (uint32_t)(((b1 - 1) >> 5) - base);       // first / last word with bits of this tile
+    unsigned long long base;     // stream word of staging word 0
+    uint32_t ws, we;             // first / last staging word with bits of this tile
+    uint32_t vs, ve;             // 16-byte vectors [vs, ve) belong to this tile alone
+    uint32_t nlo, hi_begin, nhi; // leftover words: [ws, ws + nlo) and [hi_begin, hi_begin + nhi)
+    uint32_t shared;             // bit 0: word ws is shared with the previous tile, bit 1: word we with the next; bit 2: anything to write
+};
+__device__ __forceinline__ WritePlan make_write_plan(uint64_t b0, uint64_t b1)
+{
+    WritePlan w{};
+    if (b1 <= b0) return w;
+    w.base = (b0 >> 5) & ~3ull;
+    w.ws = (uint32_t)((b0 >> 5) - w.base); w.we = (uint32_t)(((b1 - 1) >> 5) - w.base);
     const bool head_shared = (b0 & 31u) != 0, tail_shared = (b1 & 31u) != 0;
-    const uint32_t fs = ws + (head_shared ? 1u : 0u), fe1 = we + 1u - (tail_shared ? 1u : 0u);      // words [fs, fe1) belong to this tile alone
-    const uint32_t vs = (fs + 3u) >> 2, ve = fe1 >> 2;                                              // vectors [vs, ve)
-    uint32_t* g = stream_words + base;
+    const uint32_t fs = w.ws + (head_shared ? 1u : 0u), fe1 = w.we + 1u - (tail_shared ? 1u : 0u);  // words [fs, fe1) belong to this tile alone
+    w.vs = (fs + 3u) >> 2; w.ve = fe1 >> 2;
+    // leftovers: [ws, min(4 vs, we + 1)) and [max(4 ve, 4 vs), we]; at most 3 + 3 + 2 words
+    const uint32_t lo_end = w.ve > w.vs ? 4u * w.vs : w.we + 1u;
+    w.hi_begin = w.ve > w.vs ? 4u * w.ve : w.we + 1u;
+    w.nlo = lo_end > w.ws ? lo_end - w.ws : 0u; w.nhi = w.we + 1u > w.hi_begin ? w.we + 1u - w.hi_begin : 0u;
+    w.shared = (head_shared ? 1u : 0u) | (tail_shared ? 2u : 0u) | 4u;
+    return w;
+}
+__device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_words, const WritePlan& w)
+{
+    if (!(w.shared & 4u)) return;
+    const uint32_t tid = threadIdx.x;
+    uint32_t* g = stream_words + w.base;
     const uint4* sv = reinterpret_cast<const uint4*>(stg);
     uint4* gv = reinterpret_cast<uint4*>(g);
-    for (uint32_t j = vs + tid; j < ve; j += blockDim.x)
+#pragma unroll 1
+    for (uint32_t j = w.vs + tid; j < w.ve; j += kPlaceThreads)
     {
         uint4 v = sv[j];
         v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
         gv[j] = v;
     }
-    // leftovers: [ws, min(4 vs, we + 1)) and [max(4 ve, 4 vs), we]; at most 3 + 3 + 2 words
-    const uint32_t lo_end = ve > vs ? 4u * vs : we + 1u, hi_begin = ve > vs ? 4u * ve : we + 1u;
-    const uint32_t nlo = lo_end > ws ? lo_end - ws : 0u, nhi = we + 1u > hi_begin ? we + 1u - hi_begin : 0u;
-    if (tid < nlo + nhi)
+    if (tid < w.nlo + w.nhi)
     {
-        const uint32_t j = tid < nlo ? ws + tid : hi_begin + (tid - nlo);
+        const uint32_t j = tid < w.nlo ? w.ws + tid : w.hi_begin + (tid - w.nlo);
         const uint32_t v = bswap32(stg[j]);
-        if ((j == ws && head_shared) || (j == we && tail_shared)) atomicOr(g + j, v);
+        if ((j == w.ws && (w.shared & 1u)) || (j == w.we && (w.shared & 2u))) atomicOr(g + j, v);
         else g[j] = v;
     }
 }
@@ -102,13 +129,6 @@ __device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_
 __device__ __forceinline__ uint32_t staging_bit(uint64_t off, uint64_t tile_b0) { return (uint32_t)(off - (((tile_b0 >> 5) & ~3ull) << 5)); }
 
 // ---- shared-memory plan, computed on the host from the batch statistics --------------------------------------
-#ifndef FSB_K4_TILE
-#define FSB_K4_TILE 32
-#endif
-constexpr uint32_t kPlaceTile = FSB_K4_TILE;  // records per tile: one lane per record, one warp per role
-constexpr uint32_t kPlaceRoles = 4;          // quality of mate A, quality of mate B, DNA, title + meta
-static_assert(kPlaceTile == 32, "place_kernel maps the records of a tile onto the lanes of a warp");
-
 struct PlacePlan
 {
     uint32_t T;              // records per tile
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
 {
     extern __shared__ uint4 place_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(place_smem);
-    __shared__ unsigned long long tb0s[4], tb1s[4];
+    __shared__ WritePlan wplan[4];
     const DeviceParams& P = a.P;
     const SlotGeom& G = a.G;
     constexpr uint32_t T = kPlaceTile;
@@ -299,7 +319,7 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
             uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
             for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
         }
-        if (lane == 0) { tb0s[role] = cur.tb0; tb1s[role] = cur.tb1; }
+        if (lane == 0) wplan[role] = make_write_plan(cur.tb0, cur.tb1);
         if (live)
         {
             RecPlan& q = plan[lane];
@@ -339,7 +359,7 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
 
         // ---- 3. out ------------------------------------------------------------------------------------------------------------
 #pragma unroll
-        for (int s = 0; s < 4; ++s) write_out(stg[s], a.O.w[s], tb0s[s], tb1s[s]);
+        for (int s = 0; s < 4; ++s) write_out(stg[s], a.O.w[s], wplan[s]);
         __syncthreads();                                              // staging, plan and tile ranges are rewritten by the next round
         cur = nxt; nxt = nn; buf ^= 1u;
     }

@@ -189,8 +189,46 @@ FSB_HD StrandMin descend_reverse(const BV<NW>& C, const BV<NW>& H, const BV<NW>&
     return r;
 }
 
+// Both strands of one mate in one descent: the candidates of the two strands keep their own sets (Df moves up
+// through the k-mer, Dr down), but every bit step takes one decision for the union -- keep the candidates whose
+// key bit is 0 if either set has any.  What survives shares the smaller of the two strand minima; a strand whose
+// set ends up empty had the larger one.  For the selection rules of DistributeToBins (FastqCategorizer.cpp:212-245,
+// 289-336) the exact value of a losing strand does not matter -- every comparison it enters is decided by its
+// being larger than the winner -- so it is reported as 4^k; ties leave both sets populated and both exact.
+FSB_HD uint32_t key_zero_mix(uint32_t df, uint32_t dr, uint32_t plane)      // candidates whose key bit is 0 (one three-input logic op)
+{
+    return (df & ~plane) | (dr & plane);
+}
+template <int NW>
+FSB_HD uint32_t descend_step_joint(BV<NW>& Df, BV<NW>& Dr, const BV<NW>& plane)
+{
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) o |= key_zero_mix(Df.w[j], Dr.w[j], plane.w[j]);
+    const uint32_t am = mask_nonzero(o);
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { Df.w[j] = drop_ones<false>(Df.w[j], am, plane.w[j]); Dr.w[j] = drop_ones<true>(Dr.w[j], am, plane.w[j]); }
+    return am;
+}
+template <int NW>
+FSB_HD void descend_joint(const BV<NW>& Cf, const BV<NW>& Cr, const BV<NW>& H, const BV<NW>& Lo, uint32_t L, const DeviceParams& P,
+                          StrandMin& fwd, StrandMin& rev)
+{
+    BV<NW> Df = Cf, Dr = bv_shl(Cr, P.k - 1);
+    uint32_t m = 0;
+    for (uint32_t d = 0; d < P.k; ++d)
+    {
+        if (d) { Df = bv_shl(Df, 1); Dr = bv_shr(Dr, 1); }
+        m = 2 * m + descend_step_joint<NW>(Df, Dr, H);
+        m = 2 * m + descend_step_joint<NW>(Df, Dr, Lo);
+    }
+    m += P.kmer_mask;
+    if (bv_any(Df)) { fwd.sig = m; fwd.pos = bv_lowest(Df) - (P.k - 1); }
+    if (bv_any(Dr)) { rev.sig = m; rev.pos = L - P.k - bv_highest(Dr); }
+}
+
 // FM(x) and FM(rc(x)) of one mate from its bit planes (N plane already cut to the read length), plus
-// its N count.  L <= 32 * NW.
+// its N count.  L <= 32 * NW.  (A strand that loses to the other strand of the same mate reports 4^k, see above.)
 template <int NW>
 FSB_HD void plane_minimizers(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, const DeviceParams& P,
                              StrandMin& fwd, StrandMin& rev, uint32_t& nN)
@@ -201,11 +239,7 @@ FSB_HD void plane_minimizers(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm
     const bool tooManyN = nN >= L / 3;                           // FastqCategorizer.cpp:102
     fwd.sig = P.nbin; fwd.pos = 0;
     rev.sig = P.nbin; rev.pos = 0;
-    if (!tooManyN)
-    {
-        if (bv_any(Cf)) fwd = descend_forward<NW>(Cf, H, Lo, P);
-        if (bv_any(Cr)) rev = descend_reverse<NW>(Cr, H, Lo, L, P);
-    }
+    if (!tooManyN && (bv_any(Cf) || bv_any(Cr))) descend_joint<NW>(Cf, Cr, H, Lo, L, P, fwd, rev);
 }
 template <int NW>
 FSB_HD void mate_planes(const uint32_t* words, uint32_t bshift, uint32_t L, BV<NW>& H, BV<NW>& Lo, BV<NW>& Nm)
