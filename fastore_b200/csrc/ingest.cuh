@@ -124,23 +124,33 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
 // Every lane copies the aligned window around its own span, one 16-byte piece per step.  (Spreading a
 // span over several lanes would coalesce the requests, but costs two shuffles and an index
 // computation per piece; and every line is still fetched from HBM exactly once.)
-// Every lane copies the aligned window around its own span, 16-byte pieces, four per round.  (Copying a window
-// with the neighbouring lane, so that the two halves of a 32-byte sector leave in one instruction, halves the L2
-// requests but does not change the kernel's time; measured, round 1.)
+// The windows of a warp are copied by the warp together: eight lanes per window, lane k of a group copies
+// pieces k and k + 8, so that one instruction requests whole 128-byte runs (four windows at a time) instead of
+// 32 separate half-used sectors -- the memory side of K1 is bound by L2 requests, not by bytes.  Must be called
+// by all lanes of the warp.
 template <int NW>
 __device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece0, uint32_t npieces, const uint8_t* text)
 {
-    const uint8_t* src = text + (piece0 << 4);
-    uint8_t* dst = my_window + 16u;
-    npieces = min(npieces, win_pieces<NW>());
+    static_assert(win_pieces<NW>() <= 24, "three pieces per lane of a group cover a window");
+    const unsigned lane = threadIdx.x & 31, l8 = lane & 7u, grp = lane >> 3;
+    const unsigned long long my_src = (unsigned long long)(text + (piece0 << 4));
+    // shared address of the first piece (below 2^24) and the number of pieces in one word
+    const uint32_t my_dst = ((uint32_t)__cvta_generic_to_shared(my_window) + 16u) | (min(npieces, win_pieces<NW>()) << 24);
 #pragma unroll 1
-    for (uint32_t j = 0; j < npieces; j += 4)
+    for (uint32_t w0 = 0; w0 < 32u; w0 += 4)
     {
-        cp_async16(dst, src);
-        if (j + 1u < npieces) cp_async16(dst + 16u, src + 16u);
-        if (j + 2u < npieces) cp_async16(dst + 32u, src + 32u);
-        if (j + 3u < npieces) cp_async16(dst + 48u, src + 48u);
-        dst += 64u; src += 64u;
+        const unsigned from = w0 + grp;
+        const unsigned long long src = __shfl_sync(0xFFFFFFFFu, my_src, from);
+        const uint32_t dn = __shfl_sync(0xFFFFFFFFu, my_dst, from);
+        const uint32_t np = dn >> 24, dst = (dn & 0xFFFFFFu) + 16u * l8;
+        const uint8_t* sp = reinterpret_cast<const uint8_t*>(src) + 16u * l8;
+#ifndef FSB_EXP_NOGATHER
+        if (l8 < np) cp_async16_s(dst, sp);
+        if (l8 + 8u < np) cp_async16_s(dst + 128u, sp + 128u);
+        if (win_pieces<NW>() > 16 && l8 + 16u < np) cp_async16_s(dst + 256u, sp + 256u);
+#else
+        (void)dst; (void)sp; (void)np;
+#endif
     }
 }
 
@@ -383,7 +393,9 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
             for (uint32_t r = sub; r < nrec; r += 4)
             {
 #pragma unroll 1
+#ifndef FSB_EXP_NOCOPYOUT
                 for (uint32_t v = l8; v < nvec; v += 8) *reinterpret_cast<uint4*>(batch_slots + di + 4u * (v - l8)) = lds128(sa + 16u * (v - l8));
+#endif
                 sa += 16u * pl.stg_stride; di += 4u * G.words;
             }
         }
