@@ -36,6 +36,12 @@ __device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void* gme
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem_src) : "memory");
 }
+// the same, predicated inside the instruction (no branch, no reconvergence bookkeeping around it)
+__device__ __forceinline__ void cp_async16_if(bool pred, uint32_t smem_addr, const void* gmem_src)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n"
+                 ::"r"(smem_addr), "l"(gmem_src), "r"((uint32_t)pred) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
 {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -145,9 +151,9 @@ __device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece
         const uint32_t np = dn >> 24, dst = (dn & 0xFFFFFFu) + 16u * l8;
         const uint8_t* sp = reinterpret_cast<const uint8_t*>(src) + 16u * l8;
 #ifndef FSB_EXP_NOGATHER
-        if (l8 < np) cp_async16_s(dst, sp);
-        if (l8 + 8u < np) cp_async16_s(dst + 128u, sp + 128u);
-        if (win_pieces<NW>() > 16 && l8 + 16u < np) cp_async16_s(dst + 256u, sp + 256u);
+        cp_async16_if(l8 < np, dst, sp);
+        cp_async16_if(l8 + 8u < np, dst + 128u, sp + 128u);
+        if (win_pieces<NW>() > 16) cp_async16_if(l8 + 16u < np, dst + 256u, sp + 256u);
 #else
         (void)dst; (void)sp; (void)np;
 #endif

@@ -103,17 +103,20 @@ __device__ __forceinline__ WritePlan make_write_plan(uint64_t b0, uint64_t b1)
     w.shared = (head_shared ? 1u : 0u) | (tail_shared ? 2u : 0u) | 4u;
     return w;
 }
-__device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_words, const WritePlan& w)
+// Every word that is read is cleared behind the reader, so the staging is all zero again when the next tile's
+// segments are ORed into it.
+__device__ __forceinline__ void write_out(uint32_t* stg, uint32_t* stream_words, const WritePlan& w)
 {
     if (!(w.shared & 4u)) return;
     const uint32_t tid = threadIdx.x;
     uint32_t* g = stream_words + w.base;
-    const uint4* sv = reinterpret_cast<const uint4*>(stg);
+    uint4* sv = reinterpret_cast<uint4*>(stg);
     uint4* gv = reinterpret_cast<uint4*>(g);
 #pragma unroll 1
     for (uint32_t j = w.vs + tid; j < w.ve; j += kPlaceThreads)
     {
         uint4 v = sv[j];
+        sv[j] = make_uint4(0, 0, 0, 0);
         v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
         gv[j] = v;
     }
@@ -121,6 +124,7 @@ __device__ __forceinline__ void write_out(const uint32_t* stg, uint32_t* stream_
     {
         const uint32_t j = tid < w.nlo ? w.ws + tid : w.hi_begin + (tid - w.nlo);
         const uint32_t v = bswap32(stg[j]);
+        stg[j] = 0;
         if ((j == w.ws && (w.shared & 1u)) || (j == w.we && (w.shared & 2u))) atomicOr(g + j, v);
         else g[j] = v;
     }
@@ -157,7 +161,7 @@ inline PlacePlan make_place_plan(const DeviceParams& P, const SlotGeom& G, uint3
     pl.T = kPlaceTile;
     pl.threads = kPlaceRoles * pl.T;
     uint32_t o = 0;
-    pl.off_plan = o; o += pl.T * (uint32_t)sizeof(RecPlan);
+    pl.off_plan = o; o += 2u * pl.T * (uint32_t)sizeof(RecPlan);            // two plans: warps still writing a tile out must not see the next one
     o = (o + 15u) & ~15u;
     pl.slot_bytes = pl.T * pl.slot_stride * 4u + 16u;                                   // + slack: shift_copy may read a few words past a segment
     pl.off_slots = o; o += 2u * pl.slot_bytes;
@@ -252,13 +256,13 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
 {
     extern __shared__ uint4 place_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(place_smem);
-    __shared__ WritePlan wplan[4];
+    __shared__ WritePlan wplans[2][4];
     const DeviceParams& P = a.P;
     const SlotGeom& G = a.G;
     constexpr uint32_t T = kPlaceTile;
     const uint32_t tid = threadIdx.x, lane = tid & 31, role = tid >> 5;
     const uint64_t n = a.B.n_records;
-    RecPlan* plan = reinterpret_cast<RecPlan*>(smem + pl.off_plan);
+    RecPlan* plans = reinterpret_cast<RecPlan*>(smem + pl.off_plan);
     uint32_t* stg[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) stg[s] = reinterpret_cast<uint32_t*>(smem + pl.off_staging[s]);
@@ -291,15 +295,22 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
             {
                 const uint32_t rec = __shfl_sync(0xFFFFFFFFu, my_rec, q);
                 const uint4* src = slots4 + (uint64_t)rec * pieces_per_slot;
-                if (lane < npieces) cp_async16_s(sa, src);
+                cp_async16_if(lane < npieces, sa, src);
+                if (npieces > 32u)
+                {
 #pragma unroll 1
-                for (uint32_t pc = lane + 32u; pc < npieces; pc += 32) cp_async16_s(sa + 16u * (pc - lane), src + (pc - lane));
+                    for (uint32_t pc = lane + 32u; pc < npieces; pc += 32) cp_async16_s(sa + 16u * (pc - lane), src + (pc - lane));
+                }
                 sa += kPlaceRoles * pl.slot_stride * 4u;
             }
         }
         cp_async_commit();
     };
 
+    {   // the staging starts out zero; afterwards write_out clears what it reads
+        uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
+        for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
+    }
     uint64_t tile = blockIdx.x;
     const uint64_t stride = gridDim.x;
     TileRegs cur = load_tile(tile), nxt = load_tile(tile + stride);
@@ -314,11 +325,9 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         const bool live = lane < ntile;
         const uint32_t* slot_buf = reinterpret_cast<const uint32_t*>(smem + pl.off_slots + (size_t)buf * pl.slot_bytes);
 
-        // ---- 1. the tile's plan ------------------------------------------------------------------------------------------
-        {
-            uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
-            for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
-        }
+        // ---- 1. the tile's plan (in the plan buffer the previous tile did not use) -----------------------------------------
+        RecPlan* plan = plans + buf * T;
+        WritePlan* wplan = wplans[buf];
         if (lane == 0) wplan[role] = make_write_plan(cur.tb0, cur.tb1);
         if (live)
         {
@@ -360,7 +369,8 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         // ---- 3. out ------------------------------------------------------------------------------------------------------------
 #pragma unroll
         for (int s = 0; s < 4; ++s) write_out(stg[s], a.O.w[s], wplan[s]);
-        __syncthreads();                                              // staging, plan and tile ranges are rewritten by the next round
+        // no barrier here: the next round only touches the other plan buffer before its own barrier, and nothing is
+        // ORed into the staging before every warp has passed that barrier, i.e. has finished writing this tile out
         cur = nxt; nxt = nn; buf ^= 1u;
     }
     cp_async_wait_all();
