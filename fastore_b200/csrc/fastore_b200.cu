@@ -466,15 +466,20 @@ int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
     {
         const uint32_t nblocks = (uint32_t)((n + kSortTile - 1) / kSortTile);
         const uint64_t ncounts = (uint64_t)kRadix * nblocks;
+        const int total_bits = (int)(c->dp.key_bits + bits_for(b.n_chunks - 1));
+        int shift = 0;
         for (int pass = 0; pass < b.sort_passes; ++pass)
         {
-            const int shift = 8 * pass;
-            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), n, shift, c->d_counts.as<uint32_t>(), nblocks);
+            // the first digit takes the left-over bits (narrow), the others 8 bits each
+            const int width = pass == 0 ? total_bits - 8 * (b.sort_passes - 1) : 8;
+            const uint32_t mask = (1u << width) - 1u;
+            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), n, shift, mask, c->d_counts.as<uint32_t>(), nblocks);
             launches++;
             launches += exclusive_scan<uint32_t, uint32_t>(c->d_counts.as<uint32_t>(), ncounts, c->d_counts_scan.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
-            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), c->d_cards[cur].as<unsigned long long>(), n, shift,
+            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), c->d_cards[cur].as<unsigned long long>(), n, shift, mask,
                                                             c->d_counts_scan.as<uint32_t>(), nblocks, c->d_keys[cur ^ 1].as<uint32_t>(),
                                                             c->d_cards[cur ^ 1].as<unsigned long long>());
+            shift += width;
             launches++;
             cur ^= 1;
         }

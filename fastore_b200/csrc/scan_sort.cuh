@@ -257,14 +257,16 @@ inline int exclusive_scan(const IN* in, uint64_t n, OUT* out, OUT* tmp, cudaStre
     return 3;
 }
 
-// ---- stable LSD radix sort, 8-bit digits ---------------------------------------------------------
+// ---- stable LSD radix sort, digits of up to 8 bits --------------------------------------------------
+// (the first pass takes the bits that are left over: the low signature bits are uniform, and a narrow first digit
+// keeps the runs a block writes per digit long; the later digits are skewed anyway)
 constexpr int kSortThreads = 256;
 constexpr int kSortStrips = 16;                          // 32-key strips per warp
 constexpr int kSortTile = kSortThreads * kSortStrips;    // 4096 keys per block
 constexpr int kRadix = 256;
 
 // counts[digit * nblocks + block]
-__global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* __restrict__ keys, uint64_t n, int shift,
+__global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t mask,
                                                                 uint32_t* __restrict__ counts, uint32_t nblocks)
 {
     __shared__ uint32_t hist[kRadix];
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* _
     {
         const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
         const bool in = idx < n;
-        const uint32_t d = in ? ((keys[idx] >> shift) & 0xFFu) : 0xFFFFFFFFu;
+        const uint32_t d = in ? ((keys[idx] >> shift) & mask) : 0xFFFFFFFFu;
         // warp-aggregated shared atomics: bins are heavily skewed (minimizers are minima)
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
         if (in && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* _
 
 // offsets: exclusive scan of counts (same layout).  The 64-bit values are the records' cards (core.cuh).
 __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __restrict__ keys_in, const unsigned long long* __restrict__ vals_in,
-                                                              uint64_t n, int shift, const uint32_t* __restrict__ offsets, uint32_t nblocks,
+                                                              uint64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ offsets, uint32_t nblocks,
                                                               uint32_t* __restrict__ keys_out, unsigned long long* __restrict__ vals_out)
 {
     __shared__ uint32_t warp_hist[kSortThreads / 32][kRadix];   // 8 KB
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
         const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
         const bool in = idx < n;
         key[i] = in ? keys_in[idx] : 0xFFFFFFFFu;
-        const uint32_t d = in ? ((key[i] >> shift) & 0xFFu) : 0xFFFFFFFFu;
+        const uint32_t d = in ? ((key[i] >> shift) & mask) : 0xFFFFFFFFu;
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
         const uint32_t before = in ? warp_hist[warp][d] : 0;
         rank[i] = before + __popc(peers & ((1u << lane) - 1));
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
         const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
         if (idx < n)
         {
-            const uint32_t d = (key[i] >> shift) & 0xFFu;
+            const uint32_t d = (key[i] >> shift) & mask;
             const uint32_t dst = warp_hist[warp][d] + rank[i];
             keys_out[dst] = key[i];
             vals_out[dst] = vals_in[idx];
