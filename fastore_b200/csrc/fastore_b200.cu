@@ -197,12 +197,8 @@ cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_
     const uint64_t n = pa.B.n_records;
     const PlacePlan pl = make_place_plan(pa.P, pa.G, max_len, max_head);
     const uint64_t tiles = (n + pl.T - 1) / pl.T;
-    // placement tables: tile ranges, then every record's position inside its tile
-    const unsigned grid_t = (unsigned)((4 * (tiles + 1) + 255) / 256);
-    tile_base_kernel<<<grid_t, 256, 0, st>>>(pa, pl.T, tiles, pm.tbase);
-    placement_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pa, pl.T, pm);
-    // only the words two tiles share have to be zero before K4 runs
-    zero_boundary_words_kernel<<<grid_t, 256, 0, st>>>(pa.O, tiles, pm.tbase);
+    // placement tables (tile ranges, every record's position inside its tile) and the zeroing of the words two tiles share
+    placement_kernel<<<(unsigned)((tiles * pl.T + 255) / 256), 256, 0, st>>>(pa, pm, tiles);
     cudaError_t e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
     if (e != cudaSuccess) return e;
     // persistent blocks: as many as fit on the device at once
@@ -212,7 +208,7 @@ cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel, (int)pl.threads, pl.total_bytes)) != cudaSuccess) return e;
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
     place_kernel<<<blocks, pl.threads, pl.total_bytes, st>>>(pa, pl, pm, tiles);
-    *launches += 4;
+    *launches += 2;
     return cudaGetLastError();
 }
 

@@ -365,14 +365,18 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
 #endif
         }
         // ---- title, key and card --------------------------------------------------------------------------------------
+        if (P.has_headers)
+        {   // the two lanes of a pair take one part of the title each (a single-end lane takes both)
+            const uint32_t* hw = reinterpret_cast<const uint32_t*>(hslots + (size_t)lrec * pl.head_pieces * 16u);
+            const uint32_t a_head_rec = P.paired ? __shfl_sync(0xFFFFFFFFu, a_head, lane & ~1u) : a_head;
+            if (live)
+            {
+                pack_head_part(hw, 16u + a_head_rec, Hrec, m, my_stage + G.qw);
+                if (!P.paired) pack_head_part(hw, 16u + a_head_rec, Hrec, 1u, my_stage + G.qw);
+            }
+        }
         if (live && m == 0)
         {
-            if (P.has_headers)
-            {
-                SegEmit eh = seg_open(my_stage + G.qw, 0, head_bits);
-                pack_head(reinterpret_cast<const uint32_t*>(hslots + (size_t)lrec * pl.head_pieces * 16u), 16u + a_head, H, eh);
-                seg_finish(eh, false);
-            }
             keys[i] = (cur.ch << P.key_bits) | sig;
             cards[i] = card_make((uint32_t)i, inf, lenA, lenB, H);
             if (sig_out) { sig_out[i] = sig; info_out[i] = inf; }

@@ -511,13 +511,21 @@ FSB_HD uint32_t gather4x7(uint32_t x)
     return ((c & 0x3FFF0000u) >> 2) | (c & 0x00003FFFu);
 }
 // Four characters per step; `hold` keeps the n < 32 stream bits not yet pushed, left aligned.
-FSB_HD void pack_head(const uint32_t* w, uint32_t addr, uint32_t H, SegEmit& e)
+// The title is packed in two parts that start at word boundaries of the stream, so that the two lanes of a pair
+// can take one each: part 0 = the length byte and the first eight characters (64 bits), part 1 = the rest.
+// `region` is the word the title starts in (bit 0); both parts finish their own word 0.
+FSB_HD void pack_head_part(const uint32_t* w, uint32_t addr, uint32_t H, uint32_t part, uint32_t* region)
 {
-    uint32_t hold = (H & 0xFFu) << 24, n = 8;
-    if (H > 1u)
+    const uint32_t head_bits = 8u + 7u * (H ? H - 1u : 0u);
+    const uint32_t groups_total = H > 1u ? (H + 2u) >> 2 : 0u;  // ceil((H - 1) / 4); characters past the title code to unspecified bits
+    const uint32_t groups = part ? (groups_total > 2u ? groups_total - 2u : 0u) : (groups_total < 2u ? groups_total : 2u);
+    const uint32_t nbits = part ? (head_bits > 64u ? head_bits - 64u : 0u) : (head_bits < 64u ? head_bits : 64u);
+    if (nbits == 0) return;
+    SegEmit e = seg_open(region, part ? 64u : 0u, nbits);
+    uint32_t hold = part ? 0u : (H & 0xFFu) << 24, n = part ? 0u : 8u;
+    if (groups)
     {
-        SymReader rd = reader_open(w, addr + 1u, H - 1u, false);
-        const uint32_t groups = (H + 2u) >> 2;                    // ceil((H - 1) / 4); characters past the title code to unspecified bits
+        SymReader rd = reader_open(w, addr + (part ? 9u : 1u), 4u * groups, false);
         for (uint32_t g = 0; g < groups; ++g)
         {
             const uint32_t c = gather4x7(reader_next(rd)) << 4;   // 28 bits, left aligned
@@ -528,6 +536,12 @@ FSB_HD void pack_head(const uint32_t* w, uint32_t addr, uint32_t H, SegEmit& e)
     }
     if (n) seg_push(e, hold);
     seg_close(e);
+    seg_finish(e, false);
+}
+FSB_HD void pack_head(const uint32_t* w, uint32_t addr, uint32_t H, uint32_t* region)
+{
+    pack_head_part(w, addr, H, 0u, region);
+    pack_head_part(w, addr, H, 1u, region);
 }
 
 // ---- per-record framing (StoreRecords SE :734-759 / PE :815-859, StoreNextRecord :113-153) --------------

@@ -175,7 +175,7 @@ inline PlacePlan make_place_plan(const DeviceParams& P, const SlotGeom& G, uint3
 }
 
 // ---- placement tables -------------------------------------------------------------------------------------------
-// Everything K4 has to look up per record is worked out beforehand by two streaming kernels with
+// Everything K4 has to look up per record is worked out beforehand by a streaming kernel with
 // plenty of threads to hide the dependent loads (bin of the record -> start of the bin -> scans), so
 // that K4 itself only reads arrays indexed by the sorted position:
 //   tbase[tile][s]   first bit of the tile in stream s (the bin's first byte when its first record opens a bin);
@@ -189,55 +189,51 @@ struct Placement
     unsigned long long* tbase;
 };
 
-__global__ void __launch_bounds__(256) tile_base_kernel(PlaceArgs a, uint32_t T, uint64_t tiles, unsigned long long* __restrict__ tbase)
+// One kernel, one warp per tile of T = 32 sorted records: every lane works out its record's stream positions,
+// lane 0's record gives the tile's first bit (the bin's first byte when the record opens a bin), which is also where
+// the tile-boundary word may have to be cleared: write_out merges the first / last word of a tile with atomicOr when
+// it is shared with the neighbouring tile; those words -- and only those -- must be zero beforehand (this replaces
+// a memset of the whole output).  The last warp also writes the end-of-stream entry tbase[tiles].
+__global__ void __launch_bounds__(256) placement_kernel(PlaceArgs a, Placement pm, uint64_t tiles)
 {
-    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (tile, stream)
-    if (x >= 4 * (tiles + 1)) return;
-    const uint64_t tile = x >> 2;
-    const int s = (int)(x & 3u);
-    const uint64_t i0 = tile * T, n = a.B.n_records;
-    unsigned long long b0 = 0;
-    if (!(s == 3 && !a.P.has_headers))
-    {
-        if (i0 < n)
-        {
-            const uint32_t bin = a.A.bin_of[i0];
-            const uint64_t start = a.A.bin_start[bin];
-            b0 = (i0 == start) ? 8ull * a.BO.B[s][bin] : stream_offset(a, s, i0, bin, start);
-        }
-        else b0 = 8ull * a.BO.B[s][*a.nb_ptr];
-    }
-    tbase[x] = b0;
-}
-
-__global__ void __launch_bounds__(256) placement_kernel(PlaceArgs a, uint32_t T, Placement pm)
-{
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.B.n_records) return;
-    const uint32_t bin = a.A.bin_of[i];
-    const uint64_t start = a.A.bin_start[bin];
-    const uint64_t tile = i / T;
+    const uint64_t n = a.B.n_records;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // blockDim is a multiple of the tile size
+    const uint64_t tile = i / kPlaceTile;
+    if (tile >= tiles) return;                                                  // whole warps
+    const unsigned lane = threadIdx.x & 31;
+    const bool live = i < n;
+    uint32_t bin = 0;
+    uint64_t start = 0;
+    if (live) { bin = a.A.bin_of[i]; start = a.A.bin_start[bin]; }
 #pragma unroll
     for (int s = 0; s < 4; ++s)
     {
-        uint32_t loc = 0;
-        if (!(s == 3 && !a.P.has_headers)) loc = staging_bit(stream_offset(a, s, i, bin, start), pm.tbase[4 * tile + s]);
-        pm.loc[s][i] = loc;
+        const bool has = !(s == 3 && !a.P.has_headers);
+        unsigned long long off = 0, b0 = 0;
+        if (live && has)
+        {
+            off = stream_offset(a, s, i, bin, start);
+            b0 = (i == start) ? 8ull * a.BO.B[s][bin] : off;                    // meaningful on lane 0: the tile's first bit
+        }
+        b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+        if (live) pm.loc[s][i] = has ? staging_bit(off, b0) : 0u;
+        if (lane == 0)
+        {
+            pm.tbase[4 * tile + s] = b0;
+            if (b0 & 31u) a.O.w[s][b0 >> 5] = 0;
+            if (tile + 1 == tiles)
+            {   // end of the stream
+                const unsigned long long e = has ? 8ull * a.BO.B[s][*a.nb_ptr] : 0ull;
+                pm.tbase[4 * tiles + s] = e;
+                if (e & 31u) a.O.w[s][e >> 5] = 0;
+            }
+        }
     }
-    const bool nbin = (a.S.skeys[i] & ((1u << a.P.key_bits) - 1u)) == a.P.nbin;
-    pm.binfo[i] = (a.A.bin_min[bin] & 0xFFu) | ((a.A.bin_max[bin] & 0xFFu) << 8) | (i == start ? 0x10000u : 0u) | (nbin ? 0x20000u : 0u);
-}
-
-// ---- tile-boundary words ---------------------------------------------------------------------------------------
-// write_out merges the first / last word of a tile with atomicOr when it is shared with the
-// neighbouring tile; those words -- and only those -- must be zero beforehand (this replaces a
-// memset of the whole output).  One thread per (tile boundary, stream).
-__global__ void __launch_bounds__(256) zero_boundary_words_kernel(OutStreams O, uint64_t tiles, const unsigned long long* __restrict__ tbase)
-{
-    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= 4 * (tiles + 1)) return;
-    const unsigned long long b = tbase[x];
-    if (b & 31u) O.w[x & 3u][b >> 5] = 0;
+    if (live)
+    {
+        const bool nbin = (a.S.skeys[i] & ((1u << a.P.key_bits) - 1u)) == a.P.nbin;
+        pm.binfo[i] = (a.A.bin_min[bin] & 0xFFu) | ((a.A.bin_max[bin] & 0xFFu) << 8) | (i == start ? 0x10000u : 0u) | (nbin ? 0x20000u : 0u);
+    }
 }
 
 // ---- K4 --------------------------------------------------------------------------------------------------------------

@@ -206,9 +206,7 @@ int run_pack(const DeviceParams& P, const fsb_chunk* ch, const uint32_t* sig, co
             if (P.has_headers)
             {
                 head.fill(ch->text[0], ch->text_size[0], r1.head_off, r1.head_len);
-                SegEmit eh = seg_open(slot.data() + G.qw, 0, head_bits);
-                pack_head(head.w.data(), head.addr, r1.head_len, eh);
-                seg_finish(eh, false);
+                pack_head(head.w.data(), head.addr, r1.head_len, slot.data() + G.qw);
             }
             uint32_t lenB = 0;
             prepack_mate<NW>(P, G, seqA, quaA, ra.seq_len, rev, plainA, nbin ? 0u : mpos, sfx, slot.data(), head_bits, false);
