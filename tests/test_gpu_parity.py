@@ -127,3 +127,23 @@ def test_parser_table_equals_generator_table_on_gpu_path():
         got = gpu_block_dict(g.bin_chunks([chunk])[0])
     O.assert_blocks_equal(got, want, "-C headers")
     assert int(recs["head_len"].max()) < int(r1["head_len"].min())
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_many_chunks_in_one_batch(paired):
+    """More than 32 chunks in one batch: K1 then looks the chunk of a record up by binary search in global memory
+    instead of the ballot over lane-resident chunk tables, and the sort key carries six chunk bits."""
+    params = N.make_params(signature_len=8, skip_zone_len=0, paired_end=paired)
+    keep, chunks = [], []
+    for ci in range(41):
+        n = 1 if ci % 10 == 3 else 700 + 37 * ci
+        cfg = synth.synth_config(n, 100 + (ci % 3) * 25, paired=paired, seed=300 + ci, first_index=ci * 10000, nrich=0.05, lowcomplex=0.05, alln=0.01, tie=0.02)
+        t = synth.generate(cfg, threads=2)
+        keep.append(t)
+        chunks.append(N.make_chunk(t[0], t[2], t[1], t[3]))
+    with GpuBinner(params, per_read=True) as g:
+        g.stage(chunks)                 # one batch, whatever the sub-batch size of fsb_bin_chunks
+        g.run()
+        got = g.fetch()
+    for ci, ch in enumerate(chunks):
+        O.assert_blocks_equal(gpu_block_dict(got[ci]), O.bin_chunk("orc", params, ch), f"chunk {ci} of 41")
