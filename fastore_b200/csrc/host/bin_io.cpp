@@ -132,6 +132,15 @@ extern "C" int fsh_reader_next(fsh_reader* r, uint8_t* buf1, uint64_t* size1, ui
         for (int m = 0; m < nf; ++m) end[m] = r->next_record_pos(buf[m], r->block - r->window, r->block);
         if (r->paired)
         {
+            // DELIBERATE DEVIATION from FastqStream.cpp:166-189.  The reference means to advance the file that is behind by
+            // (id difference) records = 4 lines each, but it increments its read-id counter once per skipped *line*; after
+            // the first loop rid_1 is therefore 3 * diff ahead, the second branch fires as well and skips 12 * diff lines of
+            // file 2 -- the two chunks then hold different reads and every following pair of the chunk is mis-mated (the
+            // ASSERT(rid_1 == rid_2) behind it is compiled out in release builds).  Here the arithmetic is per record, so both
+            // chunks end at the same read.  Whenever the two cuts already point at the same read -- mate files with records
+            // of equal size, which is every input the parity tests and BASELINE configs use -- the code paths are identical
+            // and the chunk boundaries are the reference's, byte for byte (tests/test_bin_files.py); for inputs that trigger
+            // the reference's bug the files differ by design (tests/test_host_edge_cases.py checks the mates stay paired).
             uint64_t id1 = fsh_reader::next_read_id(buf[0] + end[0], r->window), id2 = fsh_reader::next_read_id(buf[1] + end[1], r->window);
             if (id1 < id2) { for (uint64_t i = 0, nl = (id2 - id1) * 4; i < nl; ++i) { r->skip_to_eol(buf[0], end[0], r->block); end[0]++; } id1 = id2; }
             if (id1 > id2) { for (uint64_t i = 0, nl = (id1 - id2) * 4; i < nl; ++i) { r->skip_to_eol(buf[1], end[1], r->block); end[1]++; } }

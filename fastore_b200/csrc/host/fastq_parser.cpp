@@ -42,18 +42,23 @@ inline bool is_dna(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 
 
 extern "C" uint64_t fsh_max_records(const uint8_t* text, uint64_t size)
 {
-    // a record has at least 4 line ends; count LFs (CR-only files are not produced by anything we read)
-    uint64_t lf = 0;
-    const uint8_t* p = text;
-    const uint8_t* e = text + size;
-    while (p < e)
-    {
-        const void* q = std::memchr(p, '\n', (size_t)(e - p));
-        if (!q) break;
-        lf++;
-        p = (const uint8_t*)q + 1;
-    }
-    return lf / 4 + 2;
+    // a record has at least 4 line ends.  SkipLine (FastqParser.cpp:46-68) accepts LF, CRLF and a lone CR,
+    // so line ends = LFs + CRs that are not followed by an LF (two memchr sweeps; the second finds
+    // nothing in an LF-only file)
+    auto count = [&](int ch, bool lone_only) {
+        uint64_t n = 0;
+        const uint8_t* p = text;
+        const uint8_t* e = text + size;
+        while (p < e)
+        {
+            const uint8_t* q = (const uint8_t*)std::memchr(p, ch, (size_t)(e - p));
+            if (!q) break;
+            if (!lone_only || q + 1 >= e || q[1] != '\n') n++;
+            p = q + 1;
+        }
+        return n;
+    };
+    return (count('\n', false) + count('\r', true)) / 4 + 2;
 }
 
 extern "C" int fsh_parse_chunk(const uint8_t* text, uint64_t size, int keep_headers, int keep_comments,

@@ -11,6 +11,9 @@
 // Chunk i goes to GPU i mod G; blocks are committed in chunk order (the reference's -t N writes
 // them in arrival order, which is why only its -t1 output is reproducible).  Extra options:
 //     -G<n>  GPUs to use (default: all sm_100 devices)      -P<n>  parser threads (default 4)
+//     -W<n>  workers (contexts) per GPU (default 2: one worker's copies overlap the other's kernels)
+//     -K<n>  chunks a worker hands to one fsb_bin_chunks call when that many are already parsed
+//            (default 256 MiB / block size, 1..16: small -b chunks are batched into full-size launches)
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -32,7 +35,7 @@ struct Args
 {
     std::vector<std::string> in, out;
     fsh_bin_config cfg{};
-    int gpus = 0, parsers = 4, threads = 1;
+    int gpus = 0, parsers = 4, threads = 1, workers = 2, per_call = 0;
     bool verbose = false, gz = false;
 };
 
@@ -85,6 +88,8 @@ bool parse_args(int argc, const char** argv, Args& a)
         case 'I': p.quality_offset = 64; break;
         case 'G': a.gpus = (int)v; break;
         case 'P': a.parsers = (int)std::max(1L, v); break;
+        case 'W': a.workers = (int)std::min(8L, std::max(1L, v)); break;
+        case 'K': a.per_call = (int)std::min(64L, std::max(1L, v)); break;
         }
     }
     if (a.in.empty()) { std::fprintf(stderr, "Error: no input file(s) specified\n"); return false; }
@@ -124,7 +129,7 @@ struct Pipeline
 int main(int argc, const char** argv)
 {
     Args a;
-    if (argc < 2 || !parse_args(argc, argv, a)) { std::fprintf(stderr, "usage: fastore_bin_b200 e -i<files> -o<out> [-z] [-H] [-C] [-q<0-2>] [-w<n>] [-I] [-p<n>] [-s<n>] [-m<n>] [-b<MB>] [-G<gpus>] [-P<parser threads>] [-v]\n"); return -1; }
+    if (argc < 2 || !parse_args(argc, argv, a)) { std::fprintf(stderr, "usage: fastore_bin_b200 e -i<files> -o<out> [-z] [-H] [-C] [-q<0-2>] [-w<n>] [-I] [-p<n>] [-s<n>] [-m<n>] [-b<MB>] [-G<gpus>] [-W<workers per GPU>] [-K<chunks per call>] [-P<parser threads>] [-v]\n"); return -1; }
     const bool pe = a.cfg.params.paired_end != 0;
     const int ndev = fsb_device_count();
     if (ndev == 0) { std::fprintf(stderr, "Error: no sm_100 GPU available (this tool has no CPU fallback)\n"); return -1; }
@@ -140,8 +145,10 @@ int main(int argc, const char** argv)
     if (!writer) { std::fprintf(stderr, "Error: %s\n", fsh_last_error()); return -1; }
 
     const auto t0 = std::chrono::steady_clock::now();
+    const int NWK = G * a.workers;                                  // workers: worker w drives GPU w mod G
+    const int K = a.per_call > 0 ? a.per_call : (int)std::min<uint64_t>(16, std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(a.cfg.fastq_block_size, 1)));
     Pipeline P;
-    const int nbuf = G + a.parsers + 1;
+    const int nbuf = NWK * K + a.parsers + 1;
     std::vector<Chunk> chunks((size_t)nbuf);
     for (Chunk& c : chunks)
     {
@@ -194,7 +201,8 @@ int main(int argc, const char** argv)
                     const int rc = fsh_parse_chunk(c->text[m], c->size[m], a.cfg.params.reads_have_headers, a.cfg.keep_comments, a.cfg.params.quality_offset,
                                                    a.cfg.params.quality_method, c->rec[m].data(), c->rec[m].size(), &st);
                     c->rec[m].resize(st.n_records);
-                    if (rc != FSB_OK) { c->bad = true; c->err = "chunk " + std::to_string(c->idx) + ": " + std::to_string(st.invalid_records) + " record(s) outside the input contract (symbols ACGTN, length <= 255, quality range)"; }
+                    if (st.stop_reason == FSH_STOP_CAPACITY) { c->bad = true; c->err = "chunk " + std::to_string(c->idx) + ": record table too small (internal error)"; }
+                    else if (rc != FSB_OK) { c->bad = true; c->err = "chunk " + std::to_string(c->idx) + ": " + std::to_string(st.invalid_records) + " record(s) outside the input contract (symbols ACGTN, length <= 255, quality range)"; }
                 }
                 if (pe && c->rec[0].size() != c->rec[1].size())
                 {   // the reference stops at the shorter of the two (FastqParser.cpp:527)
@@ -206,53 +214,68 @@ int main(int argc, const char** argv)
                 P.cv.notify_all();
             }
         });
-    // ---- one worker per GPU: chunk i -> GPU i mod G, blocks committed in chunk order ---------------------------------
+    // ---- workers: chunk i -> worker i mod (G * W) on GPU (i mod G * W) mod G, blocks committed in chunk order -----------
     std::atomic<uint64_t> total_records{0};
     std::vector<std::thread> t_gpu;
-    for (int g = 0; g < G; ++g)
-        t_gpu.emplace_back([&, g] {
+    for (int w = 0; w < NWK; ++w)
+        t_gpu.emplace_back([&, w] {
             fsb_ctx* ctx = nullptr;
-            if (fsb_create(&a.cfg.params, g, nullptr, &ctx) != FSB_OK) { P.fail(std::string("GPU ") + std::to_string(g) + ": " + fsb_last_error(nullptr)); return; }
-            for (uint64_t idx = (uint64_t)g; ; idx += (uint64_t)G)
+            if (fsb_create(&a.cfg.params, w % G, nullptr, &ctx) != FSB_OK) { P.fail(std::string("GPU ") + std::to_string(w % G) + ": " + fsb_last_error(nullptr)); return; }
+            std::vector<Chunk*> mine;
+            std::vector<fsb_chunk> in;
+            bool stop = false;
+            for (uint64_t idx = (uint64_t)w; !stop; )
             {
-                Chunk* c = nullptr;
+                // the worker's next chunk (blocking), plus the ones after it that are parsed already
+                mine.clear();
                 {
                     std::unique_lock<std::mutex> l(P.mu);
                     P.cv.wait(l, [&] { return P.parsed.count(idx) || (P.read_done && idx >= P.n_read) || P.failed; });
                     if (P.failed || !P.parsed.count(idx)) break;
-                    c = P.parsed[idx]; P.parsed.erase(idx);
+                    for (uint64_t j = idx; (int)mine.size() < K && P.parsed.count(j); j += (uint64_t)NWK) { mine.push_back(P.parsed[j]); P.parsed.erase(j); }
                 }
-                if (c->bad) { P.fail(c->err); break; }
-                fsb_block blk;
-                std::memset(&blk, 0, sizeof(blk));
-                const uint64_t n = c->rec[0].size();
-                if (n)
+                in.clear();
+                std::vector<size_t> slot(mine.size(), (size_t)-1);       // chunk -> position in the call (empty chunks are not sent)
+                for (size_t q = 0; q < mine.size() && !stop; ++q)
                 {
+                    Chunk* c = mine[q];
+                    if (c->bad) { P.fail(c->err); stop = true; break; }
+                    if (c->rec[0].empty()) continue;
                     fsb_chunk ch;
                     std::memset(&ch, 0, sizeof(ch));
                     for (int m = 0; m < (pe ? 2 : 1); ++m) { ch.text[m] = c->text[m]; ch.text_size[m] = c->size[m]; ch.records[m] = c->rec[m].data(); }
-                    ch.n_records = n;
-                    if (fsb_bin_chunks(ctx, &ch, 1, &blk) != FSB_OK) { P.fail(std::string("chunk ") + std::to_string(idx) + ": " + fsb_last_error(ctx)); break; }
+                    ch.n_records = c->rec[0].size();
+                    slot[q] = in.size();
+                    in.push_back(ch);
                 }
-                {   // the writer turn: BinFileWriter is single-threaded state (BinFile.cpp:103-146), and order defines the bytes
-                    std::unique_lock<std::mutex> l(P.mu);
-                    P.cv.wait(l, [&] { return P.next_write == idx || P.failed; });
-                    if (P.failed) break;
-                }
-                int rc = FSB_OK;
-                if (n)
+                if (stop) break;
+                std::vector<fsb_block> out(in.size());
+                if (!in.empty() && fsb_bin_chunks(ctx, in.data(), (uint32_t)in.size(), out.data()) != FSB_OK)
+                { P.fail(std::string("chunk ") + std::to_string(idx) + ": " + fsb_last_error(ctx)); break; }
+                for (size_t q = 0; q < mine.size() && !stop; ++q, idx += (uint64_t)NWK)
                 {
-                    rc = fsh_writer_add_titles(writer, c->text[0], c->rec[0].data(), n);
-                    if (rc == FSB_OK && pe) rc = fsh_writer_add_titles(writer, c->text[1], c->rec[1].data(), n);
-                    if (rc == FSB_OK) rc = fsh_writer_add_block(writer, &blk);
+                    Chunk* c = mine[q];
+                    const uint64_t n = c->rec[0].size();
+                    {   // the writer turn: BinFileWriter is single-threaded state (BinFile.cpp:103-146), and order defines the bytes
+                        std::unique_lock<std::mutex> l(P.mu);
+                        P.cv.wait(l, [&] { return P.next_write == idx || P.failed; });
+                        if (P.failed) { stop = true; break; }
+                    }
+                    int rc = FSB_OK;
+                    if (n)
+                    {
+                        rc = fsh_writer_add_titles(writer, c->text[0], c->rec[0].data(), n);
+                        if (rc == FSB_OK && pe) rc = fsh_writer_add_titles(writer, c->text[1], c->rec[1].data(), n);
+                        if (rc == FSB_OK) rc = fsh_writer_add_block(writer, &out[slot[q]]);
+                    }
+                    if (rc != FSB_OK) { P.fail(std::string("writing chunk ") + std::to_string(idx) + ": " + fsh_last_error()); stop = true; break; }
+                    total_records += n;
+                    if (a.verbose) std::fprintf(stderr, "\rchunk %llu: %llu records, %llu bins   ", (unsigned long long)idx, (unsigned long long)n, (unsigned long long)(n ? out[slot[q]].n_bins : 0));
+                    std::lock_guard<std::mutex> l(P.mu);
+                    P.next_write = idx + 1;
+                    P.pool.push_back(c);
+                    P.cv.notify_all();
                 }
-                if (rc != FSB_OK) { P.fail(std::string("writing chunk ") + std::to_string(idx) + ": " + fsh_last_error()); break; }
-                total_records += n;
-                if (a.verbose) std::fprintf(stderr, "\rchunk %llu: %llu records, %llu bins   ", (unsigned long long)idx, (unsigned long long)n, (unsigned long long)blk.n_bins);
-                std::lock_guard<std::mutex> l(P.mu);
-                P.next_write = idx + 1;
-                P.pool.push_back(c);
-                P.cv.notify_all();
             }
             fsb_destroy(ctx);
         });
@@ -268,8 +291,8 @@ int main(int argc, const char** argv)
     if (a.verbose)
     {
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        std::fprintf(stderr, "\n%llu records in %llu chunks on %d GPU(s): %.2f s, %.0f records/s\n", (unsigned long long)total_records.load(),
-                     (unsigned long long)P.next_write, G, s, total_records.load() / std::max(s, 1e-9));
+        std::fprintf(stderr, "\n%llu records in %llu chunks on %d GPU(s) x %d worker(s): %.2f s, %.0f records/s\n", (unsigned long long)total_records.load(),
+                     (unsigned long long)P.next_write, G, a.workers, s, total_records.load() / std::max(s, 1e-9));
     }
     return 0;
 }

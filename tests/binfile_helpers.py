@@ -54,8 +54,10 @@ def run_reference_bin(files, out_prefix: Path, flags: dict, threads: int = 1):
     subprocess.run(cmd, check=True, capture_output=True, timeout=600)
 
 
-def run_cli(files, out_prefix: Path, flags: dict, gpus: int = 1):
+def run_cli(files, out_prefix: Path, flags: dict, gpus: int = 1, workers: int | None = None, per_call: int | None = None):
     cmd = [str(CLI), "e", "-i" + " ".join(str(f) for f in files), f"-o{out_prefix}", f"-G{gpus}"] + flags_to_args(flags)
+    if workers is not None: cmd.append(f"-W{workers}")
+    if per_call is not None: cmd.append(f"-K{per_call}")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     return r
@@ -144,6 +146,25 @@ def decode_with_reference(prefix: Path, out_files, paired: bool):
     """reference `fastore_bin d`: an independent reader of our bin files (Mode C)."""
     cmd = [str(REF_DIR / "fastore_bin"), "d", f"-i{prefix}", "-o" + " ".join(str(f) for f in out_files), "-t1"] + (["-z"] if paired else [])
     subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+
+
+def downstream_roundtrip(prefix: Path, work: Path, paired: bool, rebin: bool):
+    """The reference's own consumers of a bin file (scripts/fastore_compress.sh): [fastore_rebin e -p2 ->] fastore_pack e ->
+    fastore_pack d.  Returns the decoded FASTQ paths."""
+    pe = ["-z"] if paired else []
+    src = prefix
+    if rebin:
+        subprocess.run([str(REF_DIR / "fastore_rebin"), "e", f"-i{src}", f"-o{work}/rebin2", "-t1", "-r", "-w1024", "-W1024", "-p2"] + pe,
+                       check=True, capture_output=True, timeout=900)
+        src = work / "rebin2"
+        pack = ["-r", "-f256", "-c10", "-d8", "-w1024", "-W1024"]
+    else:
+        pack = ["-f256", "-c10", "-d8", "-w256", "-W256"]
+    subprocess.run([str(REF_DIR / "fastore_pack"), "e", f"-i{src}", f"-o{work}/packed", "-t1"] + pack + pe, check=True, capture_output=True, timeout=900)
+    outs = [work / "unpacked_1.fastq"] + ([work / "unpacked_2.fastq"] if paired else [])
+    subprocess.run([str(REF_DIR / "fastore_pack"), "d", f"-i{work}/packed", "-o" + " ".join(str(o) for o in outs), "-t1"] + pe,
+                   check=True, capture_output=True, timeout=900)
+    return outs
 
 
 def fastq_records(path: Path):

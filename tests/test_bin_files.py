@@ -50,14 +50,44 @@ def test_reference_decoder_reads_our_files(tmp_path, paired):
 
 
 @pytest.mark.gpu
-def test_cli_on_all_gpus_is_byte_identical(tmp_path):
-    """Chunk i -> GPU i mod G with an ordered writer turn: the files do not depend on the number of GPUs."""
+@pytest.mark.parametrize("workers,per_call", [(2, 1), (3, 4)])
+def test_cli_with_many_workers_is_byte_identical(tmp_path, workers, per_call):
+    """Chunk i -> worker i mod (G * W) with an ordered writer turn: the files depend neither on the number of GPUs nor
+    on the workers per GPU nor on how many chunks one fsb_bin_chunks call takes.  Runs on every device the box has and
+    with at least two workers (contexts) on each, so the N>1 dispatch is exercised on a 1-GPU box too."""
     from fastore_b200 import _native as N
     G = N.cuda_lib().fsb_device_count()
-    if G < 2:
-        pytest.skip("needs at least 2 GPUs")
-    files = BF.write_fastq(tmp_path, "mg", 40000, 150, True, 220)
+    assert G >= 1
+    files = BF.write_fastq(tmp_path, "mg", 60000, 150, True, 220)
     flags = dict(paired=True, b=2)
     BF.run_reference_bin(files, tmp_path / "ref", flags)
-    BF.run_cli(files, tmp_path / "ours", flags, gpus=G)
+    BF.run_cli(files, tmp_path / "ours", flags, gpus=G, workers=workers, per_call=per_call)
     BF.assert_bin_files_equal(tmp_path / "ours", tmp_path / "ref", True)
+
+
+DOWNSTREAM = [("se_c0_pack", False, False, dict(s=10, b=2)), ("pe_c1_rebin_pack", True, True, dict(paired=True, b=2)),
+              ("se_c1_rebin_pack", False, True, dict(b=2))]
+
+
+@pytest.mark.parametrize("name,paired,rebin,flags", DOWNSTREAM, ids=[d[0] for d in DOWNSTREAM])
+def test_reference_rebin_and_pack_consume_host_chain_files(tmp_path, name, paired, rebin, flags):
+    """Mode C, downstream tools: fastore_rebin e -p2 -> fastore_pack e -> fastore_pack d (the reference's own pipeline,
+    scripts/fastore_compress.sh) accept the files of our writer and give back the input record multiset.  CPU tier: blocks
+    from the oracle, so the host writer is what is under test."""
+    files = BF.write_fastq(tmp_path, "in", 9000, 100, paired, 230 + int(paired), nrich=0.03)
+    BF.host_chain(files, tmp_path / "ours", flags, BF.oracle_producer)
+    outs = BF.downstream_roundtrip(tmp_path / "ours", tmp_path, paired, rebin)
+    for src, dec in zip(files, outs):
+        assert sorted(BF.fastq_records(src)) == sorted(BF.fastq_records(dec))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,paired,rebin,flags", DOWNSTREAM, ids=[d[0] for d in DOWNSTREAM])
+def test_reference_rebin_and_pack_consume_cli_files(tmp_path, name, paired, rebin, flags):
+    """The same with the bin files of the real CLI (GPU path): what north_star asks -- fastore_rebin and fastore_pack
+    consume our output unchanged (RebinModule.cpp:32, BinFile.cpp:592-628)."""
+    files = BF.write_fastq(tmp_path, "in", 9000, 100, paired, 230 + int(paired), nrich=0.03)
+    BF.run_cli(files, tmp_path / "ours", flags)
+    outs = BF.downstream_roundtrip(tmp_path / "ours", tmp_path, paired, rebin)
+    for src, dec in zip(files, outs):
+        assert sorted(BF.fastq_records(src)) == sorted(BF.fastq_records(dec))
