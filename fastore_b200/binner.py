@@ -35,7 +35,7 @@ class BinBlock:
 
 class GpuBinner:
     def __init__(self, params: N.FsbParams, device: int = 0, stream: int | None = None, per_read: bool = False,
-                 profile: bool = False, sub_batch_records: int | None = None):
+                 profile: bool = False, sub_batch_records: int | None = None, validate: bool | None = None):
         self._lib = N.cuda_lib()
         self._ctx = C.c_void_p()
         self.params = params
@@ -47,6 +47,8 @@ class GpuBinner:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_PER_READ, 1))
         if profile:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_PROFILE, 1))
+        if validate is not None:
+            self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_VALIDATE, 1 if validate else 0))
         if sub_batch_records is not None:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_SUBBATCH_RECORDS, sub_batch_records))
 

@@ -37,14 +37,16 @@ struct DevBuf
 {
     void* p = nullptr;
     size_t cap = 0;
-    cudaError_t ensure(size_t bytes)
+    // `zero_on`: clear the buffer on that stream when it is (re)allocated -- for buffers whose padding may be over-read by
+    // aligned vector loads (the clear is ordered before whatever the caller enqueues on the stream next)
+    cudaError_t ensure(size_t bytes, const cudaStream_t* zero_on = nullptr)
     {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         const size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
+        if (e == cudaSuccess) { cap = want; if (zero_on) e = cudaMemsetAsync(p, 0, want, *zero_on); }
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -288,7 +290,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     uint64_t h2d = 0;
     for (int m = 0; m < nfiles; ++m)
     {
-        CUDA_TRY(c, b.d_text[m].ensure(text_bytes[m] + kTextPad));
+        CUDA_TRY(c, b.d_text[m].ensure(text_bytes[m] + kTextPad, &st));      // padding between chunks is over-read by aligned window copies: keep it defined
         CUDA_TRY(c, b.d_rec[m].ensure((n + 1) * sizeof(fsb_record)));
         for (uint32_t ci = 0; ci < n_chunks; ++ci)
         {
@@ -316,7 +318,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     CUDA_TRY(c, b.d_stage_stats.ensure(sizeof(StageStats)));
     CUDA_TRY(c, b.h_stage_stats.ensure(2 * sizeof(StageStats)));
     StageStats init{};
-    init.first_bad = ~0ull; init.min_len = 0xFFFFFFFFu;
+    init.first_bad = ~0ull; init.first_bad_text = ~0ull; init.min_len = 0xFFFFFFFFu;
     b.h_stage_stats.as<StageStats>()[1] = init;                  // [1] initial value going up, [0] result coming back
     CUDA_TRY(c, cudaMemcpyAsync(b.d_stage_stats.p, b.h_stage_stats.as<StageStats>() + 1, sizeof(StageStats), cudaMemcpyHostToDevice, st));
     if (n)
@@ -326,6 +328,13 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
         const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
         stage_stats_kernel<<<blocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>());
         c->stats.kernel_launches++;
+        if (c->validate)
+        {   // FSB_OPT_VALIDATE: symbols, quality range and title characters behind the table (stage.cuh)
+            const uint64_t n_mates = c->dp.paired ? 2 * n : n;
+            const unsigned vblocks = (unsigned)std::min<uint64_t>((n_mates + 15) / 16, 148ull * 16);
+            validate_text_kernel<<<vblocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>());
+            c->stats.kernel_launches++;
+        }
     }
     CUDA_TRY(c, cudaMemcpyAsync(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, st));
     b.h2d_bytes = h2d;
@@ -349,6 +358,14 @@ int stage_complete(fsb_ctx* c, Batch& b)
         return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(stats.first_bad - b.chunk_first_rec[ci]) + " of chunk " + std::to_string(ci) +
                                           " violates the input contract (length 1..255, offsets inside the chunk, equal PE mate lengths); " +
                                           std::to_string(stats.n_bad) + " such record(s)");
+    }
+    if (stats.n_bad_text)
+    {
+        uint32_t ci = 0;
+        while (ci + 1 < n_chunks && b.chunk_first_rec[ci + 1] <= stats.first_bad_text) ++ci;
+        return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(stats.first_bad_text - b.chunk_first_rec[ci]) + " of chunk " + std::to_string(ci) +
+                                          " holds a byte outside the input contract (sequence symbols A C G T N, quality in [offset, offset + 64), 7-bit title characters); " +
+                                          std::to_string(stats.n_bad_text) + " such mate(s)");
     }
     const uint64_t bases = stats.bases, heads = stats.heads;
     b.total_bases = bases; b.total_head = heads;

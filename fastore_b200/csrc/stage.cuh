@@ -20,6 +20,8 @@ struct StageStats
     uint32_t min_len, max_len;       // over all mates
     uint32_t max_head;
     uint32_t n_bad;
+    unsigned long long first_bad_text;   // lowest record index with a symbol / quality / title byte outside the contract (~0 if none)
+    uint32_t n_bad_text, pad;
 };
 
 __global__ void __launch_bounds__(256) stage_stats_kernel(BatchView B, DeviceParams P, const uint64_t* __restrict__ text_size0,
@@ -56,6 +58,95 @@ __global__ void __launch_bounds__(256) stage_stats_kernel(BatchView B, DevicePar
     {
         atomicAdd(&st->bases, sh_bases); atomicAdd(&st->heads, sh_heads);
         atomicMin(&st->min_len, sh_min); atomicMax(&st->max_len, sh_max); atomicMax(&st->max_head, sh_hmax);
+    }
+}
+
+// ---- FSB_OPT_VALIDATE: the bytes behind the record table ---------------------------------------------------------
+// The reference leaves symbols outside ACGTN undefined (out-of-table look-ups in ComputeRC / StoreDna,
+// FastqRecord.h:95-96, FastqPacker.cpp:24-30) and indexes its 64-entry quality table with (q - offset)
+// unchecked (FastqPacker.cpp:250); K1 would code such bytes as something, silently.  This kernel rejects them
+// before the pipeline runs: sequence bytes must be one of A C G T N, quality bytes must lie in
+// [offset, offset + 64) for the 6- and 3-bit modes and be >= offset for the 1-bit mode, kept title characters
+// must be 7-bit (StoreHeader packs 7 bits per character, FastqPacker.cpp:272-287) -- the same rules the host
+// parser applies (csrc/host/fastq_parser.cpp).  It is a streaming pass over the staged text with 16-byte loads
+// (a half warp per mate: lane j checks the j-th aligned 16-byte piece of the sequence, of the quality and of the
+// title), part of fsb_stage, not of the timed fsb_run path.
+__device__ __forceinline__ uint32_t bytes_in_range_mask(int32_t lo, int32_t hi, int32_t word_base)     // 0xFF for every byte of the word whose offset is in [lo, hi)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) if (word_base + b >= lo && word_base + b < hi) m |= 0xFFu << (8 * b);
+    return m;
+}
+__device__ __forceinline__ bool dna_word_ok(uint32_t w, uint32_t m)
+{
+    // valid codes ^ 0x40: A 0x01, C 0x03, G 0x07, N 0x0E, T 0x14 -- members of a 32-bit set; anything >= 32 shifts the set out (shr clamps)
+    constexpr uint32_t kSet = (1u << 0x01) | (1u << 0x03) | (1u << 0x07) | (1u << 0x0E) | (1u << 0x14);
+    const uint32_t v = ((w ^ 0x40404040u) & m) | (0x01010101u & ~m);
+    uint32_t acc = 1;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    {
+        uint32_t r;
+        asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(kSet), "r"((v >> (8 * b)) & 0xFFu));
+        acc &= r;
+    }
+    return (acc & 1u) != 0;
+}
+__device__ __forceinline__ bool qua_word_ok(uint32_t w, uint32_t m, uint32_t off, uint32_t bad_bits)
+{
+    const uint32_t v = (w & m) | ((off * 0x01010101u) & ~m);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc |= ((v >> (8 * b)) & 0xFFu) - off;
+    return (acc & bad_bits) == 0;
+}
+
+__global__ void __launch_bounds__(256) validate_text_kernel(BatchView B, DeviceParams P, const uint64_t* __restrict__ text_size0,
+                                                            const uint64_t* __restrict__ text_size1, StageStats* __restrict__ st)
+{
+    const uint32_t half = threadIdx.x >> 4, l16 = threadIdx.x & 15u;                  // 16 half warps per block
+    const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
+    const uint32_t qua_bad = P.qua_bits == 1 ? 0x80000000u : 0xFFFFFFC0u;              // 1-bit mode: only q >= offset (the threshold compare takes any value)
+    for (uint64_t g = (uint64_t)blockIdx.x * 16u + half; g < n_mates; g += (uint64_t)gridDim.x * 16u)
+    {
+        const uint64_t i = P.paired ? (g >> 1) : g;
+        const uint32_t m = P.paired ? (uint32_t)(g & 1u) : 0u;
+        const uint32_t ch = find_chunk(B, i);
+        const fsb_record r = B.rec[m][i];
+        const uint8_t* text = B.text[m] + B.chunk_text_base[m][ch];
+        const uint64_t ts = (m ? text_size1 : text_size0)[ch];
+        // records whose views leave the chunk are reported by stage_stats_kernel; never follow them
+        if (r.seq_len < 1 || r.seq_len > 255 || (uint64_t)r.seq_off + r.seq_len > ts || (uint64_t)r.qua_off + r.seq_len > ts ||
+            (uint64_t)r.head_off + r.head_len > ts) continue;
+        bool ok = true;
+        const uint32_t L = r.seq_len, H = (m == 0 && P.has_headers) ? r.head_len : 0u;
+        // spans: sequence, quality, title characters 1 .. H-1
+        const uint64_t span_at[3] = {(uint64_t)r.seq_off, (uint64_t)r.qua_off, (uint64_t)r.head_off + 1u};
+        const uint32_t span_len[3] = {L, L, H > 1u ? H - 1u : 0u};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            if (span_len[k] == 0) continue;
+            const uint8_t* p0 = text + span_at[k];
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)15;    // the text buffers are padded: aligned pieces stay inside
+            const int32_t lo = (int32_t)(reinterpret_cast<uintptr_t>(p0) - a0), hi = lo + (int32_t)span_len[k];
+            for (int32_t piece = (int32_t)l16; piece * 16 < hi; piece += 16)
+            {
+                const uint4 q = *reinterpret_cast<const uint4*>(a0 + 16u * (uint32_t)piece);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t msk = bytes_in_range_mask(lo, hi, piece * 16 + 4 * j);
+                    if (msk == 0) continue;
+                    if (k == 0) ok = ok && dna_word_ok(w[j], msk);
+                    else if (k == 1) ok = ok && qua_word_ok(w[j], msk, P.qua_offset, qua_bad);
+                    else ok = ok && ((w[j] & msk & 0x80808080u) == 0);
+                }
+            }
+        }
+        if (!ok) { atomicAdd(&st->n_bad_text, 1u); atomicMin(&st->first_bad_text, (unsigned long long)i); }
     }
 }
 

@@ -144,7 +144,9 @@ typedef struct fsb_ctx fsb_ctx;
 enum {
     FSB_OPT_PER_READ = 1,    /* also return per-read signature/info arrays (parity Mode B)        */
     FSB_OPT_PROFILE = 2,     /* record CUDA events around every pipeline stage of fsb_run         */
-    FSB_OPT_VALIDATE = 3,    /* device-side input validation (symbols / quality range), default 1 */
+    FSB_OPT_VALIDATE = 3,    /* device-side check of the bytes behind the record table in fsb_stage / fsb_bin_chunks: sequence
+                                symbols A C G T N, quality in [offset, offset + 64) (>= offset in the 1-bit mode), 7-bit title
+                                characters; default 1.  The record table itself (lengths, offsets, mate lengths) is always checked. */
     FSB_OPT_SUBBATCH_RECORDS = 4  /* fsb_bin_chunks pipelines sub-batches of at least this many records (default 400000) */
 };
 
@@ -166,6 +168,11 @@ typedef struct fsb_stats {
 } fsb_stats;
 
 /*
+ * Limits of one call (FSB_ERR_PARAM / FSB_ERR_INPUT beyond them): a chunk text is shorter than 4 GiB (32-bit record
+ * offsets, as in fsb_record); one batch -- the chunk list of fsb_stage, or one internal sub-batch of fsb_bin_chunks,
+ * which splits longer lists itself -- holds at most 256 chunks (fewer for signature_len > 11: 2^(31 - 2 * signature_len))
+ * and at most 2^28 - 1 records; reads are 1..255 bases (FastqRecord.h:45-48) and titles at most 255 bytes.
+ *
  * Create a context bound to one GPU.  `cuda_stream` may be NULL (the context creates its own
  * stream) or a cudaStream_t the caller owns; all work of the context is enqueued on that stream.
  * One context per GPU worker; calls on one context must be serialised by the caller, different

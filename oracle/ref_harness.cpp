@@ -159,9 +159,10 @@ extern "C" int ref_bin_chunk(const fsb_params* p, const fsb_chunk* ch, orc_block
         }
     }
 
-    // one block for the life of the process: its FastqRawBlockStats tables are never freed by the
-    // reference (Stats.cpp:33-36).  Not thread-safe; the tests call this from one thread.
-    static BinaryBinBlock* blockPtr = new BinaryBinBlock();
+    // one block per calling thread for the life of the process: its FastqRawBlockStats tables are never
+    // freed by the reference (Stats.cpp:33-36).  Thread-safe: the full-size GPU test checks all chunks of a
+    // batch on a pool of threads.
+    static thread_local BinaryBinBlock* blockPtr = new BinaryBinBlock();
     BinaryBinBlock& block = *blockPtr;
     run_reference(cfg, pe, R.recs, block);
 

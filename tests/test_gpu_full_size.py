@@ -1,11 +1,14 @@
 """BASELINE.json configs[1] at full size on the GPU (-m gpu): 10 M synthetic 150 bp pairs, lossless binning
 parameters, 12 chunks in one batch -- the workload bench.py times.
 
-The oracle cannot redo 10 M pairs in test time, so the whole batch is checked through size-independent
-properties (every record lands in exactly one bin, descriptors add up to the streams, bins ascend with the
-N-bin last, raw sizes equal the input's), and two whole chunks out of the middle and the end of the batch --
-text offsets beyond 2^31, record indices in the millions -- are compared with the C port bit for bit, which
-also shows that a chunk's block does not depend on the batch it was binned in."""
+The whole batch is checked through size-independent properties (every record lands in exactly one bin,
+descriptors add up to the streams, bins ascend with the N-bin last, raw sizes equal the input's), and then
+EVERY chunk of the batch -- text offsets beyond 2^31, record indices in the millions -- is compared bit for
+bit (streams, descriptors, per-read signature / position / flags) with the compiled reference's own
+Categorize + PackToBins (oracle/_ref/libfastore_ref.so; the C port where the reference is not built), one
+chunk per host thread.  That also shows that a chunk's block does not depend on the batch it was binned in."""
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import pytest
 
@@ -46,10 +49,16 @@ def test_baseline_config1_full_size():
         assert np.array_equal(counts[sig], bins["records_count"].astype(np.int64)), f"chunk {ci}: per-bin record counts"
         # lossless 6-bit quality: 2 * 150 * 6 bits per pair, byte padding per bin only
         assert blk.qua.size >= (n * 2 * bench.READ_LEN * 6) // 8 and blk.qua.size <= (n * 2 * bench.READ_LEN * 6) // 8 + bins.shape[0]
-    # whole chunks against the C port, bit for bit
-    for ci in (len(chunks) // 2, len(chunks) - 1):
+    # every chunk against the compiled reference, bit for bit (ctypes releases the GIL: one chunk per host thread)
+    kind = "ref" if O.have_reference() else "orc"
+
+    def check(ci):
         blk = blocks[ci]
         got = {"meta": blk.meta, "dna": blk.dna, "qua": blk.qua, "head": blk.head, "bins": blk.bins,
                "raw_dna_size": blk.raw_dna_size, "raw_head_size": blk.raw_head_size, "n_records": blk.n_records,
                "read_signature": blk.read_signature, "read_info": blk.read_info}
-        O.assert_blocks_equal(got, O.bin_chunk("orc", params, chunks[ci]), f"chunk {ci} of the 10 M-pair batch")
+        O.assert_blocks_equal(got, O.bin_chunk(kind, params, chunks[ci]), f"chunk {ci} of the 10 M-pair batch vs '{kind}'")
+        return ci
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(chunks), bench.host_threads()))) as ex:
+        assert sorted(ex.map(check, range(len(chunks)))) == list(range(len(chunks)))

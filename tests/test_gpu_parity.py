@@ -115,6 +115,44 @@ def test_input_contract_errors():
         assert blk.n_records == 3
 
 
+@pytest.mark.parametrize("paired", [False, True])
+def test_bytes_outside_the_contract_are_rejected_on_the_device(paired):
+    """FSB_OPT_VALIDATE (default on): a caller that wires the reference's parser straight to the C ABI gets FSB_ERR_INPUT
+    for symbols outside ACGTN, qualities outside [offset, offset + 64) and 8-bit title characters instead of silently
+    mis-coded streams (the reference itself leaves these undefined: FastqRecord.h:95-96, FastqPacker.cpp:250)."""
+    cfg = synth.synth_config(700, 100, paired=paired, seed=77, nrich=0.05)
+    t1, t2, r1, r2 = synth.generate(cfg)
+    params = N.make_params(signature_len=8, skip_zone_len=0, paired_end=paired)
+    binary = N.make_params(signature_len=8, skip_zone_len=0, paired_end=paired, quality_method=N.FSB_QUA_BINARY)
+
+    def poke(text, off, value):
+        t = text.copy()
+        t[off] = value
+        return t
+
+    last = len(r1) - 1
+    cases = [("lowercase base", 0, int(r1["seq_off"][5]) + 17, ord("a")), ("IUPAC base", 0, int(r1["seq_off"][last]) + 99, ord("R")),
+             ("dot", 0, int(r1["seq_off"][300]), ord(".")), ("quality below the offset", 0, int(r1["qua_off"][123]) + 50, 32),
+             ("quality above offset + 63", 0, int(r1["qua_off"][0]), 33 + 64), ("8-bit title character", 0, int(r1["head_off"][17]) + 3, 0xC3)]
+    if paired:
+        cases += [("lowercase base in mate 2", 1, int(r2["seq_off"][last]) + 99, ord("t")), ("mate 2 quality below the offset", 1, int(r2["qua_off"][9]), 10)]
+    with GpuBinner(params) as g, GpuBinner(binary) as gb:
+        for what, mate, off, value in cases:
+            a, b = (poke(t1, off, value), t2) if mate == 0 else (t1, poke(t2, off, value))
+            with pytest.raises(FastoreError, match="outside the input contract"):
+                g.bin_chunks([N.make_chunk(a, r1, b, r2)])
+        # the 1-bit mode only needs q >= offset (the threshold compare takes any value above it)
+        hi = poke(t1, int(r1["qua_off"][0]), 33 + 64)
+        assert gb.bin_chunks([N.make_chunk(hi, r1, t2, r2)])[0].n_records == len(r1)
+        with pytest.raises(FastoreError, match="outside the input contract"):
+            gb.bin_chunks([N.make_chunk(poke(t1, int(r1["qua_off"][0]), 32), r1, t2, r2)])
+        # bytes next to the checked spans do not matter, the clean input passes, and the check can be switched off
+        assert g.bin_chunks([N.make_chunk(poke(t1, int(r1["seq_off"][5]) - 1, ord("\r")), r1, t2, r2)])[0].n_records == len(r1)
+        assert g.bin_chunks([N.make_chunk(t1, r1, t2, r2)])[0].n_records == len(r1)
+    with GpuBinner(params, validate=False) as g:
+        assert g.bin_chunks([N.make_chunk(poke(t1, int(r1["seq_off"][5]) + 17, ord("a")), r1, t2, r2)])[0].n_records == len(r1)
+
+
 def test_parser_table_equals_generator_table_on_gpu_path():
     """host parser -> C ABI: the table the parser builds drives the device exactly like the generator's."""
     cfg = synth.synth_config(3000, 100, paired=False, seed=33, header_comments=True)
