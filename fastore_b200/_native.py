@@ -22,7 +22,7 @@ FSB_INFO_SWAPPED = 0x00020000
 FSB_INFO_PLAIN_A = 0x00040000
 FSB_INFO_PLAIN_B = 0x00080000
 FSB_OPT_PER_READ, FSB_OPT_PROFILE, FSB_OPT_VALIDATE, FSB_OPT_SUBBATCH_RECORDS = 1, 2, 3, 4
-FSB_STAGE_NAMES = ("ingest", "sort", "layout", "place")
+FSB_STAGE_NAMES = ("ingest", "sort", "layout", "place", "check")     # "check": input-check kernels of fsb_stage, reported on request
 
 
 class FsbParams(C.Structure):

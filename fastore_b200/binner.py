@@ -105,11 +105,13 @@ class GpuBinner:
         self._check(self._lib.fsb_fetch(self._ctx, blocks, self._n_staged))
         return [self._to_block(b) for b in blocks] if copy else blocks
 
-    def stage_times(self):
-        ms = (C.c_float * 4)()
+    def stage_times(self, n_stages: int = 4):
+        """Per-stage device milliseconds since the last call: the four stages of fsb_run, plus "check" (the input-check
+        kernels of fsb_stage) when n_stages is 5."""
+        ms = (C.c_float * n_stages)()
         runs = C.c_uint32()
-        self._check(self._lib.fsb_stage_times(self._ctx, ms, 4, C.byref(runs)))
-        return {n: float(ms[i]) for i, n in enumerate(N.FSB_STAGE_NAMES)}, int(runs.value)
+        self._check(self._lib.fsb_stage_times(self._ctx, ms, n_stages, C.byref(runs)))
+        return {n: float(ms[i]) for i, n in enumerate(N.FSB_STAGE_NAMES[:n_stages])}, int(runs.value)
 
     def stats(self) -> dict:
         s = N.FsbStats()

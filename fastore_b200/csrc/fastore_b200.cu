@@ -132,6 +132,9 @@ struct fsb_ctx
     int pending_profiles = 0;
     float stage_ms[FSB_STAGE_COUNT] = {0, 0, 0, 0};
     uint32_t stage_runs = 0;
+    cudaEvent_t ev_check[2] = {nullptr, nullptr};   // around the input-check kernels of fsb_stage (FSB_OPT_PROFILE)
+    bool check_pending = false;
+    float check_ms = 0;
 
     fsb_stats stats{};
 };
@@ -255,7 +258,7 @@ HostOut* host_out(fsb_ctx* c, size_t g)
 // things the reference only ASSERTs: FastqRecord.h:87, FastqParser.cpp:130) together with the batch
 // statistics that size the buffers, and the copy of those statistics back.  The batch's input
 // buffers must not be in use.
-int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st)
+int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, bool profile = false)
 {
     b.staged = false; b.ran = false;
     const int nfiles = c->dp.paired ? 2 : 1;
@@ -326,6 +329,11 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
         const BatchView B = batch_view(b);
         const uint64_t* m64 = b.d_chunk_meta.as<uint64_t>();
         const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
+        if (profile)
+        {
+            for (cudaEvent_t& e : c->ev_check) if (!e) CUDA_TRY(c, cudaEventCreate(&e));
+            CUDA_TRY(c, cudaEventRecord(c->ev_check[0], st));
+        }
         stage_stats_kernel<<<blocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>());
         c->stats.kernel_launches++;
         if (c->validate)
@@ -335,6 +343,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
             validate_text_kernel<<<vblocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>());
             c->stats.kernel_launches++;
         }
+        if (profile) { CUDA_TRY(c, cudaEventRecord(c->ev_check[1], st)); c->check_pending = true; }
     }
     CUDA_TRY(c, cudaMemcpyAsync(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, st));
     b.h2d_bytes = h2d;
@@ -714,6 +723,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     if (c->s_h2d) { cudaStreamSynchronize(c->s_h2d); cudaStreamDestroy(c->s_h2d); }
     if (c->s_d2h) { cudaStreamSynchronize(c->s_d2h); cudaStreamDestroy(c->s_d2h); }
     for (auto& e : c->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_check) if (e) cudaEventDestroy(e);
     for (Batch& b : c->batch)
     {
         DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
@@ -782,7 +792,16 @@ extern "C" int fsb_stage_times(fsb_ctx* c, float* ms, uint32_t n_stages, uint32_
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = resolve_profiles(c);
     if (rc != FSB_OK) return rc;
-    for (uint32_t s = 0; s < n_stages; ++s) ms[s] = s < FSB_STAGE_COUNT ? c->stage_ms[s] : 0.f;
+    if (c->check_pending)
+    {
+        CUDA_TRY(c, cudaEventSynchronize(c->ev_check[1]));
+        float t = 0;
+        CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev_check[0], c->ev_check[1]));
+        c->check_ms += t;
+        c->check_pending = false;
+    }
+    for (uint32_t s = 0; s < n_stages; ++s) ms[s] = s < FSB_STAGE_COUNT ? c->stage_ms[s] : (s == FSB_STAGE_CHECK ? c->check_ms : 0.f);
+    c->check_ms = 0;
     if (n_runs) *n_runs = c->stage_runs;
     for (int s = 0; s < FSB_STAGE_COUNT; ++s) c->stage_ms[s] = 0;
     c->stage_runs = 0;
@@ -796,7 +815,7 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // nothing may still be using the batch's buffers
     Batch& b = c->batch[0];
-    int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream);
+    int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream, c->profile);
     if (rc != FSB_OK) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // pageable user buffers must outlive the copies; the statistics are back
     return stage_complete(c, b);

@@ -156,7 +156,9 @@ enum {
     FSB_STAGE_SORT = 1,      /* K2/K3: histogram + scan + stable rank (radix passes)              */
     FSB_STAGE_LAYOUT = 2,    /* bin boundaries, per-bin length stats, bit-offset scans            */
     FSB_STAGE_PLACE = 3,     /* K4: gather the slots and shift them into the four streams         */
-    FSB_STAGE_COUNT = 4
+    FSB_STAGE_COUNT = 4,
+    FSB_STAGE_CHECK = 4      /* not part of fsb_run: the input-check kernels of the last fsb_stage calls (record table +
+                                FSB_OPT_VALIDATE byte check); reported as ms[4] when fsb_stage_times is asked for 5 values */
 };
 
 typedef struct fsb_stats {
@@ -208,7 +210,7 @@ int fsb_run(fsb_ctx* ctx);
 int fsb_fetch(fsb_ctx* ctx, fsb_block* blocks, uint32_t n_blocks);
 int fsb_sync(fsb_ctx* ctx);
 
-/* Accumulated per-stage device time in milliseconds since the last call (needs FSB_OPT_PROFILE). */
+/* Accumulated per-stage device time in milliseconds since the last call (needs FSB_OPT_PROFILE); n_runs counts fsb_run calls. */
 int fsb_stage_times(fsb_ctx* ctx, float* ms, uint32_t n_stages, uint32_t* n_runs);
 
 int fsb_get_stats(const fsb_ctx* ctx, fsb_stats* out);

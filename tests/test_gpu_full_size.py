@@ -23,8 +23,10 @@ N_PAIRS = 10_000_000
 
 def test_baseline_config1_full_size():
     import bench
-    params = bench.lossless_pe_params()
-    chunks, keep = bench.workload_chunks(0, N_PAIRS, pinned=False, threads=min(16, bench.host_threads()))
+    w = bench.WORKLOADS["c2"]
+    READ_LEN = w["L"]
+    params = bench.make_params(w)
+    chunks, keep = bench.workload_chunks(w, bench.rank_shards(w, 0, 1, N_PAIRS), pinned=False, threads=min(16, bench.host_threads()))
     assert len(chunks) >= 10 and sum(int(c.n_records) for c in chunks) == N_PAIRS
     with GpuBinner(params, per_read=True) as g:
         blocks = g.bin_chunks(chunks)
@@ -39,7 +41,7 @@ def test_baseline_config1_full_size():
         assert sig[-1] <= nbin and (sig[:-1] < nbin).all()
         for field, stream in (("meta_size", blk.meta), ("dna_size", blk.dna), ("qua_size", blk.qua), ("head_size", blk.head)):
             assert int(bins[field].sum()) == stream.size, f"chunk {ci}: {field} does not add up to the stream"
-        assert int(bins["raw_dna_size"].sum()) == blk.raw_dna_size == 2 * bench.READ_LEN * n
+        assert int(bins["raw_dna_size"].sum()) == blk.raw_dna_size == 2 * READ_LEN * n
         assert int(bins["raw_head_size"].sum()) == blk.raw_head_size
         # per-read results: every signature is a bin of the chunk, and the per-bin counts agree
         rs = blk.read_signature
@@ -48,7 +50,7 @@ def test_baseline_config1_full_size():
         assert np.array_equal(np.nonzero(counts)[0], sig), f"chunk {ci}: bins vs per-read signatures"
         assert np.array_equal(counts[sig], bins["records_count"].astype(np.int64)), f"chunk {ci}: per-bin record counts"
         # lossless 6-bit quality: 2 * 150 * 6 bits per pair, byte padding per bin only
-        assert blk.qua.size >= (n * 2 * bench.READ_LEN * 6) // 8 and blk.qua.size <= (n * 2 * bench.READ_LEN * 6) // 8 + bins.shape[0]
+        assert blk.qua.size >= (n * 2 * READ_LEN * 6) // 8 and blk.qua.size <= (n * 2 * READ_LEN * 6) // 8 + bins.shape[0]
     # every chunk against the compiled reference, bit for bit (ctypes releases the GIL: one chunk per host thread)
     kind = "ref" if O.have_reference() else "orc"
 
