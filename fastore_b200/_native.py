@@ -21,7 +21,7 @@ FSB_INFO_REVERSE = 0x00010000
 FSB_INFO_SWAPPED = 0x00020000
 FSB_INFO_PLAIN_A = 0x00040000
 FSB_INFO_PLAIN_B = 0x00080000
-FSB_OPT_PER_READ, FSB_OPT_PROFILE, FSB_OPT_VALIDATE, FSB_OPT_SUBBATCH_RECORDS = 1, 2, 3, 4
+FSB_OPT_PER_READ, FSB_OPT_PROFILE, FSB_OPT_VALIDATE, FSB_OPT_SUBBATCH_RECORDS, FSB_OPT_RUN_SPLIT = 1, 2, 3, 4, 5
 FSB_STAGE_NAMES = ("ingest", "sort", "layout", "place", "check")     # "check": input-check kernels of fsb_stage, reported on request
 
 

@@ -35,7 +35,8 @@ class BinBlock:
 
 class GpuBinner:
     def __init__(self, params: N.FsbParams, device: int = 0, stream: int | None = None, per_read: bool = False,
-                 profile: bool = False, sub_batch_records: int | None = None, validate: bool | None = None):
+                 profile: bool = False, sub_batch_records: int | None = None, validate: bool | None = None,
+                 run_split: int | None = None):
         self._lib = N.cuda_lib()
         self._ctx = C.c_void_p()
         self.params = params
@@ -49,6 +50,8 @@ class GpuBinner:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_PROFILE, 1))
         if validate is not None:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_VALIDATE, 1 if validate else 0))
+        if run_split is not None:
+            self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_RUN_SPLIT, run_split))
         if sub_batch_records is not None:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_SUBBATCH_RECORDS, sub_batch_records))
 
@@ -74,6 +77,10 @@ class GpuBinner:
         if rc != N.FSB_OK:
             msg = self._lib.fsb_last_error(self._ctx)
             raise FastoreError(f"fastore_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def set_run_split(self, n: int):
+        """Sub-batches fsb_run cuts the next staged batch into (overlapped on two streams)."""
+        self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_RUN_SPLIT, n))
 
     # -- the path ---------------------------------------------------------------------------------
     @staticmethod

@@ -6,6 +6,10 @@
 // processed by one pass of the pipeline ("batch"): bins are keyed by (chunk, signature), so every
 // chunk still yields exactly its own BinaryBinBlock, byte for byte.
 //
+// fsb_run can split the staged batch into sub-batches of whole chunks that go through the pipeline on
+// two streams ("lanes", each with its own intermediates): K1 of one sub-batch is bound by the integer
+// pipe, sort / layout / K4 of the other by latency and HBM, so they share the SMs well.
+//
 // fsb_bin_chunks (host buffers in, host blocks out) cuts its chunk list into sub-batches and runs
 // them as a three-stage pipeline over two sets of device buffers: host->device copy of sub-batch
 // g+1, kernels of g and device->host copy of g-1 overlap on three streams, the way the reference's
@@ -79,6 +83,18 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 } // namespace
 
+// A run of whole chunks of a staged batch that goes through the kernel pipeline on its own (fsb_run may split a batch
+// into several to overlap them on two streams).  Record, bin and output offsets are relative to the batch.
+struct Sub
+{
+    uint32_t c0 = 0, c1 = 0;                     // chunks [c0, c1)
+    uint64_t r0 = 0, r1 = 0;                     // records [r0, r1)
+    uint64_t nb_max = 0, bin_off = 0;            // bound of the number of bins; first entry in the batch's descriptor array
+    int sort_passes = 0;
+    size_t out_off[4] = {0, 0, 0, 0}, out_cap[4] = {0, 0, 0, 0};   // its region of the batch's output streams (bytes, 64-byte aligned)
+    size_t meta_first = 0;                       // index of its relative first-record table in the device chunk tables
+};
+
 // One staged group of chunks: its inputs and its results on the device.
 struct Batch
 {
@@ -90,12 +106,12 @@ struct Batch
     std::vector<uint64_t> meta_host;             // host copy of the chunk tables (must outlive its async copy)
     uint64_t total_bases = 0, total_head = 0, nb_max = 0, algorithmic_in = 0, h2d_bytes = 0;
     uint32_t min_len = 0, max_len = 0, max_head = 0;
-    int sort_passes = 0;
     SlotGeom geom{};
-    size_t out_cap[4] = {0, 0, 0, 0};
+    std::vector<Sub> subs;
+    size_t out_total[4] = {0, 0, 0, 0};          // sum of the sub-batches' regions
 
-    DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats;
-    PinBuf h_stage_stats;
+    DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats, d_chunk_sums;
+    PinBuf h_stage_stats, h_chunk_sums;
     DevBuf d_out[4], d_desc, d_summary, d_sig, d_info;
     cudaEvent_t ev_h2d = nullptr, ev_run = nullptr, ev_d2h = nullptr;
 };
@@ -122,10 +138,27 @@ struct fsb_ctx
     Batch batch[2];                              // [0] is the batch of fsb_stage / fsb_run / fsb_fetch
     std::vector<HostOut*> host;                  // [g] results of sub-batch g ([0] for the resident interface)
 
-    // intermediates, shared by all batches (the kernels of different batches run on one stream)
-    DevBuf d_keys[2], d_cards[2], d_slots, d_counts, d_counts_scan, d_scan_tmp;
-    DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head, d_tbase;
-    DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4];
+    // the pipeline's intermediates; lane 0 runs on `stream`, lane 1 (second stream) only when fsb_run splits a batch
+    struct Lane
+    {
+        cudaStream_t st = nullptr;
+        bool own = false;
+        cudaEvent_t ev_done = nullptr;
+        DevBuf d_keys[2], d_cards[2], d_slots, d_counts, d_counts_scan, d_scan_tmp;
+        DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head, d_tbase;
+        DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4];
+        template <class F> void each(F f)
+        {
+            DevBuf* all[] = {&d_keys[0], &d_keys[1], &d_cards[0], &d_cards[1], &d_slots, &d_counts, &d_counts_scan, &d_scan_tmp, &d_flags, &d_flags_excl,
+                             &d_bin_of, &d_bin_start, &d_bin_min, &d_bin_max, &d_raw_dna, &d_raw_head, &d_tbase, &d_bits[0], &d_bits[1], &d_bits[2], &d_bits[3],
+                             &d_P[0], &d_P[1], &d_P[2], &d_P[3], &d_bytes[0], &d_bytes[1], &d_bytes[2], &d_bytes[3], &d_BO[0], &d_BO[1], &d_BO[2], &d_BO[3]};
+            for (DevBuf* d : all) f(*d);
+        }
+    } lane[2];
+    cudaEvent_t ev_fork = nullptr;
+    uint32_t run_split = 1;                      // sub-batches fsb_run cuts a staged batch into (FSB_OPT_RUN_SPLIT)
+    uint32_t k1_batches_per_warp = 32, k4_tiles_per_block = 64;   // block granularity of K1 / K4 when sub-batches share the GPU (0: persistent)
+    bool block_grids_always = false;             // use that granularity for unsplit runs too (measurement only)
 
     // ---- profiling -----------------------------------------------------------------------------
     std::vector<cudaEvent_t> events;             // kMaxPendingProfiles * (FSB_STAGE_COUNT + 1)
@@ -169,12 +202,24 @@ BatchView batch_view(const Batch& b)
     B.n_chunks = b.n_chunks; B.n_records = b.n_records;
     return B;
 }
+// the same for one sub-batch: records and chunks counted from its own start
+BatchView sub_view(const Batch& b, const Sub& s)
+{
+    BatchView B = batch_view(b);
+    const uint64_t* meta = b.d_chunk_meta.as<uint64_t>();
+    B.rec[0] += s.r0; if (B.rec[1]) B.rec[1] += s.r0;
+    B.chunk_first_rec = meta + s.meta_first;
+    B.chunk_text_base[0] += s.c0; B.chunk_text_base[1] += s.c0;
+    B.n_chunks = s.c1 - s.c0; B.n_records = s.r1 - s.r0;
+    return B;
+}
 
 template <int NW, int Q>
-cudaError_t launch_ingest_q(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t* keys, unsigned long long* cards,
+cudaError_t launch_ingest_q(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t R, uint32_t* keys, unsigned long long* cards,
                             uint32_t* slots, uint32_t* sig, uint32_t* info, cudaStream_t st)
 {
-    const IngestPlan pl = make_ingest_plan<NW>(P, G, max_head);
+    IngestPlan pl = make_ingest_plan<NW>(P, G, max_head);
+    pl.batches_per_warp = R;
     cudaError_t e = cudaFuncSetAttribute(ingest_kernel<NW, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
     if (e != cudaSuccess) return e;
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
@@ -184,23 +229,26 @@ cudaError_t launch_ingest_q(const BatchView& B, const DeviceParams& P, const Slo
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ingest_kernel<NW, Q>, (int)(pl.warps * 32), pl.total_bytes)) != cudaSuccess) return e;
     const uint64_t need = (n_mates + pl.warps * 32 - 1) / (pl.warps * 32);
-    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
+    // persistent: as many blocks as fit on the device at once; otherwise every block owns R warp batches per warp
+    const unsigned blocks = R ? (unsigned)std::max<uint64_t>(1, (need + R - 1) / R)
+                              : (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
     ingest_kernel<NW, Q><<<blocks, pl.warps * 32, pl.total_bytes, st>>>(B, P, G, pl, keys, cards, slots, sig, info);
     return cudaGetLastError();
 }
 template <int NW>
-cudaError_t launch_ingest(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t* keys, unsigned long long* cards,
+cudaError_t launch_ingest(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t R, uint32_t* keys, unsigned long long* cards,
                           uint32_t* slots, uint32_t* sig, uint32_t* info, cudaStream_t st)
 {
-    if (P.qua_bits == 6) return launch_ingest_q<NW, 6>(B, P, G, max_head, keys, cards, slots, sig, info, st);
-    if (P.qua_bits == 3) return launch_ingest_q<NW, 3>(B, P, G, max_head, keys, cards, slots, sig, info, st);
-    return launch_ingest_q<NW, 1>(B, P, G, max_head, keys, cards, slots, sig, info, st);
+    if (P.qua_bits == 6) return launch_ingest_q<NW, 6>(B, P, G, max_head, R, keys, cards, slots, sig, info, st);
+    if (P.qua_bits == 3) return launch_ingest_q<NW, 3>(B, P, G, max_head, R, keys, cards, slots, sig, info, st);
+    return launch_ingest_q<NW, 1>(B, P, G, max_head, R, keys, cards, slots, sig, info, st);
 }
 
-cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_len, uint32_t max_head, cudaStream_t st, int* launches)
+cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_len, uint32_t max_head, uint32_t R, cudaStream_t st, int* launches)
 {
     const uint64_t n = pa.B.n_records;
-    const PlacePlan pl = make_place_plan(pa.P, pa.G, max_len, max_head);
+    PlacePlan pl = make_place_plan(pa.P, pa.G, max_len, max_head);
+    pl.tiles_per_block = R;
     const uint64_t tiles = (n + pl.T - 1) / pl.T;
     // placement tables (tile ranges, every record's position inside its tile) and the zeroing of the words two tiles share
     placement_kernel<<<(unsigned)((tiles * pl.T + 255) / 256), 256, 0, st>>>(pa, pm, tiles);
@@ -211,7 +259,8 @@ cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel, (int)pl.threads, pl.total_bytes)) != cudaSuccess) return e;
-    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
+    const unsigned blocks = R ? (unsigned)std::max<uint64_t>(1, (tiles + R - 1) / R)
+                              : (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
     place_kernel<<<blocks, pl.threads, pl.total_bytes, st>>>(pa, pl, pm, tiles);
     *launches += 2;
     return cudaGetLastError();
@@ -238,10 +287,10 @@ int resolve_profiles(fsb_ctx* c)
 }
 
 // A shared intermediate may be in use by kernels of the previous sub-batch: wait for them before it is reallocated.
-cudaError_t ensure_shared(fsb_ctx* c, DevBuf& b, size_t bytes)
+cudaError_t ensure_shared(cudaStream_t st, DevBuf& b, size_t bytes)
 {
     if (bytes <= b.cap) return cudaSuccess;
-    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
     return b.ensure(bytes);
 }
@@ -257,8 +306,8 @@ HostOut* host_out(fsb_ctx* c, size_t g)
 // check of the record tables (offsets inside the chunk, lengths, PE mate-length equality - the
 // things the reference only ASSERTs: FastqRecord.h:87, FastqParser.cpp:130) together with the batch
 // statistics that size the buffers, and the copy of those statistics back.  The batch's input
-// buffers must not be in use.
-int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, bool profile = false)
+// buffers must not be in use.  `split` = sub-batches of whole chunks the kernels will run as.
+int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, uint32_t split, bool profile = false)
 {
     b.staged = false; b.ran = false;
     const int nfiles = c->dp.paired ? 2 : 1;
@@ -287,8 +336,28 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     b.chunk_first_rec[n_chunks] = n;
     if (n > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
     b.n_records = n;
-    b.nb_max = std::min<uint64_t>(n, (uint64_t)n_chunks * ((uint64_t)c->dp.nbin + 1));
-    b.sort_passes = (int)((c->dp.key_bits + bits_for(n_chunks - 1) + 7) / 8);
+
+    // ---- sub-batches: runs of whole chunks with about n / split records each --------------------------------------
+    b.subs.clear();
+    {
+        const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(split, n_chunks));
+        uint32_t c0 = 0;
+        for (uint32_t j = 0; j < S && c0 < n_chunks; ++j)
+        {
+            const uint64_t goal = n * (uint64_t)(j + 1) / S;                 // records the first j + 1 sub-batches should hold together
+            uint32_t c1 = n_chunks;
+            if (j + 1 < S)
+            {
+                const uint32_t last = n_chunks - (S - 1 - j);               // leave a chunk for every later sub-batch
+                c1 = c0 + 1;
+                while (c1 < last && b.chunk_first_rec[c1] < goal) ++c1;
+            }
+            Sub sb;
+            sb.c0 = c0; sb.c1 = c1; sb.r0 = b.chunk_first_rec[c0]; sb.r1 = b.chunk_first_rec[c1];
+            b.subs.push_back(sb);
+            c0 = c1;
+        }
+    }
 
     uint64_t h2d = 0;
     for (int m = 0; m < nfiles; ++m)
@@ -306,7 +375,8 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
             h2d += ch.text_size[m] + ch.n_records * sizeof(fsb_record);
         }
     }
-    // chunk tables: [first_rec (n_chunks+1)] [text_base0] [text_base1] [text_size0] [text_size1]  (n_chunks each)
+    // chunk tables: [first_rec (n_chunks+1)] [text_base0] [text_base1] [text_size0] [text_size1]  (n_chunks each), then per sub-batch
+    // its own first-record table counted from the sub-batch's first record (chunks + 1 entries)
     std::vector<uint64_t>& meta = b.meta_host;
     meta.clear();
     meta.insert(meta.end(), b.chunk_first_rec.begin(), b.chunk_first_rec.end());
@@ -314,16 +384,24 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     meta.insert(meta.end(), b.chunk_text_base[1].begin(), b.chunk_text_base[1].end());
     for (int m = 0; m < 2; ++m)
         for (uint32_t ci = 0; ci < n_chunks; ++ci) meta.push_back(chunks[ci].text_size[m]);
+    for (Sub& sb : b.subs)
+    {
+        sb.meta_first = meta.size();
+        for (uint32_t ci = sb.c0; ci <= sb.c1; ++ci) meta.push_back(b.chunk_first_rec[ci] - sb.r0);
+    }
     CUDA_TRY(c, b.d_chunk_meta.ensure(meta.size() * sizeof(uint64_t)));
     CUDA_TRY(c, cudaMemcpyAsync(b.d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     h2d += meta.size() * sizeof(uint64_t);
 
     CUDA_TRY(c, b.d_stage_stats.ensure(sizeof(StageStats)));
     CUDA_TRY(c, b.h_stage_stats.ensure(2 * sizeof(StageStats)));
+    CUDA_TRY(c, b.d_chunk_sums.ensure((size_t)n_chunks * 2 * sizeof(uint64_t)));
+    CUDA_TRY(c, b.h_chunk_sums.ensure((size_t)n_chunks * 2 * sizeof(uint64_t)));
     StageStats init{};
     init.first_bad = ~0ull; init.first_bad_text = ~0ull; init.min_len = 0xFFFFFFFFu;
     b.h_stage_stats.as<StageStats>()[1] = init;                  // [1] initial value going up, [0] result coming back
     CUDA_TRY(c, cudaMemcpyAsync(b.d_stage_stats.p, b.h_stage_stats.as<StageStats>() + 1, sizeof(StageStats), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemsetAsync(b.d_chunk_sums.p, 0, (size_t)n_chunks * 2 * sizeof(uint64_t), st));
     if (n)
     {
         const BatchView B = batch_view(b);
@@ -334,7 +412,8 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
             for (cudaEvent_t& e : c->ev_check) if (!e) CUDA_TRY(c, cudaEventCreate(&e));
             CUDA_TRY(c, cudaEventRecord(c->ev_check[0], st));
         }
-        stage_stats_kernel<<<blocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>());
+        stage_stats_kernel<<<blocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>(),
+                                                    b.d_chunk_sums.as<unsigned long long>());
         c->stats.kernel_launches++;
         if (c->validate)
         {   // FSB_OPT_VALIDATE: symbols, quality range and title characters behind the table (stage.cuh)
@@ -346,13 +425,14 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
         if (profile) { CUDA_TRY(c, cudaEventRecord(c->ev_check[1], st)); c->check_pending = true; }
     }
     CUDA_TRY(c, cudaMemcpyAsync(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(b.h_chunk_sums.p, b.d_chunk_sums.p, (size_t)n_chunks * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     b.h2d_bytes = h2d;
     c->stats.h2d_bytes += h2d;
     return FSB_OK;
 }
 
 // Stage, step 2 (after everything stage_enqueue put on its stream has completed): reject contract
-// violations, then size the result buffers of the batch (which must not be in use) and the shared
+// violations, then size the result buffers of the batch (which must not be in use) and the lanes'
 // intermediates.
 int stage_complete(fsb_ctx* c, Batch& b)
 {
@@ -381,51 +461,79 @@ int stage_complete(fsb_ctx* c, Batch& b)
     b.min_len = n ? stats.min_len : 0; b.max_len = stats.max_len; b.max_head = stats.max_head;
     b.geom = make_slot_geom(c->dp, b.max_len, b.max_head);
 
-    // ---- shared intermediates (grow-only) -----------------------------------------------------------
-    const uint64_t nsort_blocks = (n + kSortTile - 1) / kSortTile;
-    const uint64_t ncounts = (uint64_t)kRadix * std::max<uint64_t>(nsort_blocks, 1);
-    const uint64_t nbm = b.nb_max;
-    for (int i = 0; i < 2; ++i)
+    // ---- the sub-batches' regions of the results (exact stream sizes are only known on the device after the layout scans) ----
+    const uint64_t* sums = b.h_chunk_sums.as<uint64_t>();
+    uint64_t bin_off = 0;
+    size_t off[4] = {0, 0, 0, 0};
+    for (Sub& sb : b.subs)
     {
-        CUDA_TRY(c, ensure_shared(c, c->d_keys[i], (n + 1) * 4));
-        CUDA_TRY(c, ensure_shared(c, c->d_cards[i], (n + 1) * 8));
+        const uint64_t ns = sb.r1 - sb.r0;
+        uint64_t sb_bases = 0, sb_heads = 0;
+        for (uint32_t ci = sb.c0; ci < sb.c1; ++ci) { sb_bases += sums[2 * ci]; sb_heads += sums[2 * ci + 1]; }
+        sb.nb_max = std::min<uint64_t>(ns, (uint64_t)(sb.c1 - sb.c0) * ((uint64_t)c->dp.nbin + 1));
+        sb.sort_passes = (int)((c->dp.key_bits + bits_for(sb.c1 - sb.c0 - 1) + 7) / 8);
+        sb.bin_off = bin_off; bin_off += sb.nb_max + 1;
+        const uint64_t pad_bytes = sb.nb_max + 64;                          // < 1 byte of padding per bin and stream
+        sb.out_cap[0] = align_up((28 * ns + 17 * sb.nb_max) / 8 + pad_bytes, 64);
+        sb.out_cap[1] = align_up(3 * sb_bases / 8 + pad_bytes, 64);
+        sb.out_cap[2] = align_up((uint64_t)c->dp.qua_bits * sb_bases / 8 + pad_bytes, 64);
+        sb.out_cap[3] = align_up(c->dp.has_headers ? (8 * ns + 7 * sb_heads) / 8 + pad_bytes : 64, 64);
+        for (int s = 0; s < 4; ++s) { sb.out_off[s] = off[s]; off[s] += sb.out_cap[s]; }
     }
-    CUDA_TRY(c, ensure_shared(c, c->d_slots, (n + 1) * (size_t)b.geom.words * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_counts, (ncounts + 1) * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_counts_scan, (ncounts + 1) * 4));
-    const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(n, ncounts), nbm) + 1;
-    CUDA_TRY(c, ensure_shared(c, c->d_scan_tmp, 4 * (scan_num_tiles(max_scan_n) + 2) * 8));
-    CUDA_TRY(c, ensure_shared(c, c->d_flags, (n + 1) * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_tbase, ((n + kPlaceTile - 1) / kPlaceTile + 2) * 4 * 8));
-    CUDA_TRY(c, ensure_shared(c, c->d_flags_excl, (n + 2) * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_bin_of, (n + 1) * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_bin_start, (nbm + 2) * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_bin_min, (nbm + 1) * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_bin_max, (nbm + 1) * 4));
-    CUDA_TRY(c, ensure_shared(c, c->d_raw_dna, (nbm + 1) * 8));
-    CUDA_TRY(c, ensure_shared(c, c->d_raw_head, (nbm + 1) * 8));
-    for (int s = 0; s < 4; ++s)
+    for (int s = 0; s < 4; ++s) b.out_total[s] = off[s];
+    b.nb_max = bin_off;
+
+    // ---- the lanes' intermediates (grow-only): lane l runs the sub-batches l, l + 2, .. ---------------------------------
+    const size_t n_lanes = std::min<size_t>(2, b.subs.size());
+    for (size_t l = 0; l < n_lanes; ++l)
     {
-        CUDA_TRY(c, ensure_shared(c, c->d_bits[s], (n + 1) * 4));
-        CUDA_TRY(c, ensure_shared(c, c->d_P[s], (n + 2) * 8));
-        CUDA_TRY(c, ensure_shared(c, c->d_bytes[s], (nbm + 1) * 8));
-        CUDA_TRY(c, ensure_shared(c, c->d_BO[s], (nbm + 2) * 8));
+        fsb_ctx::Lane& L = c->lane[l];
+        if (!L.st)
+        {
+            CUDA_TRY(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+            L.own = true;
+            CUDA_TRY(c, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+        }
+        uint64_t ln = 0, lnbm = 0;
+        for (size_t j = l; j < b.subs.size(); j += 2) { ln = std::max(ln, b.subs[j].r1 - b.subs[j].r0); lnbm = std::max(lnbm, b.subs[j].nb_max); }
+        const uint64_t nsort_blocks = (ln + kSortTile - 1) / kSortTile;
+        const uint64_t ncounts = (uint64_t)kRadix * std::max<uint64_t>(nsort_blocks, 1);
+        for (int i = 0; i < 2; ++i)
+        {
+            CUDA_TRY(c, ensure_shared(L.st, L.d_keys[i], (ln + 1) * 4));
+            CUDA_TRY(c, ensure_shared(L.st, L.d_cards[i], (ln + 1) * 8));
+        }
+        CUDA_TRY(c, ensure_shared(L.st, L.d_slots, (ln + 1) * (size_t)b.geom.words * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_counts, (ncounts + 1) * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_counts_scan, (ncounts + 1) * 4));
+        const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(ln, ncounts), lnbm) + 1;
+        CUDA_TRY(c, ensure_shared(L.st, L.d_scan_tmp, 4 * (scan_num_tiles(max_scan_n) + 2) * 8));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_flags, (ln + 1) * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_tbase, ((ln + kPlaceTile - 1) / kPlaceTile + 2) * 4 * 8));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_flags_excl, (ln + 2) * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_bin_of, (ln + 1) * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_bin_start, (lnbm + 2) * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_bin_min, (lnbm + 1) * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_bin_max, (lnbm + 1) * 4));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_raw_dna, (lnbm + 1) * 8));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_raw_head, (lnbm + 1) * 8));
+        for (int s = 0; s < 4; ++s)
+        {
+            CUDA_TRY(c, ensure_shared(L.st, L.d_bits[s], (ln + 1) * 4));
+            CUDA_TRY(c, ensure_shared(L.st, L.d_P[s], (ln + 2) * 8));
+            CUDA_TRY(c, ensure_shared(L.st, L.d_bytes[s], (lnbm + 1) * 8));
+            CUDA_TRY(c, ensure_shared(L.st, L.d_BO[s], (lnbm + 2) * 8));
+        }
     }
     // ---- results of this batch ---------------------------------------------------------------------------
-    CUDA_TRY(c, b.d_desc.ensure((nbm + 1) * sizeof(fsb_bin_descriptor)));
+    CUDA_TRY(c, b.d_desc.ensure((b.nb_max + 1) * sizeof(fsb_bin_descriptor)));
     CUDA_TRY(c, b.d_summary.ensure((size_t)n_chunks * sizeof(ChunkSummary)));
     if (c->per_read)
     {
         CUDA_TRY(c, b.d_info.ensure((n + 1) * 4));
         CUDA_TRY(c, b.d_sig.ensure((n + 1) * 4));
     }
-    // upper bounds of the stream sizes (exact sizes are only known on the device after the layout scans)
-    const uint64_t pad_bytes = nbm + 64;                                    // < 1 byte of padding per bin and stream
-    b.out_cap[0] = align_up((28 * n + 17 * nbm) / 8 + pad_bytes, 64);
-    b.out_cap[1] = align_up(3 * bases / 8 + pad_bytes, 64);
-    b.out_cap[2] = align_up((uint64_t)c->dp.qua_bits * bases / 8 + pad_bytes, 64);
-    b.out_cap[3] = align_up(c->dp.has_headers ? (8 * n + 7 * heads) / 8 + pad_bytes : 64, 64);
-    for (int s = 0; s < 4; ++s) CUDA_TRY(c, b.d_out[s].ensure(b.out_cap[s]));
+    for (int s = 0; s < 4; ++s) CUDA_TRY(c, b.d_out[s].ensure(b.out_total[s] + 64));
 
     // SURVEY 8(d) algorithmic input bytes: every sequence, quality and kept header byte once
     b.algorithmic_in = 2 * bases + (c->dp.has_headers ? heads : 0);
@@ -434,48 +542,41 @@ int stage_complete(fsb_ctx* c, Batch& b)
 }
 
 // ------------------------------------------------------------------------------------------------
-// The kernels of one batch on the context's stream: K1 ingest -> sort -> layout -> K4 place.
-int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
+// The kernels of one sub-batch on one lane: K1 ingest -> sort -> layout -> K4 place.  `ev` (FSB_STAGE_COUNT + 1
+// events, or null) brackets the stages; `R1` / `R4`: block granularity of K1 / K4 (0 = persistent grids).
+int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* ev, uint32_t R1, uint32_t R4)
 {
-    cudaStream_t st = c->stream;
-    const uint64_t n = b.n_records;
+    cudaStream_t st = L.st;
+    const uint64_t n = sb.r1 - sb.r0;
     const DeviceParams& P = c->dp;
     uint64_t launches = 0;
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[0], st));
 
-    cudaEvent_t* ev = nullptr;
-    if (profile)
-    {
-        if (c->pending_profiles == kMaxPendingProfiles) { int rc = resolve_profiles(c); if (rc != FSB_OK) return rc; }
-        const size_t need = (size_t)(c->pending_profiles + 1) * (FSB_STAGE_COUNT + 1);
-        while (c->events.size() < need) { cudaEvent_t e; CUDA_TRY(c, cudaEventCreate(&e)); c->events.push_back(e); }
-        ev = &c->events[(size_t)c->pending_profiles * (FSB_STAGE_COUNT + 1)];
-        CUDA_TRY(c, cudaEventRecord(ev[0], st));
-    }
-
-    const BatchView B = batch_view(b);
+    const BatchView B = sub_view(b, sb);
+    const uint32_t sub_chunks = sb.c1 - sb.c0;
     const unsigned tpb = 256;
     const unsigned grid_n = (unsigned)std::max<uint64_t>(1, (n + tpb - 1) / tpb);
 
     // ---- K1: ingest (signature + prepacked slots) -----------------------------------------------------------
     if (n)
     {
-        uint32_t* keys = c->d_keys[0].as<uint32_t>();
-        unsigned long long* cards = c->d_cards[0].as<unsigned long long>();
-        uint32_t* slots = c->d_slots.as<uint32_t>();
-        uint32_t* sig = c->per_read ? b.d_sig.as<uint32_t>() : nullptr;
-        uint32_t* info = c->per_read ? b.d_info.as<uint32_t>() : nullptr;
+        uint32_t* keys = L.d_keys[0].as<uint32_t>();
+        unsigned long long* cards = L.d_cards[0].as<unsigned long long>();
+        uint32_t* slots = L.d_slots.as<uint32_t>();
+        uint32_t* sig = c->per_read ? b.d_sig.as<uint32_t>() + sb.r0 : nullptr;
+        uint32_t* info = c->per_read ? b.d_info.as<uint32_t>() + sb.r0 : nullptr;
         const SlotGeom& G = b.geom;
         cudaError_t e = cudaSuccess;
         switch ((b.max_len + 31) / 32)              // words of 32 bases per mate
         {
-        case 0: case 1: e = launch_ingest<1>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
-        case 2: e = launch_ingest<2>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
-        case 3: e = launch_ingest<3>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
-        case 4: e = launch_ingest<4>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
-        case 5: e = launch_ingest<5>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
-        case 6: e = launch_ingest<6>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
-        case 7: e = launch_ingest<7>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
-        default: e = launch_ingest<8>(B, P, G, b.max_head, keys, cards, slots, sig, info, st); break;
+        case 0: case 1: e = launch_ingest<1>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        case 2: e = launch_ingest<2>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        case 3: e = launch_ingest<3>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        case 4: e = launch_ingest<4>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        case 5: e = launch_ingest<5>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        case 6: e = launch_ingest<6>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        case 7: e = launch_ingest<7>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        default: e = launch_ingest<8>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
         }
         CUDA_TRY(c, e);
         launches++;
@@ -488,72 +589,73 @@ int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
     {
         const uint32_t nblocks = (uint32_t)((n + kSortTile - 1) / kSortTile);
         const uint64_t ncounts = (uint64_t)kRadix * nblocks;
-        const int total_bits = (int)(c->dp.key_bits + bits_for(b.n_chunks - 1));
+        const int total_bits = (int)(c->dp.key_bits + bits_for(sub_chunks - 1));
         int shift = 0;
-        for (int pass = 0; pass < b.sort_passes; ++pass)
+        for (int pass = 0; pass < sb.sort_passes; ++pass)
         {
             // the first digit takes the left-over bits (narrow), the others 8 bits each
-            const int width = pass == 0 ? total_bits - 8 * (b.sort_passes - 1) : 8;   // (7,7,7) and (8,8,5) measured slower than (5,8,8)
+            const int width = pass == 0 ? total_bits - 8 * (sb.sort_passes - 1) : 8;   // (7,7,7) and (8,8,5) measured slower than (5,8,8)
             const uint32_t mask = (1u << width) - 1u;
-            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), n, shift, mask, c->d_counts.as<uint32_t>(), nblocks);
+            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), n, shift, mask, L.d_counts.as<uint32_t>(), nblocks);
             launches++;
-            launches += exclusive_scan<uint32_t, uint32_t>(c->d_counts.as<uint32_t>(), ncounts, c->d_counts_scan.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
-            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(c->d_keys[cur].as<uint32_t>(), c->d_cards[cur].as<unsigned long long>(), n, shift, mask,
-                                                            c->d_counts_scan.as<uint32_t>(), nblocks, c->d_keys[cur ^ 1].as<uint32_t>(),
-                                                            c->d_cards[cur ^ 1].as<unsigned long long>());
+            launches += exclusive_scan<uint32_t, uint32_t>(L.d_counts.as<uint32_t>(), ncounts, L.d_counts_scan.as<uint32_t>(), L.d_scan_tmp.as<uint32_t>(), st);
+            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), L.d_cards[cur].as<unsigned long long>(), n, shift, mask,
+                                                            L.d_counts_scan.as<uint32_t>(), nblocks, L.d_keys[cur ^ 1].as<uint32_t>(),
+                                                            L.d_cards[cur ^ 1].as<unsigned long long>());
             shift += width;
             launches++;
             cur ^= 1;
         }
     }
-    const uint32_t* sorted_keys = c->d_keys[cur].as<uint32_t>();
-    const unsigned long long* sorted_cards = c->d_cards[cur].as<unsigned long long>();
+    const uint32_t* sorted_keys = L.d_keys[cur].as<uint32_t>();
+    const unsigned long long* sorted_cards = L.d_cards[cur].as<unsigned long long>();
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[2], st));
 
     // ---- layout --------------------------------------------------------------------------------------
     SortedView S{sorted_keys, sorted_cards};
-    BinArrays A{c->d_bin_of.as<uint32_t>(), c->d_bin_start.as<uint32_t>(), c->d_bin_min.as<uint32_t>(), c->d_bin_max.as<uint32_t>(),
-                c->d_raw_dna.as<unsigned long long>(), c->d_raw_head.as<unsigned long long>()};
-    StreamScans SC{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
-    BinOffsets BO{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
-    const uint32_t* nb_ptr = c->d_flags_excl.as<uint32_t>() + n;
+    BinArrays A{L.d_bin_of.as<uint32_t>(), L.d_bin_start.as<uint32_t>(), L.d_bin_min.as<uint32_t>(), L.d_bin_max.as<uint32_t>(),
+                L.d_raw_dna.as<unsigned long long>(), L.d_raw_head.as<unsigned long long>()};
+    StreamScans SC{{L.d_P[0].as<uint64_t>(), L.d_P[1].as<uint64_t>(), L.d_P[2].as<uint64_t>(), L.d_P[3].as<uint64_t>()}};
+    BinOffsets BO{{L.d_BO[0].as<uint64_t>(), L.d_BO[1].as<uint64_t>(), L.d_BO[2].as<uint64_t>(), L.d_BO[3].as<uint64_t>()}};
+    const uint32_t* nb_ptr = L.d_flags_excl.as<uint32_t>() + n;
+    fsb_bin_descriptor* desc = b.d_desc.as<fsb_bin_descriptor>() + sb.bin_off;
     {
-        const uint64_t nbm = b.nb_max;
-        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_min.p, 0xFF, (nbm + 1) * 4, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->d_bin_max.p, 0, (nbm + 1) * 4, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_dna.p, 0, (nbm + 1) * 8, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->d_raw_head.p, 0, (nbm + 1) * 8, st));
+        const uint64_t nbm = sb.nb_max;
+        CUDA_TRY(c, cudaMemsetAsync(L.d_bin_min.p, 0xFF, (nbm + 1) * 4, st));
+        CUDA_TRY(c, cudaMemsetAsync(L.d_bin_max.p, 0, (nbm + 1) * 4, st));
+        CUDA_TRY(c, cudaMemsetAsync(L.d_raw_dna.p, 0, (nbm + 1) * 8, st));
+        CUDA_TRY(c, cudaMemsetAsync(L.d_raw_head.p, 0, (nbm + 1) * 8, st));
         if (n)
         {
-            bin_flags_kernel<<<grid_n, tpb, 0, st>>>(sorted_keys, n, c->d_flags.as<uint32_t>());
+            bin_flags_kernel<<<grid_n, tpb, 0, st>>>(sorted_keys, n, L.d_flags.as<uint32_t>());
             launches++;
         }
-        launches += exclusive_scan<uint32_t, uint32_t>(c->d_flags.as<uint32_t>(), n, c->d_flags_excl.as<uint32_t>(), c->d_scan_tmp.as<uint32_t>(), st);
+        launches += exclusive_scan<uint32_t, uint32_t>(L.d_flags.as<uint32_t>(), n, L.d_flags_excl.as<uint32_t>(), L.d_scan_tmp.as<uint32_t>(), st);
         if (n)
         {
-            bin_stats_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, c->d_flags.as<uint32_t>(), c->d_flags_excl.as<uint32_t>(), A);
-            read_bits_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, A, c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(),
-                                                      c->d_bits[3].as<uint32_t>());
+            bin_stats_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, L.d_flags.as<uint32_t>(), L.d_flags_excl.as<uint32_t>(), A);
+            read_bits_kernel<<<grid_n, tpb, 0, st>>>(n, P, S, A, L.d_bits[0].as<uint32_t>(), L.d_bits[1].as<uint32_t>(), L.d_bits[2].as<uint32_t>(),
+                                                      L.d_bits[3].as<uint32_t>());
             launches += 2;
         }
         {
-            Ptr4<const uint32_t> in4{{c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(), c->d_bits[3].as<uint32_t>()}};
-            Ptr4<uint64_t> out4{{c->d_P[0].as<uint64_t>(), c->d_P[1].as<uint64_t>(), c->d_P[2].as<uint64_t>(), c->d_P[3].as<uint64_t>()}};
-            launches += exclusive_scan4<uint32_t, uint64_t>(in4, n, out4, c->d_scan_tmp.as<uint64_t>(), st);
+            Ptr4<const uint32_t> in4{{L.d_bits[0].as<uint32_t>(), L.d_bits[1].as<uint32_t>(), L.d_bits[2].as<uint32_t>(), L.d_bits[3].as<uint32_t>()}};
+            Ptr4<uint64_t> out4{{L.d_P[0].as<uint64_t>(), L.d_P[1].as<uint64_t>(), L.d_P[2].as<uint64_t>(), L.d_P[3].as<uint64_t>()}};
+            launches += exclusive_scan4<uint32_t, uint64_t>(in4, n, out4, L.d_scan_tmp.as<uint64_t>(), st);
         }
         if (nbm)
         {
             const unsigned grid_b = (unsigned)((nbm + tpb - 1) / tpb);
-            bin_sizes_kernel<<<grid_b, tpb, 0, st>>>(P, n, nb_ptr, nbm, sorted_keys, A, SC, c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(),
-                                                      c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>(), b.d_desc.as<fsb_bin_descriptor>());
+            bin_sizes_kernel<<<grid_b, tpb, 0, st>>>(P, n, nb_ptr, nbm, sorted_keys, A, SC, L.d_bytes[0].as<uint64_t>(), L.d_bytes[1].as<uint64_t>(),
+                                                      L.d_bytes[2].as<uint64_t>(), L.d_bytes[3].as<uint64_t>(), desc);
             launches++;
         }
         {
-            Ptr4<const uint64_t> in4{{c->d_bytes[0].as<uint64_t>(), c->d_bytes[1].as<uint64_t>(), c->d_bytes[2].as<uint64_t>(), c->d_bytes[3].as<uint64_t>()}};
-            Ptr4<uint64_t> out4{{c->d_BO[0].as<uint64_t>(), c->d_BO[1].as<uint64_t>(), c->d_BO[2].as<uint64_t>(), c->d_BO[3].as<uint64_t>()}};
-            launches += exclusive_scan4<uint64_t, uint64_t>(in4, nbm, out4, c->d_scan_tmp.as<uint64_t>(), st);
+            Ptr4<const uint64_t> in4{{L.d_bytes[0].as<uint64_t>(), L.d_bytes[1].as<uint64_t>(), L.d_bytes[2].as<uint64_t>(), L.d_bytes[3].as<uint64_t>()}};
+            Ptr4<uint64_t> out4{{L.d_BO[0].as<uint64_t>(), L.d_BO[1].as<uint64_t>(), L.d_BO[2].as<uint64_t>(), L.d_BO[3].as<uint64_t>()}};
+            launches += exclusive_scan4<uint64_t, uint64_t>(in4, nbm, out4, L.d_scan_tmp.as<uint64_t>(), st);
         }
-        chunk_summary_kernel<<<b.n_chunks, 128, 0, st>>>(B, nb_ptr, A.bin_of, BO, b.d_desc.as<fsb_bin_descriptor>(), b.d_summary.as<ChunkSummary>());
+        chunk_summary_kernel<<<sub_chunks, 128, 0, st>>>(B, nb_ptr, A.bin_of, BO, desc, b.d_summary.as<ChunkSummary>() + sb.c0);
         launches++;
     }
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[3], st));
@@ -561,23 +663,56 @@ int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
     // ---- K4: place ------------------------------------------------------------------------------------
     if (n)
     {
-        PlaceArgs pa{B, P, b.geom, S, A, SC, BO, {{b.d_out[0].as<uint32_t>(), b.d_out[1].as<uint32_t>(), b.d_out[2].as<uint32_t>(), b.d_out[3].as<uint32_t>()}},
-                     c->d_slots.as<uint32_t>(), nb_ptr};
+        PlaceArgs pa{B, P, b.geom, S, A, SC, BO,
+                     {{reinterpret_cast<uint32_t*>(b.d_out[0].as<uint8_t>() + sb.out_off[0]), reinterpret_cast<uint32_t*>(b.d_out[1].as<uint8_t>() + sb.out_off[1]),
+                       reinterpret_cast<uint32_t*>(b.d_out[2].as<uint8_t>() + sb.out_off[2]), reinterpret_cast<uint32_t*>(b.d_out[3].as<uint8_t>() + sb.out_off[3])}},
+                     L.d_slots.as<uint32_t>(), nb_ptr};
         // the per-read bit lengths and the bin flags are spent: their arrays take the placement tables
-        Placement pm{{c->d_bits[0].as<uint32_t>(), c->d_bits[1].as<uint32_t>(), c->d_bits[2].as<uint32_t>(), c->d_bits[3].as<uint32_t>()},
-                     c->d_flags.as<uint32_t>(), c->d_tbase.as<unsigned long long>()};
+        Placement pm{{L.d_bits[0].as<uint32_t>(), L.d_bits[1].as<uint32_t>(), L.d_bits[2].as<uint32_t>(), L.d_bits[3].as<uint32_t>()},
+                     L.d_flags.as<uint32_t>(), L.d_tbase.as<unsigned long long>()};
         int place_launches = 0;
-        CUDA_TRY(c, launch_place(pa, pm, b.max_len, b.max_head, st, &place_launches));
+        CUDA_TRY(c, launch_place(pa, pm, b.max_len, b.max_head, R4, st, &place_launches));
         launches += place_launches;
     }
-    if (ev)
-    {
-        CUDA_TRY(c, cudaEventRecord(ev[4], st));
-        c->pending_profiles++;
-    }
+    if (ev) CUDA_TRY(c, cudaEventRecord(ev[4], st));
     CUDA_TRY(c, cudaGetLastError());
     c->stats.kernel_launches += launches;
     c->stats.records += n;
+    return FSB_OK;
+}
+
+// The kernels of one batch.  A batch staged as one sub-batch runs on the context's stream with persistent K1 / K4 grids.
+// Several sub-batches alternate between the two lanes (sub-batch j on lane j mod 2): lane 1's stream forks from the
+// context's stream and joins it again, so callers still see one stream; K1 and K4 then run with block-sized work units
+// and the hardware interleaves the blocks of whatever kernels the two lanes have in flight.
+int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
+{
+    const bool split = b.subs.size() > 1;
+    cudaEvent_t* ev = nullptr;
+    if (profile && !split)
+    {
+        if (c->pending_profiles == kMaxPendingProfiles) { int rc = resolve_profiles(c); if (rc != FSB_OK) return rc; }
+        const size_t need = (size_t)(c->pending_profiles + 1) * (FSB_STAGE_COUNT + 1);
+        while (c->events.size() < need) { cudaEvent_t e; CUDA_TRY(c, cudaEventCreate(&e)); c->events.push_back(e); }
+        ev = &c->events[(size_t)c->pending_profiles * (FSB_STAGE_COUNT + 1)];
+    }
+    if (split)
+    {
+        CUDA_TRY(c, cudaEventRecord(c->ev_fork, c->stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->lane[1].st, c->ev_fork, 0));
+    }
+    for (size_t j = 0; j < b.subs.size(); ++j)
+    {
+        const bool blocks = split || c->block_grids_always;
+        const int rc = run_sub(c, b, b.subs[j], c->lane[split ? (j & 1) : 0], ev, blocks ? c->k1_batches_per_warp : 0u, blocks ? c->k4_tiles_per_block : 0u);
+        if (rc != FSB_OK) return rc;
+    }
+    if (split)
+    {
+        CUDA_TRY(c, cudaEventRecord(c->lane[1].ev_done, c->lane[1].st));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->lane[1].ev_done, 0));
+    }
+    if (ev) c->pending_profiles++;
     b.ran = true;
     return FSB_OK;
 }
@@ -590,25 +725,31 @@ int summary_enqueue(fsb_ctx* c, Batch& b, HostOut& h, cudaStream_t st)
     CUDA_TRY(c, cudaMemcpyAsync(h.summary.p, b.d_summary.p, (size_t)b.n_chunks * sizeof(ChunkSummary), cudaMemcpyDeviceToHost, st));
     return FSB_OK;
 }
-// Results, step 2 (summary on the host): enqueue the copies of the streams and descriptors.
+// Results, step 2 (summary on the host): enqueue the copies of the streams and descriptors, sub-batch by sub-batch
+// (every sub-batch owns a region of the batch's streams and of its descriptor array; the host buffers mirror them).
 int fetch_enqueue(fsb_ctx* c, Batch& b, HostOut& h, cudaStream_t st)
 {
     const uint64_t n = b.n_records;
     uint64_t d2h = (size_t)b.n_chunks * sizeof(ChunkSummary);
     const ChunkSummary* sum = h.summary.as<ChunkSummary>();
-    const ChunkSummary& last = sum[b.n_chunks - 1];
-    const uint64_t nb = last.first_bin + last.n_bins;
-    for (int s = 0; s < 4; ++s)
+    for (int s = 0; s < 4; ++s) CUDA_TRY(c, h.out[s].ensure(b.out_total[s] + 64));
+    CUDA_TRY(c, h.desc.ensure((b.nb_max + 1) * sizeof(fsb_bin_descriptor)));
+    for (const Sub& sb : b.subs)
     {
-        const uint64_t total = last.off[s] + last.size[s];
-        if (total > b.out_cap[s]) return fail(c, FSB_ERR_STATE, "internal error: stream size exceeds its bound");
-        CUDA_TRY(c, h.out[s].ensure(total + 64));
-        if (total) CUDA_TRY(c, cudaMemcpyAsync(h.out[s].p, b.d_out[s].p, total, cudaMemcpyDeviceToHost, st));
-        d2h += total;
+        const ChunkSummary& last = sum[sb.c1 - 1];
+        const uint64_t nb = last.first_bin + last.n_bins;
+        if (nb > sb.nb_max) return fail(c, FSB_ERR_STATE, "internal error: bin count exceeds its bound");
+        for (int s = 0; s < 4; ++s)
+        {
+            const uint64_t total = last.off[s] + last.size[s];
+            if (total > sb.out_cap[s]) return fail(c, FSB_ERR_STATE, "internal error: stream size exceeds its bound");
+            if (total) CUDA_TRY(c, cudaMemcpyAsync(h.out[s].as<uint8_t>() + sb.out_off[s], b.d_out[s].as<uint8_t>() + sb.out_off[s], total, cudaMemcpyDeviceToHost, st));
+            d2h += total;
+        }
+        if (nb) CUDA_TRY(c, cudaMemcpyAsync(h.desc.as<fsb_bin_descriptor>() + sb.bin_off, b.d_desc.as<fsb_bin_descriptor>() + sb.bin_off, nb * sizeof(fsb_bin_descriptor),
+                                            cudaMemcpyDeviceToHost, st));
+        d2h += nb * sizeof(fsb_bin_descriptor);
     }
-    CUDA_TRY(c, h.desc.ensure((nb + 1) * sizeof(fsb_bin_descriptor)));
-    if (nb) CUDA_TRY(c, cudaMemcpyAsync(h.desc.p, b.d_desc.p, nb * sizeof(fsb_bin_descriptor), cudaMemcpyDeviceToHost, st));
-    d2h += nb * sizeof(fsb_bin_descriptor);
     if (c->per_read)
     {
         CUDA_TRY(c, h.sig.ensure((n + 1) * 4));
@@ -629,26 +770,27 @@ void fill_blocks(fsb_ctx* c, const Batch& b, const HostOut& h, fsb_block* blocks
 {
     const ChunkSummary* sum = h.summary.as<ChunkSummary>();
     uint64_t alg_out = 0;
-    for (uint32_t ci = 0; ci < b.n_chunks; ++ci)
-    {
-        const ChunkSummary& s = sum[ci];
-        fsb_block& o = blocks[ci];
-        std::memset(&o, 0, sizeof(o));
-        o.meta = h.out[0].as<uint8_t>() + s.off[0]; o.meta_size = s.size[0];
-        o.dna = h.out[1].as<uint8_t>() + s.off[1];  o.dna_size = s.size[1];
-        o.qua = h.out[2].as<uint8_t>() + s.off[2];  o.qua_size = s.size[2];
-        o.head = h.out[3].as<uint8_t>() + s.off[3]; o.head_size = s.size[3];
-        o.raw_dna_size = s.raw_dna; o.raw_head_size = s.raw_head;
-        o.bins = h.desc.as<fsb_bin_descriptor>() + s.first_bin;
-        o.n_bins = s.n_bins;
-        o.n_records = b.chunk_first_rec[ci + 1] - b.chunk_first_rec[ci];
-        if (c->per_read)
+    for (const Sub& sb : b.subs)
+        for (uint32_t ci = sb.c0; ci < sb.c1; ++ci)
         {
-            o.read_signature = h.sig.as<uint32_t>() + b.chunk_first_rec[ci];
-            o.read_info = h.info.as<uint32_t>() + b.chunk_first_rec[ci];
+            const ChunkSummary& s = sum[ci];                     // offsets and bin indices count from the sub-batch's regions
+            fsb_block& o = blocks[ci];
+            std::memset(&o, 0, sizeof(o));
+            o.meta = h.out[0].as<uint8_t>() + sb.out_off[0] + s.off[0]; o.meta_size = s.size[0];
+            o.dna = h.out[1].as<uint8_t>() + sb.out_off[1] + s.off[1];  o.dna_size = s.size[1];
+            o.qua = h.out[2].as<uint8_t>() + sb.out_off[2] + s.off[2];  o.qua_size = s.size[2];
+            o.head = h.out[3].as<uint8_t>() + sb.out_off[3] + s.off[3]; o.head_size = s.size[3];
+            o.raw_dna_size = s.raw_dna; o.raw_head_size = s.raw_head;
+            o.bins = h.desc.as<fsb_bin_descriptor>() + sb.bin_off + s.first_bin;
+            o.n_bins = s.n_bins;
+            o.n_records = b.chunk_first_rec[ci + 1] - b.chunk_first_rec[ci];
+            if (c->per_read)
+            {
+                o.read_signature = h.sig.as<uint32_t>() + b.chunk_first_rec[ci];
+                o.read_info = h.info.as<uint32_t>() + b.chunk_first_rec[ci];
+            }
+            alg_out += s.size[0] + s.size[1] + s.size[2] + s.size[3];
         }
-        alg_out += s.size[0] + s.size[1] + s.size[2] + s.size[3];
-    }
     c->stats.algorithmic_bytes += b.algorithmic_in + alg_out;
 }
 
@@ -702,6 +844,16 @@ extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fs
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(nullptr, FSB_ERR_CUDA, "cudaStreamCreate failed"); }
         c->own_stream = true;
     }
+    c->lane[0].st = c->stream; c->lane[0].own = false;
+    if (cudaEventCreateWithFlags(&c->lane[0].ev_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess)
+    {
+        fsb_destroy(c);
+        return fail(nullptr, FSB_ERR_CUDA, "cudaEventCreate failed");
+    }
+    // tuning knobs for experiments (the defaults are what the measurements in DESIGN.md chose)
+    if (const char* e = std::getenv("FSB_RUN_SPLIT")) c->run_split = (uint32_t)std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("FSB_K1_R")) c->k1_batches_per_warp = (uint32_t)std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("FSB_K4_R")) c->k4_tiles_per_block = (uint32_t)std::max(0, std::atoi(e));
     for (Batch& b : c->batch)
     {
         if (cudaEventCreateWithFlags(&b.ev_h2d, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b.ev_run, cudaEventDisableTiming) != cudaSuccess ||
@@ -726,19 +878,22 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     for (cudaEvent_t e : c->ev_check) if (e) cudaEventDestroy(e);
     for (Batch& b : c->batch)
     {
-        DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
+        DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_chunk_sums, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
                          &b.d_desc, &b.d_summary, &b.d_sig, &b.d_info};
         for (DevBuf* d : dev) d->release();
-        b.h_stage_stats.release();
+        b.h_stage_stats.release(); b.h_chunk_sums.release();
         if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
         if (b.ev_run) cudaEventDestroy(b.ev_run);
         if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);
     }
-    DevBuf* dev[] = {&c->d_keys[0], &c->d_keys[1], &c->d_cards[0], &c->d_cards[1], &c->d_slots, &c->d_counts, &c->d_counts_scan, &c->d_scan_tmp, &c->d_flags,
-                     &c->d_flags_excl, &c->d_tbase, &c->d_bin_of, &c->d_bin_start, &c->d_bin_min, &c->d_bin_max, &c->d_raw_dna, &c->d_raw_head, &c->d_bits[0], &c->d_bits[1],
-                     &c->d_bits[2], &c->d_bits[3], &c->d_P[0], &c->d_P[1], &c->d_P[2], &c->d_P[3], &c->d_bytes[0], &c->d_bytes[1],
-                     &c->d_bytes[2], &c->d_bytes[3], &c->d_BO[0], &c->d_BO[1], &c->d_BO[2], &c->d_BO[3]};
-    for (DevBuf* d : dev) d->release();
+    for (fsb_ctx::Lane& L : c->lane)
+    {
+        if (L.st && L.own) cudaStreamSynchronize(L.st);
+        L.each([](DevBuf& d) { d.release(); });
+        if (L.ev_done) cudaEventDestroy(L.ev_done);
+        if (L.st && L.own) cudaStreamDestroy(L.st);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (HostOut* h : c->host)
     {
         if (!h) continue;
@@ -759,6 +914,10 @@ extern "C" int fsb_set_option(fsb_ctx* c, int option, int64_t value)
     case FSB_OPT_PROFILE: c->profile = value != 0; return FSB_OK;
     case FSB_OPT_VALIDATE: c->validate = value != 0; return FSB_OK;
     case FSB_OPT_SUBBATCH_RECORDS: c->sub_batch_records = value > 0 ? (uint64_t)value : 1; return FSB_OK;
+    case FSB_OPT_RUN_SPLIT: c->run_split = value > 0 ? (uint32_t)std::min<int64_t>(value, 64) : 1; return FSB_OK;
+    case FSB_OPT_K1_BLOCK_BATCHES: c->k1_batches_per_warp = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FSB_OK;
+    case FSB_OPT_K4_BLOCK_TILES: c->k4_tiles_per_block = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FSB_OK;
+    case FSB_OPT_BLOCK_GRIDS_ALWAYS: c->block_grids_always = value != 0; return FSB_OK;
     }
     return fail(c, FSB_ERR_PARAM, "unknown option");
 }
@@ -815,7 +974,7 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // nothing may still be using the batch's buffers
     Batch& b = c->batch[0];
-    int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream, c->profile);
+    int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream, c->run_split, c->profile);
     if (rc != FSB_OK) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // pageable user buffers must outlive the copies; the statistics are back
     return stage_complete(c, b);
@@ -902,7 +1061,7 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         return FSB_OK;
     };
 
-    rc = stage_enqueue(c, c->batch[0], chunks + first[0], first[1] - first[0], c->s_h2d);
+    rc = stage_enqueue(c, c->batch[0], chunks + first[0], first[1] - first[0], c->s_h2d, 1);
     if (rc == FSB_OK) { cudaError_t e = cudaEventRecord(c->batch[0].ev_h2d, c->s_h2d); if (e != cudaSuccess) rc = fail(c, FSB_ERR_CUDA, cudaGetErrorString(e)); }
     for (uint32_t g = 0; g < G && rc == FSB_OK; ++g)
     {
@@ -919,7 +1078,7 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         if (g + 1 < G)
         {
             Batch& nx = c->batch[(g + 1) & 1];
-            if ((rc = stage_enqueue(c, nx, chunks + first[g + 1], first[g + 2] - first[g + 1], c->s_h2d)) != FSB_OK) break;
+            if ((rc = stage_enqueue(c, nx, chunks + first[g + 1], first[g + 2] - first[g + 1], c->s_h2d, 1)) != FSB_OK) break;
             if (cudaEventRecord(nx.ev_h2d, c->s_h2d) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
         }
     }

@@ -85,6 +85,7 @@ struct IngestPlan
     uint32_t head_pieces;    // 16-byte pieces per title window incl. the guard piece (0: no titles)
     uint32_t off_head, off_staging, off_lut, off_chunks, total_bytes;
     uint32_t blocks_per_sm;
+    uint32_t batches_per_warp;   // 0: persistent warps striding over the whole batch; R > 0: block b owns the warp batches [b * warps * R, (b + 1) * warps * R)
 };
 
 // the bit-spreading tables of pack_core.cuh; every block copies them into shared memory
@@ -196,6 +197,10 @@ __device__ __forceinline__ uint32_t chunk_of(const ChunkTables& T, uint64_t i)
 // Persistent warps: a warp walks over warp batches of 32 mates (stride = warps of the grid); the record
 // table entries of the next batch are loaded while the signature search of the current one runs, and
 // its sequence / title windows are requested as soon as the current quality regions have left.
+// With pl.batches_per_warp = R > 0 the grid is not persistent: a block owns R * warps consecutive warp
+// batches and the hardware hands blocks out as SM resources free up -- the mode used when another
+// sub-batch's kernels share the GPU (a persistent grid that could not start all its blocks at once would
+// end with a long tail).
 template <int NW, int Q>
 __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest_kernel(BatchView B, DeviceParams P, SlotGeom G, IngestPlan pl, uint32_t* __restrict__ keys,
                                                                       unsigned long long* __restrict__ cards, uint32_t* __restrict__ slots,
@@ -234,9 +239,11 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
 
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
     const uint64_t n_wb = (n_mates + 31u) >> 5;                                       // warp batches
-    const uint64_t wb_stride = (uint64_t)gridDim.x * pl.warps;
-    uint64_t wb = (uint64_t)blockIdx.x * pl.warps + warp;
-    if (wb >= n_wb) return;                                                           // (no block-wide barriers below)
+    const uint32_t R = pl.batches_per_warp;
+    const uint64_t wb_stride = R ? (uint64_t)pl.warps : (uint64_t)gridDim.x * pl.warps;
+    const uint64_t wb_end = R ? min(n_wb, ((uint64_t)blockIdx.x + 1u) * pl.warps * R) : n_wb;
+    uint64_t wb = (R ? (uint64_t)blockIdx.x * pl.warps * R : (uint64_t)blockIdx.x * pl.warps) + warp;
+    if (wb >= wb_end) return;                                                         // (no block-wide barriers below)
     const unsigned m = P.paired ? (lane & 1u) : 0u;
     const uint32_t lrec = P.paired ? (lane >> 1) : lane;                              // record index inside the warp
     const uint8_t* my_text = m ? B.text[1] : B.text[0];
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
     for (;;)
     {
         const uint64_t wb_next = wb + wb_stride;
-        const bool more = wb_next < n_wb;                                             // warp uniform
+        const bool more = wb_next < wb_end;                                           // warp uniform
         const bool live = cur.live;
         const uint32_t L = cur.rec.w & 0xFFFFu, H = (m == 0 && P.has_headers) ? ((cur.rec.w >> 16) & 0xFFu) : 0u;
         const uint64_t i = P.paired ? ((wb * 32u + lane) >> 1) : (wb * 32u + lane);   // record (pair) index

@@ -140,6 +140,7 @@ struct PlacePlan
     uint32_t slot_stride;    // words per slot in shared memory (odd number of 16-byte units: conflict-free 16-byte reads)
     uint32_t slot_bytes;     // one buffer of T slots (there are two: the next tile's slots arrive while this one is placed)
     uint32_t off_plan, off_slots, off_staging[4], staging_bytes, total_bytes;
+    uint32_t tiles_per_block;  // 0: persistent blocks striding over all tiles; R > 0: block b owns the tiles [b * R, (b + 1) * R)
 };
 inline uint32_t staging_words(uint32_t T, uint32_t bits_per_record) { return ((T * bits_per_record + 31u) / 32u + 6u + 3u) & ~3u; }
 
@@ -265,10 +266,13 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
     const uint32_t npieces = (G.qw + G.tw + 3u) >> 2;
     const uint32_t* my_loc = role == 0 ? pm.loc[0] : (role == 1 ? pm.loc[1] : (role == 2 ? pm.loc[2] : pm.loc[3]));
 
+    // persistent: tiles blockIdx.x, + gridDim.x, ..; otherwise a run of consecutive tiles per block (see ingest_kernel)
+    const uint64_t stride = pl.tiles_per_block ? 1u : gridDim.x;
+    const uint64_t tile_end = pl.tiles_per_block ? min(tiles, ((uint64_t)blockIdx.x + 1u) * pl.tiles_per_block) : tiles;
     auto load_tile = [&](uint64_t tile) -> TileRegs
     {
         TileRegs r{};
-        if (tile < tiles)
+        if (tile < tile_end)
         {
             const uint64_t i = tile * T + lane;
             if (i < n) { r.card = a.S.cards[i]; r.loc = my_loc[i]; r.binfo = pm.binfo[i]; }
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
     // warp w fetches the slots of records w, w + 4, .. of the tile: lane p copies 16-byte piece p, p + 32, ..
     auto gather = [&](uint64_t tile, const TileRegs& r, uint32_t buf)
     {
-        if (tile < tiles)
+        if (tile < tile_end)
         {
             const uint32_t ntile = (uint32_t)min((uint64_t)T, n - tile * T);
             const uint32_t my_rec = card_rec(r.card);
@@ -307,12 +311,11 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
         for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
     }
-    uint64_t tile = blockIdx.x;
-    const uint64_t stride = gridDim.x;
+    uint64_t tile = pl.tiles_per_block ? (uint64_t)blockIdx.x * pl.tiles_per_block : (uint64_t)blockIdx.x;
     TileRegs cur = load_tile(tile), nxt = load_tile(tile + stride);
     uint32_t buf = 0;
     gather(tile, cur, buf);
-    for (; tile < tiles; tile += stride)
+    for (; tile < tile_end; tile += stride)
     {
         gather(tile + stride, nxt, buf ^ 1u);                         // in flight while this tile is placed
         const TileRegs nn = load_tile(tile + 2 * stride);             // used in the next round

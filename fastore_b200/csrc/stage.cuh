@@ -24,8 +24,11 @@ struct StageStats
     uint32_t n_bad_text, pad;
 };
 
+// chunk_sums[2 c] / [2 c + 1]: bases (both mates) and kept title bytes of chunk c -- they bound the chunk's output, which lets
+// fsb_run give every sub-batch of whole chunks its own region of the output streams.
 __global__ void __launch_bounds__(256) stage_stats_kernel(BatchView B, DeviceParams P, const uint64_t* __restrict__ text_size0,
-                                                          const uint64_t* __restrict__ text_size1, StageStats* __restrict__ st)
+                                                          const uint64_t* __restrict__ text_size1, StageStats* __restrict__ st,
+                                                          unsigned long long* __restrict__ chunk_sums)
 {
     __shared__ unsigned long long sh_bases, sh_heads;
     __shared__ uint32_t sh_min, sh_max, sh_hmax;
@@ -33,23 +36,39 @@ __global__ void __launch_bounds__(256) stage_stats_kernel(BatchView B, DevicePar
     __syncthreads();
     uint64_t bases = 0, heads = 0;
     uint32_t mn = 0xFFFFFFFFu, mx = 0, hmx = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B.n_records; i += (uint64_t)gridDim.x * blockDim.x)
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < B.n_records; i0 += (uint64_t)gridDim.x * blockDim.x)     // block uniform
     {
-        const uint32_t ch = find_chunk(B, i);
-        const fsb_record a = B.rec[0][i];
-        const uint64_t ts0 = text_size0[ch];
-        bool ok = a.seq_len >= 1 && a.seq_len <= 255 && (uint64_t)a.seq_off + a.seq_len <= ts0 && (uint64_t)a.qua_off + a.seq_len <= ts0 &&
-                  (uint64_t)a.head_off + a.head_len <= ts0;
-        bases += a.seq_len; heads += a.head_len;
-        mn = min(mn, (uint32_t)a.seq_len); mx = max(mx, (uint32_t)a.seq_len); hmx = max(hmx, (uint32_t)a.head_len);
-        if (P.paired)
+        const uint64_t i = i0 + threadIdx.x;
+        const bool live = i < B.n_records;
+        uint32_t ch = 0xFFFFFFFFu, rb = 0, rh = 0;
+        if (live)
         {
-            const fsb_record b = B.rec[1][i];
-            const uint64_t ts1 = text_size1[ch];
-            ok = ok && b.seq_len == a.seq_len && (uint64_t)b.seq_off + b.seq_len <= ts1 && (uint64_t)b.qua_off + b.seq_len <= ts1;
-            bases += b.seq_len;
+            ch = find_chunk(B, i);
+            const fsb_record a = B.rec[0][i];
+            const uint64_t ts0 = text_size0[ch];
+            bool ok = a.seq_len >= 1 && a.seq_len <= 255 && (uint64_t)a.seq_off + a.seq_len <= ts0 && (uint64_t)a.qua_off + a.seq_len <= ts0 &&
+                      (uint64_t)a.head_off + a.head_len <= ts0;
+            rb = a.seq_len; rh = a.head_len;
+            mn = min(mn, (uint32_t)a.seq_len); mx = max(mx, (uint32_t)a.seq_len); hmx = max(hmx, (uint32_t)a.head_len);
+            if (P.paired)
+            {
+                const fsb_record b = B.rec[1][i];
+                const uint64_t ts1 = text_size1[ch];
+                ok = ok && b.seq_len == a.seq_len && (uint64_t)b.seq_off + b.seq_len <= ts1 && (uint64_t)b.qua_off + b.seq_len <= ts1;
+                rb += b.seq_len;
+            }
+            if (!ok) { atomicAdd(&st->n_bad, 1u); atomicMin(&st->first_bad, (unsigned long long)i); }
         }
-        if (!ok) { atomicAdd(&st->n_bad, 1u); atomicMin(&st->first_bad, (unsigned long long)i); }
+        bases += rb; heads += rh;
+        // per-chunk sums: the lanes of a warp nearly always share the chunk, one lane per (warp, chunk) adds
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, ch);
+        const uint32_t sb = __reduce_add_sync(peers, rb), sh = __reduce_add_sync(peers, rh);
+        if (live && (unsigned)(__ffs(peers) - 1) == lane)
+        {
+            atomicAdd(&chunk_sums[2 * ch], (unsigned long long)sb);
+            atomicAdd(&chunk_sums[2 * ch + 1], (unsigned long long)sh);
+        }
     }
     atomicAdd(&sh_bases, (unsigned long long)bases); atomicAdd(&sh_heads, (unsigned long long)heads);
     atomicMin(&sh_min, mn); atomicMax(&sh_max, mx); atomicMax(&sh_hmax, hmx);

@@ -147,7 +147,13 @@ enum {
     FSB_OPT_VALIDATE = 3,    /* device-side check of the bytes behind the record table in fsb_stage / fsb_bin_chunks: sequence
                                 symbols A C G T N, quality in [offset, offset + 64) (>= offset in the 1-bit mode), 7-bit title
                                 characters; default 1.  The record table itself (lengths, offsets, mate lengths) is always checked. */
-    FSB_OPT_SUBBATCH_RECORDS = 4  /* fsb_bin_chunks pipelines sub-batches of at least this many records (default 400000) */
+    FSB_OPT_SUBBATCH_RECORDS = 4, /* fsb_bin_chunks pipelines sub-batches of at least this many records (default 400000) */
+    FSB_OPT_RUN_SPLIT = 5,        /* fsb_run cuts the staged batch into this many sub-batches of whole chunks and overlaps them on
+                                     two streams (takes effect at the next fsb_stage; 1 = one pass on the context's stream) */
+    /* tuning knobs behind the measurements in DESIGN.md (may change between versions) */
+    FSB_OPT_K1_BLOCK_BATCHES = 6, /* warp batches per warp of a K1 block when sub-batches share the GPU (0: persistent grid) */
+    FSB_OPT_K4_BLOCK_TILES = 7,   /* tiles per K4 block in that mode (0: persistent grid) */
+    FSB_OPT_BLOCK_GRIDS_ALWAYS = 8 /* use those block sizes for unsplit runs as well */
 };
 
 /* pipeline stages reported by fsb_stage_times (order of execution inside fsb_run) */

@@ -170,6 +170,35 @@ def test_parser_table_equals_generator_table_on_gpu_path():
     assert int(recs["head_len"].max()) < int(r1["head_len"].min())
 
 
+@pytest.mark.parametrize("paired,split", [(True, 2), (False, 3), (True, 4), (True, 9)])
+def test_run_split_gives_the_same_blocks(paired, split):
+    """FSB_OPT_RUN_SPLIT: fsb_run cuts the staged batch into sub-batches of whole chunks and runs them on two streams with
+    their own intermediates and their own regions of the result buffers (non-persistent K1 / K4 grids).  Every chunk
+    must still yield exactly its own block, whatever the split (9 > chunks: one chunk per sub-batch), run after run."""
+    params = N.make_params(signature_len=8, skip_zone_len=0, paired_end=paired)
+    keep, chunks = [], []
+    for ci, (n, L) in enumerate([(9000, 100), (1, 100), (12000, 151), (5000, 36), (4097, 100), (20000, 150), (300, 150)]):
+        cfg = synth.synth_config(n, L, paired=paired, seed=950 + ci, first_index=ci * 100000, nrich=0.05, lowcomplex=0.05, alln=0.01, tie=0.02)
+        t = synth.generate(cfg, threads=2)
+        keep.append(t)
+        chunks.append(N.make_chunk(t[0], t[2], t[1], t[3]))
+    want = [O.bin_chunk("orc", params, ch) for ch in chunks]
+    with GpuBinner(params, per_read=True, run_split=split) as g:
+        g.stage(chunks)
+        for rep in range(3):
+            g.run()
+            got = g.fetch()
+            for ci in range(len(chunks)):
+                O.assert_blocks_equal(gpu_block_dict(got[ci]), want[ci], f"split {split}, run {rep}, chunk {ci}")
+        # back to one pass on the same context
+        g.set_run_split(1)
+        g.stage(chunks)
+        g.run()
+        got = g.fetch()
+        for ci in range(len(chunks)):
+            O.assert_blocks_equal(gpu_block_dict(got[ci]), want[ci], f"unsplit after split, chunk {ci}")
+
+
 @pytest.mark.parametrize("paired", [False, True])
 def test_many_chunks_in_one_batch(paired):
     """More than 32 chunks in one batch: K1 then looks the chunk of a record up by binary search in global memory
