@@ -30,6 +30,7 @@
 #include "ingest.cuh"
 #include "layout.cuh"
 #include "place.cuh"
+#include "layout_fused.cuh"
 
 using namespace fsb;
 
@@ -90,7 +91,7 @@ struct Sub
     uint32_t c0 = 0, c1 = 0;                     // chunks [c0, c1)
     uint64_t r0 = 0, r1 = 0;                     // records [r0, r1)
     uint64_t nb_max = 0, bin_off = 0;            // bound of the number of bins; first entry in the batch's descriptor array
-    int sort_passes = 0;
+    uint64_t tile_off = 0, n_tiles = 0;          // its sort tiles in the batch's tile table
     size_t out_off[4] = {0, 0, 0, 0}, out_cap[4] = {0, 0, 0, 0};   // its region of the batch's output streams (bytes, 64-byte aligned)
     size_t meta_first = 0;                       // index of its relative first-record table in the device chunk tables
 };
@@ -110,7 +111,8 @@ struct Batch
     std::vector<Sub> subs;
     size_t out_total[4] = {0, 0, 0, 0};          // sum of the sub-batches' regions
 
-    DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats, d_chunk_sums;
+    std::vector<SortTile> tiles_host;            // sort tiles of all sub-batches (must outlive its async copy)
+    DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats, d_chunk_sums, d_sort_tiles;
     PinBuf h_stage_stats, h_chunk_sums;
     DevBuf d_out[4], d_desc, d_summary, d_sig, d_info;
     cudaEvent_t ev_h2d = nullptr, ev_run = nullptr, ev_d2h = nullptr;
@@ -147,11 +149,13 @@ struct fsb_ctx
         DevBuf d_keys[2], d_cards[2], d_slots, d_counts, d_counts_scan, d_scan_tmp;
         DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head, d_tbase;
         DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4];
+        DevBuf d_lay_states, d_chunk_start, d_nb;     // the one-scan layout (layout_fused.cuh)
         template <class F> void each(F f)
         {
             DevBuf* all[] = {&d_keys[0], &d_keys[1], &d_cards[0], &d_cards[1], &d_slots, &d_counts, &d_counts_scan, &d_scan_tmp, &d_flags, &d_flags_excl,
                              &d_bin_of, &d_bin_start, &d_bin_min, &d_bin_max, &d_raw_dna, &d_raw_head, &d_tbase, &d_bits[0], &d_bits[1], &d_bits[2], &d_bits[3],
-                             &d_P[0], &d_P[1], &d_P[2], &d_P[3], &d_bytes[0], &d_bytes[1], &d_bytes[2], &d_bytes[3], &d_BO[0], &d_BO[1], &d_BO[2], &d_BO[3]};
+                             &d_P[0], &d_P[1], &d_P[2], &d_P[3], &d_bytes[0], &d_bytes[1], &d_bytes[2], &d_bytes[3], &d_BO[0], &d_BO[1], &d_BO[2], &d_BO[3],
+                             &d_lay_states, &d_chunk_start, &d_nb};
             for (DevBuf* d : all) f(*d);
         }
     } lane[2];
@@ -159,6 +163,7 @@ struct fsb_ctx
     uint32_t run_split = 1;                      // sub-batches fsb_run cuts a staged batch into (FSB_OPT_RUN_SPLIT)
     uint32_t k1_batches_per_warp = 32, k4_tiles_per_block = 64;   // block granularity of K1 / K4 when sub-batches share the GPU (0: persistent)
     bool block_grids_always = false;             // use that granularity for unsplit runs too (measurement only)
+    bool fused_layout = true;                    // batches of one read length take the one-scan layout (FSB_OPT_FUSED_LAYOUT, measurement only)
 
     // ---- profiling -----------------------------------------------------------------------------
     std::vector<cudaEvent_t> events;             // kMaxPendingProfiles * (FSB_STAGE_COUNT + 1)
@@ -244,14 +249,15 @@ cudaError_t launch_ingest(const BatchView& B, const DeviceParams& P, const SlotG
     return launch_ingest_q<NW, 1>(B, P, G, max_head, R, keys, cards, slots, sig, info, st);
 }
 
-cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_len, uint32_t max_head, uint32_t R, cudaStream_t st, int* launches)
+cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_len, uint32_t max_head, uint32_t R, bool tables_ready, cudaStream_t st, int* launches)
 {
     const uint64_t n = pa.B.n_records;
     PlacePlan pl = make_place_plan(pa.P, pa.G, max_len, max_head);
     pl.tiles_per_block = R;
     const uint64_t tiles = (n + pl.T - 1) / pl.T;
-    // placement tables (tile ranges, every record's position inside its tile) and the zeroing of the words two tiles share
-    placement_kernel<<<(unsigned)((tiles * pl.T + 255) / 256), 256, 0, st>>>(pa, pm, tiles);
+    // placement tables (tile ranges, every record's position inside its tile) and the zeroing of the words two tiles share --
+    // unless the one-scan layout has produced them already
+    if (!tables_ready) { placement_kernel<<<(unsigned)((tiles * pl.T + 255) / 256), 256, 0, st>>>(pa, pm, tiles); *launches += 1; }
     cudaError_t e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total_bytes);
     if (e != cudaSuccess) return e;
     // persistent blocks: as many as fit on the device at once
@@ -262,7 +268,7 @@ cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_
     const unsigned blocks = R ? (unsigned)std::max<uint64_t>(1, (tiles + R - 1) / R)
                               : (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
     place_kernel<<<blocks, pl.threads, pl.total_bytes, st>>>(pa, pl, pm, tiles);
-    *launches += 2;
+    *launches += 1;
     return cudaGetLastError();
 }
 
@@ -392,6 +398,32 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     CUDA_TRY(c, b.d_chunk_meta.ensure(meta.size() * sizeof(uint64_t)));
     CUDA_TRY(c, cudaMemcpyAsync(b.d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     h2d += meta.size() * sizeof(uint64_t);
+    // sort tiles: every tile lies inside one chunk (scan_sort.cuh)
+    b.tiles_host.clear();
+    for (Sub& sb : b.subs)
+    {
+        sb.tile_off = b.tiles_host.size();
+        uint32_t cblk = 0;
+        for (uint32_t ci = sb.c0; ci < sb.c1; ++ci)
+        {
+            const uint64_t first = b.chunk_first_rec[ci] - sb.r0, cnt = b.chunk_first_rec[ci + 1] - b.chunk_first_rec[ci];
+            const uint32_t nblk = (uint32_t)((cnt + kSortTile - 1) / kSortTile);
+            for (uint32_t k = 0; k < nblk; ++k)
+            {
+                SortTile t{};
+                t.first = (uint32_t)(first + (uint64_t)k * kSortTile);
+                t.count = (uint32_t)std::min<uint64_t>(kSortTile, cnt - (uint64_t)k * kSortTile);
+                t.cblk = cblk; t.blk = k; t.nblk = nblk;
+                b.tiles_host.push_back(t);
+            }
+            cblk += nblk;
+        }
+        sb.n_tiles = b.tiles_host.size() - sb.tile_off;
+    }
+    CUDA_TRY(c, b.d_sort_tiles.ensure((b.tiles_host.size() + 1) * sizeof(SortTile)));
+    if (!b.tiles_host.empty())
+        CUDA_TRY(c, cudaMemcpyAsync(b.d_sort_tiles.p, b.tiles_host.data(), b.tiles_host.size() * sizeof(SortTile), cudaMemcpyHostToDevice, st));
+    h2d += b.tiles_host.size() * sizeof(SortTile);
 
     CUDA_TRY(c, b.d_stage_stats.ensure(sizeof(StageStats)));
     CUDA_TRY(c, b.h_stage_stats.ensure(2 * sizeof(StageStats)));
@@ -471,7 +503,6 @@ int stage_complete(fsb_ctx* c, Batch& b)
         uint64_t sb_bases = 0, sb_heads = 0;
         for (uint32_t ci = sb.c0; ci < sb.c1; ++ci) { sb_bases += sums[2 * ci]; sb_heads += sums[2 * ci + 1]; }
         sb.nb_max = std::min<uint64_t>(ns, (uint64_t)(sb.c1 - sb.c0) * ((uint64_t)c->dp.nbin + 1));
-        sb.sort_passes = (int)((c->dp.key_bits + bits_for(sb.c1 - sb.c0 - 1) + 7) / 8);
         sb.bin_off = bin_off; bin_off += sb.nb_max + 1;
         const uint64_t pad_bytes = sb.nb_max + 64;                          // < 1 byte of padding per bin and stream
         sb.out_cap[0] = align_up((28 * ns + 17 * sb.nb_max) / 8 + pad_bytes, 64);
@@ -494,10 +525,12 @@ int stage_complete(fsb_ctx* c, Batch& b)
             L.own = true;
             CUDA_TRY(c, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
         }
-        uint64_t ln = 0, lnbm = 0;
-        for (size_t j = l; j < b.subs.size(); j += 2) { ln = std::max(ln, b.subs[j].r1 - b.subs[j].r0); lnbm = std::max(lnbm, b.subs[j].nb_max); }
-        const uint64_t nsort_blocks = (ln + kSortTile - 1) / kSortTile;
-        const uint64_t ncounts = (uint64_t)kRadix * std::max<uint64_t>(nsort_blocks, 1);
+        uint64_t ln = 0, lnbm = 0, ltiles = 0;
+        for (size_t j = l; j < b.subs.size(); j += 2)
+        {
+            ln = std::max(ln, b.subs[j].r1 - b.subs[j].r0); lnbm = std::max(lnbm, b.subs[j].nb_max); ltiles = std::max(ltiles, b.subs[j].n_tiles);
+        }
+        const uint64_t ncounts = (uint64_t)kMaxRadix * std::max<uint64_t>(ltiles, 1);
         for (int i = 0; i < 2; ++i)
         {
             CUDA_TRY(c, ensure_shared(L.st, L.d_keys[i], (ln + 1) * 4));
@@ -508,7 +541,12 @@ int stage_complete(fsb_ctx* c, Batch& b)
         CUDA_TRY(c, ensure_shared(L.st, L.d_counts_scan, (ncounts + 1) * 4));
         const uint64_t max_scan_n = std::max<uint64_t>(std::max<uint64_t>(ln, ncounts), lnbm) + 1;
         CUDA_TRY(c, ensure_shared(L.st, L.d_scan_tmp, 4 * (scan_num_tiles(max_scan_n) + 2) * 8));
-        CUDA_TRY(c, ensure_shared(L.st, L.d_flags, (ln + 1) * 4));
+        uint32_t lchunks = 0;
+        for (size_t j = l; j < b.subs.size(); j += 2) lchunks = std::max(lchunks, b.subs[j].c1 - b.subs[j].c0);
+        CUDA_TRY(c, ensure_shared(L.st, L.d_lay_states, ((ln + kLayBlock - 1) / kLayBlock + 2) * sizeof(LayState)));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_chunk_start, ((size_t)lchunks + 2) * sizeof(ChunkStart)));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_nb, 64));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_flags, (ln + 4) * 4));
         CUDA_TRY(c, ensure_shared(L.st, L.d_tbase, ((ln + kPlaceTile - 1) / kPlaceTile + 2) * 4 * 8));
         CUDA_TRY(c, ensure_shared(L.st, L.d_flags_excl, (ln + 2) * 4));
         CUDA_TRY(c, ensure_shared(L.st, L.d_bin_of, (ln + 1) * 4));
@@ -519,7 +557,7 @@ int stage_complete(fsb_ctx* c, Batch& b)
         CUDA_TRY(c, ensure_shared(L.st, L.d_raw_head, (lnbm + 1) * 8));
         for (int s = 0; s < 4; ++s)
         {
-            CUDA_TRY(c, ensure_shared(L.st, L.d_bits[s], (ln + 1) * 4));
+            CUDA_TRY(c, ensure_shared(L.st, L.d_bits[s], (ln + 4) * 4));
             CUDA_TRY(c, ensure_shared(L.st, L.d_P[s], (ln + 2) * 8));
             CUDA_TRY(c, ensure_shared(L.st, L.d_bytes[s], (lnbm + 1) * 8));
             CUDA_TRY(c, ensure_shared(L.st, L.d_BO[s], (lnbm + 2) * 8));
@@ -583,26 +621,25 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
     }
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[1], st));
 
-    // ---- K2/K3: stable radix sort of (chunk:signature -> card) --------------------------------------------
+    // ---- K2/K3: stable radix sort of the signatures inside every chunk segment (card as value) -------------------
     int cur = 0;
     if (n)
     {
-        const uint32_t nblocks = (uint32_t)((n + kSortTile - 1) / kSortTile);
-        const uint64_t ncounts = (uint64_t)kRadix * nblocks;
-        const int total_bits = (int)(c->dp.key_bits + bits_for(sub_chunks - 1));
+        const SortTile* tiles = b.d_sort_tiles.as<SortTile>() + sb.tile_off;
+        const uint32_t nblocks = (uint32_t)sb.n_tiles;
+        int width[8];
+        const int passes = sort_plan((int)c->dp.key_bits, width);
         int shift = 0;
-        for (int pass = 0; pass < sb.sort_passes; ++pass)
+        for (int pass = 0; pass < passes; ++pass)
         {
-            // the first digit takes the left-over bits (narrow), the others 8 bits each
-            const int width = pass == 0 ? total_bits - 8 * (sb.sort_passes - 1) : 8;   // (7,7,7) and (8,8,5) measured slower than (5,8,8)
-            const uint32_t mask = (1u << width) - 1u;
-            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), n, shift, mask, L.d_counts.as<uint32_t>(), nblocks);
+            const uint32_t radix = 1u << width[pass], mask = radix - 1u;
+            const uint64_t ncounts = (uint64_t)radix * nblocks;
+            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), tiles, shift, mask, radix, L.d_counts.as<uint32_t>());
             launches++;
             launches += exclusive_scan<uint32_t, uint32_t>(L.d_counts.as<uint32_t>(), ncounts, L.d_counts_scan.as<uint32_t>(), L.d_scan_tmp.as<uint32_t>(), st);
-            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), L.d_cards[cur].as<unsigned long long>(), n, shift, mask,
-                                                            L.d_counts_scan.as<uint32_t>(), nblocks, L.d_keys[cur ^ 1].as<uint32_t>(),
-                                                            L.d_cards[cur ^ 1].as<unsigned long long>());
-            shift += width;
+            sort_scatter<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), L.d_cards[cur].as<unsigned long long>(), tiles, shift, mask, radix,
+                                                            L.d_counts_scan.as<uint32_t>(), L.d_keys[cur ^ 1].as<uint32_t>(), L.d_cards[cur ^ 1].as<unsigned long long>());
+            shift += width[pass];
             launches++;
             cur ^= 1;
         }
@@ -617,8 +654,26 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
                 L.d_raw_dna.as<unsigned long long>(), L.d_raw_head.as<unsigned long long>()};
     StreamScans SC{{L.d_P[0].as<uint64_t>(), L.d_P[1].as<uint64_t>(), L.d_P[2].as<uint64_t>(), L.d_P[3].as<uint64_t>()}};
     BinOffsets BO{{L.d_BO[0].as<uint64_t>(), L.d_BO[1].as<uint64_t>(), L.d_BO[2].as<uint64_t>(), L.d_BO[3].as<uint64_t>()}};
-    const uint32_t* nb_ptr = L.d_flags_excl.as<uint32_t>() + n;
+    const bool fused = c->fused_layout && n && b.min_len == b.max_len;      // one read length: the layout is a single scan (layout_core.cuh)
+    const uint32_t* nb_ptr = fused ? L.d_nb.as<uint32_t>() : L.d_flags_excl.as<uint32_t>() + n;
     fsb_bin_descriptor* desc = b.d_desc.as<fsb_bin_descriptor>() + sb.bin_off;
+    OutStreams O{{reinterpret_cast<uint32_t*>(b.d_out[0].as<uint8_t>() + sb.out_off[0]), reinterpret_cast<uint32_t*>(b.d_out[1].as<uint8_t>() + sb.out_off[1]),
+                  reinterpret_cast<uint32_t*>(b.d_out[2].as<uint8_t>() + sb.out_off[2]), reinterpret_cast<uint32_t*>(b.d_out[3].as<uint8_t>() + sb.out_off[3])}};
+    // the placement tables take the arrays of the per-read bit lengths and the bin flags
+    Placement pm{{L.d_bits[0].as<uint32_t>(), L.d_bits[1].as<uint32_t>(), L.d_bits[2].as<uint32_t>(), L.d_bits[3].as<uint32_t>()},
+                 L.d_flags.as<uint32_t>(), L.d_tbase.as<unsigned long long>()};
+    if (fused)
+    {
+        const unsigned nlay = (unsigned)((n + kLayBlock - 1) / kLayBlock);
+        LayState* states = L.d_lay_states.as<LayState>();
+        ChunkStart* cstart = L.d_chunk_start.as<ChunkStart>();
+        lay_reduce_kernel<<<nlay, kLayThreads, 0, st>>>(n, P, S, b.min_len, states);
+        lay_scan_kernel<<<1, kLayScanThreads, 0, st>>>(states, nlay);
+        lay_apply_kernel<<<nlay, kLayThreads, 0, st>>>(n, sub_chunks, P, S, b.min_len, states, LayOut{pm, O, desc, cstart, L.d_nb.as<uint32_t>()});
+        chunk_summary_fused_kernel<<<sub_chunks, 128, 0, st>>>(B, cstart, desc, b.d_summary.as<ChunkSummary>() + sb.c0);
+        launches += 4;
+    }
+    else
     {
         const uint64_t nbm = sb.nb_max;
         CUDA_TRY(c, cudaMemsetAsync(L.d_bin_min.p, 0xFF, (nbm + 1) * 4, st));
@@ -663,15 +718,9 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
     // ---- K4: place ------------------------------------------------------------------------------------
     if (n)
     {
-        PlaceArgs pa{B, P, b.geom, S, A, SC, BO,
-                     {{reinterpret_cast<uint32_t*>(b.d_out[0].as<uint8_t>() + sb.out_off[0]), reinterpret_cast<uint32_t*>(b.d_out[1].as<uint8_t>() + sb.out_off[1]),
-                       reinterpret_cast<uint32_t*>(b.d_out[2].as<uint8_t>() + sb.out_off[2]), reinterpret_cast<uint32_t*>(b.d_out[3].as<uint8_t>() + sb.out_off[3])}},
-                     L.d_slots.as<uint32_t>(), nb_ptr};
-        // the per-read bit lengths and the bin flags are spent: their arrays take the placement tables
-        Placement pm{{L.d_bits[0].as<uint32_t>(), L.d_bits[1].as<uint32_t>(), L.d_bits[2].as<uint32_t>(), L.d_bits[3].as<uint32_t>()},
-                     L.d_flags.as<uint32_t>(), L.d_tbase.as<unsigned long long>()};
+        PlaceArgs pa{B, P, b.geom, S, A, SC, BO, O, L.d_slots.as<uint32_t>(), nb_ptr};
         int place_launches = 0;
-        CUDA_TRY(c, launch_place(pa, pm, b.max_len, b.max_head, R4, st, &place_launches));
+        CUDA_TRY(c, launch_place(pa, pm, b.max_len, b.max_head, R4, fused, st, &place_launches));
         launches += place_launches;
     }
     if (ev) CUDA_TRY(c, cudaEventRecord(ev[4], st));
@@ -878,7 +927,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     for (cudaEvent_t e : c->ev_check) if (e) cudaEventDestroy(e);
     for (Batch& b : c->batch)
     {
-        DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_chunk_sums, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
+        DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_chunk_sums, &b.d_sort_tiles, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
                          &b.d_desc, &b.d_summary, &b.d_sig, &b.d_info};
         for (DevBuf* d : dev) d->release();
         b.h_stage_stats.release(); b.h_chunk_sums.release();
@@ -918,6 +967,7 @@ extern "C" int fsb_set_option(fsb_ctx* c, int option, int64_t value)
     case FSB_OPT_K1_BLOCK_BATCHES: c->k1_batches_per_warp = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FSB_OK;
     case FSB_OPT_K4_BLOCK_TILES: c->k4_tiles_per_block = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FSB_OK;
     case FSB_OPT_BLOCK_GRIDS_ALWAYS: c->block_grids_always = value != 0; return FSB_OK;
+    case FSB_OPT_FUSED_LAYOUT: c->fused_layout = value != 0; return FSB_OK;
     }
     return fail(c, FSB_ERR_PARAM, "unknown option");
 }

@@ -257,56 +257,76 @@ inline int exclusive_scan(const IN* in, uint64_t n, OUT* out, OUT* tmp, cudaStre
     return 3;
 }
 
-// ---- stable LSD radix sort, digits of up to 8 bits --------------------------------------------------
-// (the first pass takes the bits that are left over: the low signature bits are uniform, and a narrow first digit
-// keeps the runs a block writes per digit long; the later digits are skewed anyway)
+// ---- stable LSD radix sort over chunk segments, digits of up to 9 bits -----------------------------------
+// The keys are chunk : signature, and the records of a batch already arrive chunk by chunk.  Only the
+// signature needs sorting: every sort tile lies inside one chunk (the host lays the tiles out, SortTile),
+// and the count table is chunk-major -- [chunk][digit][tile of the chunk] -- so that one exclusive scan over
+// the whole table yields global destinations in (chunk, digit, tile) order.  The chunk bits never enter a
+// digit: 2k + 1 signature bits take two passes for k = 8 (8 + 9 bits) where chunk : signature took three.
+// (The first pass takes the bits that are left over: the low signature bits are uniform, and a narrow first
+// digit keeps the runs a block writes per digit long; the later digits are skewed anyway.)
 constexpr int kSortThreads = 256;
 constexpr int kSortStrips = 16;                          // 32-key strips per warp
-constexpr int kSortTile = kSortThreads * kSortStrips;    // 4096 keys per block
-constexpr int kRadix = 256;
+constexpr int kSortTile = kSortThreads * kSortStrips;    // up to 4096 keys per block
+constexpr int kMaxRadix = 512;
 
-// counts[digit * nblocks + block]
-__global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t mask,
-                                                                uint32_t* __restrict__ counts, uint32_t nblocks)
+struct SortTile
 {
-    __shared__ uint32_t hist[kRadix];
-    hist[threadIdx.x] = 0;
+    uint32_t first;          // first key of the tile (index inside the sub-batch)
+    uint32_t count;          // keys in the tile (1 .. kSortTile)
+    uint32_t cblk;           // tiles of all earlier chunks of the sub-batch
+    uint32_t blk, nblk;      // index of the tile inside its chunk, tiles of that chunk
+    uint32_t pad[3];
+};
+__device__ __forceinline__ uint64_t sort_count_index(const SortTile& t, uint32_t radix, uint32_t digit)
+{
+    return (uint64_t)radix * t.cblk + (uint64_t)digit * t.nblk + t.blk;
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* __restrict__ keys, const SortTile* __restrict__ tiles, int shift, uint32_t mask,
+                                                                uint32_t radix, uint32_t* __restrict__ counts)
+{
+    __shared__ uint32_t hist[kMaxRadix];
+    for (uint32_t d = threadIdx.x; d < radix; d += kSortThreads) hist[d] = 0;
     __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+    const SortTile t = tiles[blockIdx.x];
 #pragma unroll 4
     for (int i = 0; i < kSortStrips; ++i)
     {
-        const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
-        const bool in = idx < n;
-        const uint32_t d = in ? ((keys[idx] >> shift) & mask) : 0xFFFFFFFFu;
+        const uint32_t local = (uint32_t)i * kSortThreads + threadIdx.x;
+        const bool in = local < t.count;
+        const uint32_t d = in ? ((keys[t.first + local] >> shift) & mask) : 0xFFFFFFFFu;
         // warp-aggregated shared atomics: bins are heavily skewed (minimizers are minima)
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
         if (in && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
     }
     __syncthreads();
-    counts[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+    for (uint32_t d = threadIdx.x; d < radix; d += kSortThreads) counts[sort_count_index(t, radix, d)] = hist[d];
 }
 
 // offsets: exclusive scan of counts (same layout).  The 64-bit values are the records' cards (core.cuh).
 __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __restrict__ keys_in, const unsigned long long* __restrict__ vals_in,
-                                                              uint64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ offsets, uint32_t nblocks,
-                                                              uint32_t* __restrict__ keys_out, unsigned long long* __restrict__ vals_out)
+                                                              const SortTile* __restrict__ tiles, int shift, uint32_t mask, uint32_t radix,
+                                                              const uint32_t* __restrict__ offsets, uint32_t* __restrict__ keys_out,
+                                                              unsigned long long* __restrict__ vals_out)
 {
-    __shared__ uint32_t warp_hist[kSortThreads / 32][kRadix];   // 8 KB
+    __shared__ uint32_t warp_hist[kSortThreads / 32][kMaxRadix];   // 16 KB
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (kSortThreads / 32) * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
+    for (uint32_t w = 0; w < kSortThreads / 32; ++w)
+        for (uint32_t d = threadIdx.x; d < radix; d += kSortThreads) warp_hist[w][d] = 0;
     __syncthreads();
+    const SortTile t = tiles[blockIdx.x];
 
     // each warp owns a contiguous run of kSortStrips * 32 keys (keeps the order stable)
-    const uint64_t wbase = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (kSortStrips * 32);
+    const uint32_t wlocal = warp * (kSortStrips * 32);
     uint32_t key[kSortStrips];
     uint32_t rank[kSortStrips];
 #pragma unroll
     for (int i = 0; i < kSortStrips; ++i)
     {
-        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
-        const bool in = idx < n;
-        key[i] = in ? keys_in[idx] : 0xFFFFFFFFu;
+        const uint32_t local = wlocal + (uint32_t)i * 32 + lane;
+        const bool in = local < t.count;
+        key[i] = in ? keys_in[t.first + local] : 0xFFFFFFFFu;
         const uint32_t d = in ? ((key[i] >> shift) & mask) : 0xFFFFFFFFu;
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
         const uint32_t before = in ? warp_hist[warp][d] : 0;
@@ -316,14 +336,15 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
         __syncwarp();
     }
     __syncthreads();
-    // digit = threadIdx.x: turn per-warp counts into global bases
+    // per digit: turn per-warp counts into global bases
+    for (uint32_t d = threadIdx.x; d < radix; d += kSortThreads)
     {
-        uint32_t run = offsets[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
+        uint32_t run = offsets[sort_count_index(t, radix, d)];
 #pragma unroll
         for (int w = 0; w < kSortThreads / 32; ++w)
         {
-            const uint32_t c = warp_hist[w][threadIdx.x];
-            warp_hist[w][threadIdx.x] = run;
+            const uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = run;
             run += c;
         }
     }
@@ -331,15 +352,24 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
 #pragma unroll
     for (int i = 0; i < kSortStrips; ++i)
     {
-        const uint64_t idx = wbase + (uint64_t)i * 32 + lane;
-        if (idx < n)
+        const uint32_t local = wlocal + (uint32_t)i * 32 + lane;
+        if (local < t.count)
         {
             const uint32_t d = (key[i] >> shift) & mask;
             const uint32_t dst = warp_hist[warp][d] + rank[i];
             keys_out[dst] = key[i];
-            vals_out[dst] = vals_in[idx];
+            vals_out[dst] = vals_in[t.first + local];
         }
     }
+}
+
+// digit widths of the passes, least significant first: as few passes of at most 9 bits as cover `bits`, evenly wide, the narrower ones first
+inline int sort_plan(int bits, int (&width)[8])
+{
+    const int passes = (bits + 8) / 9;
+    const int base = bits / passes, rem = bits % passes;
+    for (int p = 0; p < passes; ++p) width[p] = base + (p >= passes - rem ? 1 : 0);
+    return passes;
 }
 
 } // namespace fsb

@@ -153,7 +153,8 @@ enum {
     /* tuning knobs behind the measurements in DESIGN.md (may change between versions) */
     FSB_OPT_K1_BLOCK_BATCHES = 6, /* warp batches per warp of a K1 block when sub-batches share the GPU (0: persistent grid) */
     FSB_OPT_K4_BLOCK_TILES = 7,   /* tiles per K4 block in that mode (0: persistent grid) */
-    FSB_OPT_BLOCK_GRIDS_ALWAYS = 8 /* use those block sizes for unsplit runs as well */
+    FSB_OPT_BLOCK_GRIDS_ALWAYS = 8, /* use those block sizes for unsplit runs as well */
+    FSB_OPT_FUSED_LAYOUT = 9      /* 1 (default): batches whose reads all have one length take the one-scan layout; 0: always the general kernels */
 };
 
 /* pipeline stages reported by fsb_stage_times (order of execution inside fsb_run) */

@@ -270,3 +270,127 @@ extern "C" int emul_pack(const fsb_params* p, const fsb_chunk* ch, uint8_t* meta
     }
     return FSB_ERR_INPUT;
 }
+
+// ================================================================================================
+// layout as one scan (layout_core.cuh): the three phases of layout_fused.cuh -- per-thread run states, block
+// states, exclusive scan over the blocks, absolute walk -- with a free choice of records per thread and threads
+// per block, against the plain sequential walk over the sorted records.  Returns the number of mismatches
+// (positions, bin descriptors, bin count), or a negative value when the chunk's reads differ in length.
+#include "../../fastore_b200/csrc/layout_core.cuh"
+
+extern "C" long emul_layout_fused(const fsb_params* p, const fsb_chunk* ch, uint32_t per_thread, uint32_t threads)
+{
+    const DeviceParams P = make_device_params(*p);
+    const uint64_t n = ch->n_records;
+    if (n == 0) return 0;
+    std::vector<uint32_t> sig(n), info(n);
+    if (emul_signatures(p, ch, sig.data(), info.data()) != FSB_OK) return -2;
+    const bool pe = P.paired != 0;
+    uint32_t ulen = ch->records[0][0].seq_len;
+    for (int m = 0; m < (pe ? 2 : 1); ++m)
+        for (uint64_t i = 0; i < n; ++i) if (ch->records[m][i].seq_len != ulen) return -1;
+    // sorted keys and cards (one chunk: chunk bits 0; a second pseudo-chunk is made of the upper half to exercise chunk starts)
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    const uint64_t half = n / 2;
+    auto chunk_of_rec = [&](uint32_t r) { return r < half ? 0u : 1u; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const uint64_t ka = ((uint64_t)chunk_of_rec(a) << P.key_bits) | sig[a], kb = ((uint64_t)chunk_of_rec(b) << P.key_bits) | sig[b];
+        return ka < kb; });
+    std::vector<uint32_t> keys(n);
+    std::vector<uint64_t> cards(n);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const uint32_t r = order[i];
+        keys[i] = (chunk_of_rec(r) << P.key_bits) | sig[r];
+        cards[i] = card_make(r, info[r], ch->records[0][r].seq_len, pe ? ch->records[1][r].seq_len : 0, P.has_headers ? ch->records[0][r].head_len : 0);
+    }
+    // ---- the plain walk (the way run_pack above lays a chunk out) --------------------------------------------
+    std::vector<uint64_t> want_at[4];
+    for (auto& v : want_at) v.resize(n);
+    std::vector<fsb_bin_descriptor> want_desc;
+    {
+        uint64_t pos[4] = {0, 0, 0, 0}, start[4] = {0, 0, 0, 0};
+        fsb_bin_descriptor d{};
+        for (uint64_t i = 0; i < n; ++i)
+        {
+            const bool st = i == 0 || keys[i] != keys[i - 1];
+            if (st)
+            {
+                for (int s = 0; s < 4; ++s) { pos[s] = (pos[s] + 7) & ~7ull; start[s] = pos[s]; }
+                pos[0] += 17;
+                d = fsb_bin_descriptor{};
+                d.signature = keys[i] & ((1u << P.key_bits) - 1u);
+            }
+            const uint64_t c = cards[i];
+            const bool nbin = d.signature == P.nbin;
+            const ReadBits rb = read_bit_lengths(P, nbin, card_info(c), card_lenA(c), card_lenB(c), card_head(c), ulen, ulen);
+            const uint32_t bits[4] = {rb.meta, rb.dna, rb.qua, rb.head};
+            for (int s = 0; s < 4; ++s) { want_at[s][i] = pos[s]; pos[s] += bits[s]; }
+            d.records_count++; d.raw_dna_size += card_lenA(c) + card_lenB(c); d.raw_head_size += P.has_headers ? card_head(c) : 0;
+            if (i + 1 == n || keys[i + 1] != keys[i])
+            {
+                d.meta_size = (((pos[0] + 7) & ~7ull) - start[0]) >> 3; d.dna_size = (((pos[1] + 7) & ~7ull) - start[1]) >> 3;
+                d.qua_size = (((pos[2] + 7) & ~7ull) - start[2]) >> 3; d.head_size = (((pos[3] + 7) & ~7ull) - start[3]) >> 3;
+                want_desc.push_back(d);
+            }
+        }
+    }
+    // ---- the three phases ------------------------------------------------------------------------------------------
+    const uint64_t per_block = (uint64_t)per_thread * threads;
+    const uint64_t nblocks = (n + per_block - 1) / per_block;
+    auto run_state = [&](uint64_t i0, uint64_t cnt) {
+        LayState st = lay_identity();
+        for (uint64_t j = 0; j < cnt; ++j)
+            lay_push(st, lay_record(P, i0 + j == 0, keys[i0 + j], i0 + j ? keys[i0 + j - 1] : 0u, cards[i0 + j], ulen));
+        return st;
+    };
+    auto thread_run = [&](uint64_t blk, uint32_t t, uint64_t& i0, uint64_t& cnt) {
+        i0 = (blk * threads + t) * per_thread;
+        cnt = i0 < n ? std::min<uint64_t>(per_thread, n - i0) : 0;
+    };
+    std::vector<LayState> block_state(nblocks + 1);
+    for (uint64_t blk = 0; blk < nblocks; ++blk)                        // lay_reduce
+    {
+        LayState tot = lay_identity();
+        for (uint32_t t = 0; t < threads; ++t) { uint64_t i0, cnt; thread_run(blk, t, i0, cnt); tot = lay_combine(tot, run_state(i0, cnt)); }
+        block_state[blk] = tot;
+    }
+    {                                                                   // lay_scan (exclusive, in place)
+        LayState carry = lay_identity();
+        for (uint64_t blk = 0; blk < nblocks; ++blk) { const LayState mine = block_state[blk]; block_state[blk] = carry; carry = lay_combine(carry, mine); }
+        block_state[nblocks] = carry;
+    }
+    long bad = 0;
+    std::vector<fsb_bin_descriptor> got_desc(want_desc.size() + 1);
+    uint32_t nb_total = 0;
+    for (uint64_t blk = 0; blk < nblocks; ++blk)                        // lay_apply
+    {
+        LayState before = block_state[blk];
+        for (uint32_t t = 0; t < threads; ++t)
+        {
+            uint64_t i0, cnt;
+            thread_run(blk, t, i0, cnt);
+            LayCursor cur = lay_cursor(before);
+            for (uint64_t j = 0; j < cnt; ++j)
+            {
+                const uint64_t i = i0 + j;
+                const LayRec r = lay_record(P, i == 0, keys[i], i ? keys[i - 1] : 0u, cards[i], ulen);
+                uint64_t at[4];
+                lay_step(cur, r, at);
+                for (int s = 0; s < 4; ++s) if (at[s] != want_at[s][i]) bad++;
+                if (i + 1 == n || keys[i + 1] != keys[i])
+                {
+                    if (cur.nb == 0 || cur.nb > want_desc.size()) { bad++; continue; }
+                    got_desc[cur.nb - 1] = lay_descriptor(cur, keys[i] & ((1u << P.key_bits) - 1u));
+                }
+                if (i + 1 == n) nb_total = cur.nb;
+            }
+            before = lay_combine(before, run_state(i0, cnt));
+        }
+    }
+    if (nb_total != want_desc.size()) bad++;
+    if (block_state[nblocks].nstarts != want_desc.size()) bad++;
+    for (size_t b = 0; b < want_desc.size(); ++b) if (std::memcmp(&got_desc[b], &want_desc[b], sizeof(fsb_bin_descriptor)) != 0) bad++;
+    return bad;
+}

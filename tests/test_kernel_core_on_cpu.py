@@ -58,3 +58,19 @@ def test_pack_core_matches_oracle(emul, name):
         got = bufs[k][: want[s].size]
         bad = np.nonzero(got != want[s])[0]
         assert bad.size == 0, f"{name}: stream {s} differs at byte {bad[0]} of {want[s].size} ({bad.size} bytes differ)"
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+@pytest.mark.parametrize("per_thread,threads", [(32, 128), (3, 5), (1, 7), (32, 4)])
+def test_one_scan_layout_matches_the_sequential_walk(emul, name, per_thread, threads):
+    """layout_core.cuh: the framing rules as an associative scan (run states, block states, exclusive scan, absolute
+    walk) give every record the bit positions and every bin the descriptor of the plain sequential walk, for any
+    decomposition into threads and blocks.  Cases whose reads differ in length are outside this form (they take the
+    general layout kernels) and are skipped here."""
+    params, chunk, keep = make_case(name)
+    emul.emul_layout_fused.restype = C.c_long
+    emul.emul_layout_fused.argtypes = [C.POINTER(N.FsbParams), C.POINTER(N.FsbChunk), C.c_uint32, C.c_uint32]
+    bad = emul.emul_layout_fused(C.byref(params), C.byref(chunk), per_thread, threads)
+    if bad == -1:
+        pytest.skip("reads of different lengths")
+    assert bad == 0, f"{name}: {bad} mismatches"
