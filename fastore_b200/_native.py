@@ -127,6 +127,19 @@ def host_lib() -> C.CDLL:
         lib.fsh_parse_chunk.restype = C.c_int
         lib.fsh_parse_chunk.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_uint64, C.POINTER(FshParseStats)]
+        lib.fsh_parse_chunk_ex.restype = C.c_int
+        lib.fsh_parse_chunk_ex.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_uint64, C.POINTER(FshParseStats)]
+        lib.fsh_titles_new.restype = C.c_void_p
+        lib.fsh_titles_new.argtypes = []
+        lib.fsh_titles_free.restype = None
+        lib.fsh_titles_free.argtypes = [C.c_void_p]
+        lib.fsh_titles_add.restype = C.c_int
+        lib.fsh_titles_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.fsh_titles_consistent.restype = C.c_int
+        lib.fsh_titles_consistent.argtypes = [C.c_void_p]
+        lib.fsh_writer_merge_titles.restype = C.c_int
+        lib.fsh_writer_merge_titles.argtypes = [C.c_void_p, C.c_void_p]
         lib.fsh_max_records.restype = C.c_uint64
         lib.fsh_max_records.argtypes = [C.c_void_p, C.c_uint64]
         lib.fsh_cut_position.restype = C.c_uint64

@@ -87,6 +87,8 @@ def build_oracle(verbose=False) -> None:
     _run(["make", "-C", ROOT / "oracle", "port"], verbose)
     if Path(os.environ.get("FASTORE_REFERENCE", "/root/reference")).is_dir():
         _run(["make", "-C", ROOT / "oracle", "-j8", "ref"], verbose)
+        if CUDA_LIB.exists():                      # the reference's fastore_bin with the C ABI bound in (integration/)
+            _run(["make", "-C", ROOT / "oracle", "ref_gpu"], verbose)
 
 
 def build_all(force=False, verbose=False) -> None:

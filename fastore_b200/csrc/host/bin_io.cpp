@@ -240,12 +240,15 @@ extern "C" fsh_writer* fsh_writer_open(const char* prefix, const fsh_bin_config*
     return w;
 }
 
-// Titles of one parsed chunk -> header field statistics (Stats.cpp:90-169).
-extern "C" int fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const fsb_record* records, uint64_t n)
+namespace {
+
+// FastqRawBlockStats::Update(const FastqRecord&) for the title of every record of a table (Stats.cpp:90-169).  Returns false
+// when a field is numeric in one record and not in another (the reference ASSERTs that this does not happen): such
+// statistics depend on the order of the records and must not be merged from parts.
+bool titles_update(std::vector<HeadField>& fields, const uint8_t* text, const fsb_record* records, uint64_t n)
 {
-    if (!w || (!text && n) || (!records && n)) return FSB_ERR_PARAM;
-    if (!w->cfg.params.reads_have_headers) return FSB_OK;
     static const char seps[] = " ./:#+";
+    bool consistent = true;
     for (uint64_t r = 0; r < n; ++r)
     {
         const char* head = (const char*)text + records[r].head_off;
@@ -258,10 +261,10 @@ extern "C" int fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const f
             const uint32_t flen = i - start;
             uint64_t v;
             const bool numeric = is_num(fs, flen, v);
-            if (w->fields.size() < field_no + 1)
+            if (fields.size() < field_no + 1)
             {
-                w->fields.emplace_back();
-                HeadField& f = w->fields.back();
+                fields.emplace_back();
+                HeadField& f = fields.back();
                 f.is_const = true;
                 f.is_numeric = numeric;
                 if (numeric) f.min_value = f.max_value = v;
@@ -270,7 +273,8 @@ extern "C" int fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const f
             }
             else
             {
-                HeadField& f = w->fields[field_no];
+                HeadField& f = fields[field_no];
+                if (numeric != f.is_numeric) consistent = false;
                 if (numeric)
                 {
                     f.min_value = std::min(f.min_value, v);
@@ -285,6 +289,59 @@ extern "C" int fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const f
             }
             start = i + 1;
             field_no++;
+        }
+    }
+    return consistent;
+}
+
+} // namespace
+
+// Titles of one parsed chunk -> header field statistics (Stats.cpp:90-169).
+extern "C" int fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const fsb_record* records, uint64_t n)
+{
+    if (!w || (!text && n) || (!records && n)) return FSB_ERR_PARAM;
+    if (!w->cfg.params.reads_have_headers) return FSB_OK;
+    titles_update(w->fields, text, records, n);
+    return FSB_OK;
+}
+
+// The same statistics gathered away from the writer (parser threads), then merged in chunk order -- what the reference does
+// with the FastqRawBlockStats of every parsed chunk (FastqRawBlockStats::Update(const FastqRawBlockStats&), Stats.cpp:205-236).
+struct fsh_titles
+{
+    std::vector<HeadField> fields;
+    bool consistent = true;
+};
+extern "C" fsh_titles* fsh_titles_new(void) { return new fsh_titles(); }
+extern "C" void fsh_titles_free(fsh_titles* t) { delete t; }
+extern "C" int fsh_titles_add(fsh_titles* t, const uint8_t* text, const fsb_record* records, uint64_t n)
+{
+    if (!t || (!text && n) || (!records && n)) return FSB_ERR_PARAM;
+    t->consistent = titles_update(t->fields, text, records, n) && t->consistent;
+    return FSB_OK;
+}
+extern "C" int fsh_titles_consistent(const fsh_titles* t) { return t && t->consistent ? 1 : 0; }
+extern "C" int fsh_writer_merge_titles(fsh_writer* w, const fsh_titles* t)
+{
+    if (!w || !t) return FSB_ERR_PARAM;
+    if (!w->cfg.params.reads_have_headers) return FSB_OK;
+    if (!t->consistent) { g_err = "title statistics of this chunk depend on the record order: add the titles with fsh_writer_add_titles"; return FSB_ERR_STATE; }
+    for (size_t i = 0; i < t->fields.size(); ++i)
+    {
+        const HeadField& p = t->fields[i];
+        if (w->fields.size() <= i) { w->fields.push_back(p); continue; }
+        HeadField& f = w->fields[i];
+        if (f.is_numeric != p.is_numeric) { g_err = "title field " + std::to_string(i) + " is numeric in one chunk and not in another"; return FSB_ERR_INPUT; }
+        if (f.is_numeric)
+        {
+            f.min_value = std::min(f.min_value, p.min_value);
+            f.max_value = std::max(f.max_value, p.max_value);
+            f.is_const = f.is_const && p.is_const && f.min_value == f.max_value;
+        }
+        else
+        {
+            f.values.insert(p.values.begin(), p.values.end());
+            f.is_const = f.is_const && p.is_const && f.values.size() == 1;
         }
     }
     return FSB_OK;

@@ -21,6 +21,20 @@ struct Cursor
     uint64_t pos;
     uint64_t size;
 
+    // The same result found with memchr: the line ends at the next LF; a CR right in front of it belongs to the line end.
+    // A CR anywhere else in the line would end the line for SkipLine: such lines take the byte-wise path.
+    uint32_t skip_line_fast()
+    {
+        if (pos >= size) return 0;
+        const uint8_t* p = mem + pos;
+        const uint64_t left = size - pos;
+        const uint8_t* lf = (const uint8_t*)std::memchr(p, '\n', (size_t)left);
+        const uint64_t span = lf ? (uint64_t)(lf - p) : left;          // bytes in front of the LF (or to the end of the chunk)
+        const uint8_t* cr = span ? (const uint8_t*)std::memchr(p, '\r', (size_t)span) : nullptr;
+        if (cr && !(lf && cr + 1 == lf)) return skip_line();           // a lone CR inside: SkipLine's rule
+        pos += span + (lf ? 1 : 0);
+        return (uint32_t)(cr ? span - 1 : span);
+    }
     // SkipLine (FastqParser.cpp:46-68): returns the line length without the line end
     uint32_t skip_line()
     {
@@ -65,6 +79,13 @@ extern "C" int fsh_parse_chunk(const uint8_t* text, uint64_t size, int keep_head
                                int quality_offset, int quality_method,
                                fsb_record* records, uint64_t capacity, fsh_parse_stats* stats)
 {
+    return fsh_parse_chunk_ex(text, size, keep_headers, keep_comments, quality_offset, quality_method, 1, records, capacity, stats);
+}
+
+extern "C" int fsh_parse_chunk_ex(const uint8_t* text, uint64_t size, int keep_headers, int keep_comments,
+                                  int quality_offset, int quality_method, int validate_bytes,
+                                  fsb_record* records, uint64_t capacity, fsh_parse_stats* stats)
+{
     fsh_parse_stats st;
     std::memset(&st, 0, sizeof(st));
     st.min_seq_len = 0xFFFFFFFFu;
@@ -76,14 +97,14 @@ extern "C" int fsh_parse_chunk(const uint8_t* text, uint64_t size, int keep_head
     while (c.pos < size)                                           // FastqParser.cpp:120
     {
         const uint64_t title = c.pos;
-        const uint32_t titleLen = c.skip_line();
+        const uint32_t titleLen = c.skip_line_fast();
         if (titleLen == 0 || text[title] != '@') { st.stop_reason = FSH_STOP_BAD_TITLE; break; }    // :125
         const uint64_t seq = c.pos;
-        const uint32_t seqLen = c.skip_line();
-        const uint32_t plen = c.skip_line();
+        const uint32_t seqLen = c.skip_line_fast();
+        const uint32_t plen = c.skip_line_fast();
         if ((uint16_t)plen == 0) { st.stop_reason = FSH_STOP_EMPTY_PLUS; break; }                   // :132-134 (uint16 plen)
         const uint64_t qua = c.pos;
-        const uint32_t qlen = c.skip_line();
+        const uint32_t qlen = c.skip_line_fast();
         if ((uint16_t)qlen != seqLen) { st.stop_reason = FSH_STOP_LEN_MISMATCH; break; }            // :137-139 (uint16 qlen)
         if (n >= capacity) { st.stop_reason = FSH_STOP_CAPACITY; break; }
 
@@ -99,7 +120,7 @@ extern "C" int fsh_parse_chunk(const uint8_t* text, uint64_t size, int keep_head
         }
 
         bool ok = seqLen >= 1 && seqLen <= 255 && headLen <= 255;
-        if (ok)
+        if (ok && validate_bytes)
         {
             for (uint32_t i = 0; i < seqLen; ++i) ok &= is_dna(text[seq + i]);
             if (range_checked)

@@ -49,6 +49,14 @@ int fsh_parse_chunk(const uint8_t* text, uint64_t size, int keep_headers, int ke
                     int quality_offset, int quality_method,
                     fsb_record* records, uint64_t capacity, fsh_parse_stats* stats);
 
+/* The same with a switch for the byte-level contract check (symbols, quality range, 7-bit titles): a caller that hands the
+ * table to the device path may leave that check to the library (FSB_OPT_VALIDATE, on by default) and pass validate_bytes = 0;
+ * lengths are always checked.  Lines are found with memchr (LF files and CRLF files at memory speed; a line holding a lone
+ * CR falls back to the byte-wise rule of SkipLine). */
+int fsh_parse_chunk_ex(const uint8_t* text, uint64_t size, int keep_headers, int keep_comments,
+                       int quality_offset, int quality_method, int validate_bytes,
+                       fsb_record* records, uint64_t capacity, fsh_parse_stats* stats);
+
 /* Upper bound of the number of records in `size` bytes of FASTQ text (for sizing the table). */
 uint64_t fsh_max_records(const uint8_t* text, uint64_t size);
 
@@ -102,6 +110,15 @@ typedef struct fsh_writer fsh_writer;
 fsh_writer* fsh_writer_open(const char* prefix, const fsh_bin_config* cfg);
 /* FastqRawBlockStats::Update for the titles of one parsed chunk (mate 1, and mate 2 in PE mode): Stats.cpp:90-169 */
 int  fsh_writer_add_titles(fsh_writer* w, const uint8_t* text, const fsb_record* records, uint64_t n_records);
+/* The same title statistics gathered per chunk away from the writer (e.g. in parser threads) and merged in chunk order, like
+ * the per-chunk FastqRawBlockStats the reference merges in BinFileWriter::WriteNextBlock (Stats.cpp:205-236).  A part whose
+ * records disagree on whether a field is numeric (fsh_titles_consistent == 0) must be added with fsh_writer_add_titles. */
+typedef struct fsh_titles fsh_titles;
+fsh_titles* fsh_titles_new(void);
+void fsh_titles_free(fsh_titles* t);
+int  fsh_titles_add(fsh_titles* t, const uint8_t* text, const fsb_record* records, uint64_t n_records);
+int  fsh_titles_consistent(const fsh_titles* t);
+int  fsh_writer_merge_titles(fsh_writer* w, const fsh_titles* t);
 int  fsh_writer_add_block(fsh_writer* w, const fsb_block* block);          /* WriteNextBlock */
 int  fsh_writer_close(fsh_writer* w);                                      /* FinishCompress; frees w */
 const char* fsh_last_error(void);

@@ -106,6 +106,7 @@ struct Chunk
     uint8_t* text[2] = {nullptr, nullptr};
     uint64_t size[2] = {0, 0};
     std::vector<fsb_record> rec[2];
+    fsh_titles* titles = nullptr;                 // header-field statistics of the chunk's titles (both mates), gathered by the parser thread
     bool bad = false;
     std::string err;
 };
@@ -198,8 +199,9 @@ int main(int argc, const char** argv)
                 {
                     c->rec[m].resize(fsh_max_records(c->text[m], c->size[m]));
                     fsh_parse_stats st;
-                    const int rc = fsh_parse_chunk(c->text[m], c->size[m], a.cfg.params.reads_have_headers, a.cfg.keep_comments, a.cfg.params.quality_offset,
-                                                   a.cfg.params.quality_method, c->rec[m].data(), c->rec[m].size(), &st);
+                    // symbols, quality range and title characters are checked on the device (FSB_OPT_VALIDATE): the parser only finds the lines
+                    const int rc = fsh_parse_chunk_ex(c->text[m], c->size[m], a.cfg.params.reads_have_headers, a.cfg.keep_comments, a.cfg.params.quality_offset,
+                                                      a.cfg.params.quality_method, 0, c->rec[m].data(), c->rec[m].size(), &st);
                     c->rec[m].resize(st.n_records);
                     if (st.stop_reason == FSH_STOP_CAPACITY) { c->bad = true; c->err = "chunk " + std::to_string(c->idx) + ": record table too small (internal error)"; }
                     else if (rc != FSB_OK) { c->bad = true; c->err = "chunk " + std::to_string(c->idx) + ": " + std::to_string(st.invalid_records) + " record(s) outside the input contract (symbols ACGTN, length <= 255, quality range)"; }
@@ -208,6 +210,12 @@ int main(int argc, const char** argv)
                 {   // the reference stops at the shorter of the two (FastqParser.cpp:527)
                     const size_t n = std::min(c->rec[0].size(), c->rec[1].size());
                     c->rec[0].resize(n); c->rec[1].resize(n);
+                }
+                if (a.cfg.params.reads_have_headers && !c->bad)
+                {   // FastqRawBlockStats of the chunk (Stats.cpp:90-169), merged into the file's statistics in chunk order by the writer turn
+                    if (c->titles) fsh_titles_free(c->titles);
+                    c->titles = fsh_titles_new();
+                    for (int m = 0; m < (pe ? 2 : 1); ++m) fsh_titles_add(c->titles, c->text[m], c->rec[m].data(), c->rec[m].size());
                 }
                 std::lock_guard<std::mutex> l(P.mu);
                 P.parsed[c->idx] = c;
@@ -264,8 +272,12 @@ int main(int argc, const char** argv)
                     int rc = FSB_OK;
                     if (n)
                     {
-                        rc = fsh_writer_add_titles(writer, c->text[0], c->rec[0].data(), n);
-                        if (rc == FSB_OK && pe) rc = fsh_writer_add_titles(writer, c->text[1], c->rec[1].data(), n);
+                        if (c->titles && fsh_titles_consistent(c->titles)) rc = fsh_writer_merge_titles(writer, c->titles);
+                        else
+                        {   // statistics that depend on the record order: record by record, as the reference's single-thread loop does
+                            rc = fsh_writer_add_titles(writer, c->text[0], c->rec[0].data(), n);
+                            if (rc == FSB_OK && pe) rc = fsh_writer_add_titles(writer, c->text[1], c->rec[1].data(), n);
+                        }
                         if (rc == FSB_OK) rc = fsh_writer_add_block(writer, &out[slot[q]]);
                     }
                     if (rc != FSB_OK) { P.fail(std::string("writing chunk ") + std::to_string(idx) + ": " + fsh_last_error()); stop = true; break; }
@@ -285,7 +297,7 @@ int main(int argc, const char** argv)
     for (auto& t : t_gpu) t.join();
     fsh_reader_close(reader);
     const int wrc = fsh_writer_close(writer);
-    for (Chunk& c : chunks) for (uint8_t* p : c.text) fsb_host_free(p);
+    for (Chunk& c : chunks) { for (uint8_t* p : c.text) fsb_host_free(p); if (c.titles) fsh_titles_free(c.titles); }
     if (P.failed) { std::fprintf(stderr, "Error: %s\n", P.error.c_str()); return -1; }
     if (wrc != FSB_OK) { std::fprintf(stderr, "Error: %s\n", fsh_last_error()); return -1; }
     if (a.verbose)

@@ -65,6 +65,32 @@ __device__ __forceinline__ void tile_range(const PlaceArgs& a, int s, uint64_t i
     else b1 = 8ull * a.BO.B[s][*a.nb_ptr];
 }
 
+// ---- TMA bulk copies with mbarrier completion (sm_90+): one instruction moves a whole slot -------------------------------
+#ifndef FSB_K4_BULK
+#define FSB_K4_BULK 1
+#endif
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one arrival that also announces `bytes` of asynchronous copies to come
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 #ifndef FSB_K4_TILE
 #define FSB_K4_TILE 32
 #endif
@@ -254,6 +280,12 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
     extern __shared__ uint4 place_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(place_smem);
     __shared__ WritePlan wplans[2][4];
+#if FSB_K4_BULK
+    __shared__ uint64_t slots_ready[2];          // one mbarrier per slot buffer: completes when all slots of a tile have landed
+    if (threadIdx.x == 0) { mbar_init(&slots_ready[0], 1); mbar_init(&slots_ready[1], 1); mbar_init_fence(); }
+    __syncthreads();
+    uint32_t ready_parity = 0;                   // bit b: parity of the phase buffer b completes next
+#endif
     const DeviceParams& P = a.P;
     const SlotGeom& G = a.G;
     constexpr uint32_t T = kPlaceTile;
@@ -280,6 +312,24 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         }
         return r;
     };
+#if FSB_K4_BULK
+    // One bulk copy (TMA, cp.async.bulk) per slot: lane q of warp (q mod 4) asks for the slot of the tile's record q; the copies
+    // report to the buffer's mbarrier, on which one thread has announced the tile's bytes.
+    auto gather = [&](uint64_t tile, const TileRegs& r, uint32_t buf)
+    {
+        if (tile < tile_end)
+        {
+            const uint32_t ntile = (uint32_t)min((uint64_t)T, n - tile * T);
+            const uint32_t bytes = npieces * 16u;
+            if (tid == 0) mbar_arrive_expect_tx(&slots_ready[buf], ntile * bytes);
+            if (lane < ntile && (lane & (kPlaceRoles - 1u)) == role)
+            {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + pl.off_slots + (size_t)buf * pl.slot_bytes) + lane * pl.slot_stride * 4u;
+                bulk_copy_g2s(dst, a.slots + (uint64_t)card_rec(r.card) * G.words, bytes, &slots_ready[buf]);
+            }
+        }
+    };
+#else
     // warp w fetches the slots of records w, w + 4, .. of the tile: lane p copies 16-byte piece p, p + 32, ..
     auto gather = [&](uint64_t tile, const TileRegs& r, uint32_t buf)
     {
@@ -307,6 +357,7 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         cp_async_commit();
     };
 
+#endif
     {   // the staging starts out zero; afterwards write_out clears what it reads
         uint4* z = reinterpret_cast<uint4*>(smem + pl.off_staging[0]);
         for (uint32_t j = tid; j < (pl.staging_bytes >> 4); j += blockDim.x) z[j] = make_uint4(0, 0, 0, 0);
@@ -345,7 +396,12 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
                 q.qa_bits = lenA * P.qua_bits;
             }
         }
+#if FSB_K4_BULK
+        mbar_wait(&slots_ready[buf], (ready_parity >> buf) & 1u);      // this tile's slots have arrived (the next tile's may still travel)
+        ready_parity ^= 1u << buf;
+#else
         cp_async_wait_group1();                                        // this tile's slots have arrived (the next tile's may still travel)
+#endif
         __syncthreads();
 
         // ---- 2. every (record, segment) to its bit phase ---------------------------------------------------------------------
@@ -372,7 +428,9 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         // ORed into the staging before every warp has passed that barrier, i.e. has finished writing this tile out
         cur = nxt; nxt = nn; buf ^= 1u;
     }
+#if !FSB_K4_BULK
     cp_async_wait_all();
+#endif
 }
 
 } // namespace fsb

@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* _
 }
 
 // offsets: exclusive scan of counts (same layout).  The 64-bit values are the records' cards (core.cuh).
-__global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __restrict__ keys_in, const unsigned long long* __restrict__ vals_in,
+// (launch bound of 4 blocks per SM: the kernel lives on scattered stores in flight, not on registers)
+__global__ void __launch_bounds__(kSortThreads, 4) sort_scatter(const uint32_t* __restrict__ keys_in, const unsigned long long* __restrict__ vals_in,
                                                               const SortTile* __restrict__ tiles, int shift, uint32_t mask, uint32_t radix,
                                                               const uint32_t* __restrict__ offsets, uint32_t* __restrict__ keys_out,
                                                               unsigned long long* __restrict__ vals_out)

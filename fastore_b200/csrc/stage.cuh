@@ -90,35 +90,40 @@ __global__ void __launch_bounds__(256) stage_stats_kernel(BatchView B, DevicePar
 // parser applies (csrc/host/fastq_parser.cpp).  It is a streaming pass over the staged text with 16-byte loads
 // (a half warp per mate: lane j checks the j-th aligned 16-byte piece of the sequence, of the quality and of the
 // title), part of fsb_stage, not of the timed fsb_run path.
-__device__ __forceinline__ uint32_t bytes_in_range_mask(int32_t lo, int32_t hi, int32_t word_base)     // 0xFF for every byte of the word whose offset is in [lo, hi)
+// 0xFF for every byte of a 4-byte word whose offset word_base + b lies in [lo, hi)
+__device__ __forceinline__ uint32_t bytes_in_range_mask(int32_t lo, int32_t hi, int32_t word_base)
 {
-    uint32_t m = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) if (word_base + b >= lo && word_base + b < hi) m |= 0xFFu << (8 * b);
-    return m;
+    const int32_t a = min(max(lo - word_base, 0), 4), b = min(max(hi - word_base, 0), 4);      // bytes [a, b) of the word
+    uint32_t ma, mb;                                                                          // shl.b32 clamps counts above 31 (result 0)
+    asm("shl.b32 %0, %1, %2;" : "=r"(ma) : "r"(0xFFFFFFFFu), "r"(8u * (uint32_t)a));
+    asm("shl.b32 %0, %1, %2;" : "=r"(mb) : "r"(0xFFFFFFFFu), "r"(8u * (uint32_t)b));
+    return ma & ~mb;
 }
+// All four bytes at once.  A valid base is one of A 0x41, C 0x43, G 0x47, T 0x54, N 0x4E: bits 7..5 are 010, and with
+// c = bits 3..1 (the code K1's bit planes are built from: A 000, C 001, T 010, G 011, N 111; 100, 101, 110 do not
+// occur) bit 4 is set for T only and bit 0 is clear for T and N only.  Bit k of every byte is looked at in place
+// (w >> k keeps it at bit 0 of the byte; the other bits of the byte are masked off at the end).
 __device__ __forceinline__ bool dna_word_ok(uint32_t w, uint32_t m)
 {
-    // valid codes ^ 0x40: A 0x01, C 0x03, G 0x07, N 0x0E, T 0x14 -- members of a 32-bit set; anything >= 32 shifts the set out (shr clamps)
-    constexpr uint32_t kSet = (1u << 0x01) | (1u << 0x03) | (1u << 0x07) | (1u << 0x0E) | (1u << 0x14);
-    const uint32_t v = ((w ^ 0x40404040u) & m) | (0x01010101u & ~m);
-    uint32_t acc = 1;
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-    {
-        uint32_t r;
-        asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(kSet), "r"((v >> (8 * b)) & 0xFFu));
-        acc &= r;
-    }
-    return (acc & 1u) != 0;
+    w = (w & m) | (0x41414141u & ~m);                                 // bytes outside the span count as 'A'
+    const uint32_t s1 = w >> 1, s2 = w >> 2, s3 = w >> 3, s4 = w >> 4, s5 = w >> 5;
+    const uint32_t isT = ~s3 & s2 & ~s1, isN = s3 & s2 & s1;
+    const uint32_t bad_code = s3 & ~(s2 & s1);
+    const uint32_t bad_b4 = s4 ^ isT, bad_b0 = w ^ ~(isT | isN);
+    const uint32_t low = (bad_code | bad_b4 | bad_b0) & 0x01010101u;
+    const uint32_t high = (s5 ^ 0x02020202u) & 0x07070707u;
+    return (low | high) == 0;
 }
-__device__ __forceinline__ bool qua_word_ok(uint32_t w, uint32_t m, uint32_t off, uint32_t bad_bits)
+// q - offset in [0, 64) for the 6- and 3-bit modes (need_range), q >= offset for the 1-bit mode; off4 = offset * 0x01010101, offset <= 127.
+// Per byte t = (q | 128) - offset never borrows from its neighbour.  For q < 128 that is q - offset + 128: in range <=> bit 7 set and
+// bit 6 clear; for q >= 128 it is q - offset itself: in range <=> bits 7 and 6 clear.
+__device__ __forceinline__ bool qua_word_ok(uint32_t w, uint32_t m, uint32_t off4, bool need_range)
 {
-    const uint32_t v = (w & m) | ((off * 0x01010101u) & ~m);
-    uint32_t acc = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc |= ((v >> (8 * b)) & 0xFFu) - off;
-    return (acc & bad_bits) == 0;
+    w = (w & m) | (off4 & ~m);                                        // bytes outside the span count as quality 0
+    const uint32_t t = (w | 0x80808080u) - off4;
+    const uint32_t h = w & 0x80808080u;
+    const uint32_t bad = need_range ? ((t ^ ~h) | (t << 1)) : (~t & ~w);
+    return (bad & 0x80808080u) == 0;
 }
 
 __global__ void __launch_bounds__(256) validate_text_kernel(BatchView B, DeviceParams P, const uint64_t* __restrict__ text_size0,
@@ -126,7 +131,8 @@ __global__ void __launch_bounds__(256) validate_text_kernel(BatchView B, DeviceP
 {
     const uint32_t half = threadIdx.x >> 4, l16 = threadIdx.x & 15u;                  // 16 half warps per block
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
-    const uint32_t qua_bad = P.qua_bits == 1 ? 0x80000000u : 0xFFFFFFC0u;              // 1-bit mode: only q >= offset (the threshold compare takes any value)
+    const bool need_range = P.qua_bits != 1;                                            // 1-bit mode: only q >= offset (the threshold compare takes any value)
+    const uint32_t off4 = (P.qua_offset & 0x7Fu) * 0x01010101u;
     for (uint64_t g = (uint64_t)blockIdx.x * 16u + half; g < n_mates; g += (uint64_t)gridDim.x * 16u)
     {
         const uint64_t i = P.paired ? (g >> 1) : g;
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(256) validate_text_kernel(BatchView B, DeviceP
                     const uint32_t msk = bytes_in_range_mask(lo, hi, piece * 16 + 4 * j);
                     if (msk == 0) continue;
                     if (k == 0) ok = ok && dna_word_ok(w[j], msk);
-                    else if (k == 1) ok = ok && qua_word_ok(w[j], msk, P.qua_offset, qua_bad);
+                    else if (k == 1) ok = ok && qua_word_ok(w[j], msk, off4, need_range);
                     else ok = ok && ((w[j] & msk & 0x80808080u) == 0);
                 }
             }

@@ -74,8 +74,9 @@ def make_config(flags: dict) -> N.FshBinConfig:
     return cfg
 
 
-def host_chain(files, out_prefix: Path, flags: dict, producer):
-    """reader -> parser -> producer(params, chunk) -> writer, chunk by chunk, like the -t1 loop of BinModule.cpp:124-167."""
+def host_chain(files, out_prefix: Path, flags: dict, producer, merge_titles: bool = False):
+    """reader -> parser -> producer(params, chunk) -> writer, chunk by chunk, like the -t1 loop of BinModule.cpp:124-167.
+    merge_titles: gather the title statistics per chunk (fsh_titles) and merge them, the way the CLI's parser threads do."""
     lib = N.host_lib()
     cfg = make_config(flags)
     paired = bool(flags.get("paired"))
@@ -103,9 +104,18 @@ def host_chain(files, out_prefix: Path, flags: dict, producer):
             continue
         chunk = N.make_chunk(t1, r1, t2, r2)
         blk, keep = producer(cfg.params, chunk)
-        assert lib.fsh_writer_add_titles(wr, N.np_ptr(t1), N.np_ptr(r1), len(r1)) == 0
-        if paired:
-            assert lib.fsh_writer_add_titles(wr, N.np_ptr(t2), N.np_ptr(r2), len(r2)) == 0
+        if merge_titles:
+            tt = lib.fsh_titles_new()
+            assert lib.fsh_titles_add(tt, N.np_ptr(t1), N.np_ptr(r1), len(r1)) == 0
+            if paired:
+                assert lib.fsh_titles_add(tt, N.np_ptr(t2), N.np_ptr(r2), len(r2)) == 0
+            assert lib.fsh_titles_consistent(tt) == 1
+            assert lib.fsh_writer_merge_titles(wr, tt) == 0, lib.fsh_last_error()
+            lib.fsh_titles_free(tt)
+        else:
+            assert lib.fsh_writer_add_titles(wr, N.np_ptr(t1), N.np_ptr(r1), len(r1)) == 0
+            if paired:
+                assert lib.fsh_writer_add_titles(wr, N.np_ptr(t2), N.np_ptr(r2), len(r2)) == 0
         assert lib.fsh_writer_add_block(wr, C.byref(blk)) == 0, lib.fsh_last_error()
         del keep
     lib.fsh_reader_close(rd)

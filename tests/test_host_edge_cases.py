@@ -49,3 +49,71 @@ def test_pe_chunks_stay_paired_when_the_cut_points_differ(tmp_path):
     want = sorted((a[1], a[2], b[1], b[2]) for a, b in zip(BF.fastq_records(files[0]), recs2))
     got = sorted((a[1], a[2], b[1], b[2]) for a, b in zip(BF.fastq_records(outs[0]), BF.fastq_records(outs[1])))
     assert got == want
+
+
+def _parse(text, validate, **kw):
+    lib = N.host_lib()
+    cap = int(lib.fsh_max_records(N.np_ptr(text), text.size))
+    recs = np.zeros(cap, dtype=N.RECORD_DTYPE)
+    st = N.FshParseStats()
+    rc = lib.fsh_parse_chunk_ex(N.np_ptr(text), text.size, int(kw.get("keep_headers", True)), int(kw.get("keep_comments", True)), 33, 0, validate,
+                                N.np_ptr(recs), cap, C.byref(st))
+    return rc, recs[: st.n_records].copy(), st
+
+
+def test_memchr_line_scanner_follows_skipline():
+    """fsh_parse_chunk_ex finds line ends with memchr; it has to give what SkipLine (FastqParser.cpp:46-68) gives byte by byte:
+    LF, CRLF and lone-CR line ends, a CR in the middle of a line, a chunk without a final line end, a record cut short."""
+    cfg = synth.synth_config(300, 80, seed=41, header_comments=True)
+    t1, _, r1, _ = synth.generate(cfg, threads=1)
+    raw = t1.tobytes()
+    lines = raw.split(b"\n")
+    mixed = b""
+    for i, ln in enumerate(lines[:-1]):                       # every record with a different kind of line end
+        mixed += ln + (b"\n", b"\r\n", b"\r")[(i // 4) % 3]
+    variants = {"lf": raw, "crlf": raw.replace(b"\n", b"\r\n"), "cr": raw.replace(b"\n", b"\r"), "mixed": mixed, "no_final_eol": raw[:-1],
+                "cut_short": raw[: len(raw) // 2], "cr_inside_title": raw.replace(b" len=", b"\rlen=", 3)}
+    for name, txt in variants.items():
+        text = np.frombuffer(txt, dtype=np.uint8).copy()
+        rc0, a, st0 = _parse(text, 1)
+        # the byte-wise reference of this test: SkipLine restated in Python
+        pos, want = 0, []
+        def skip():
+            nonlocal pos
+            n0 = pos
+            while pos < len(txt) and txt[pos] not in (10, 13):
+                pos += 1
+            ln = pos - n0
+            if pos < len(txt):
+                pos += 2 if (txt[pos] == 13 and pos + 1 < len(txt) and txt[pos + 1] == 10) else 1
+            return n0, ln
+        while pos < len(txt):
+            h, hl = skip()
+            if hl == 0 or txt[h] != ord("@"):
+                break
+            s_, sl = skip()
+            _, pl = skip()
+            if pl == 0:
+                break
+            q, ql = skip()
+            if ql != sl:
+                break
+            want.append((h, s_, q, sl, hl))
+        got = [(int(r["head_off"]), int(r["seq_off"]), int(r["qua_off"]), int(r["seq_len"]), int(r["head_len"])) for r in a]
+        assert got == want, name
+        rc1, b, st1 = _parse(text, 0)
+        assert np.array_equal(a, b) and st0.consumed_bytes == st1.consumed_bytes and st0.stop_reason == st1.stop_reason, name
+    # the byte-level contract check is what validate_bytes switches
+    bad = np.frombuffer(raw.replace(b"A", b"a", 1), dtype=np.uint8).copy()
+    assert _parse(bad, 1)[0] == N.FSB_ERR_INPUT and _parse(bad, 0)[0] == N.FSB_OK
+
+
+@pytest.mark.skipif(not BF.have_ref_tools(), reason="oracle/_ref tools not built (no /root/reference here)")
+def test_title_statistics_merged_per_chunk_equal_the_reference(tmp_path):
+    """The CLI's parser threads gather the header-field statistics per chunk (fsh_titles) and the writer merges them in chunk
+    order; the footer must be the one the reference writes from its record-by-record statistics."""
+    files = BF.write_fastq(tmp_path, "in", 16000, 100, True, 250, header_comments=True)
+    flags = dict(paired=True, b=2)
+    BF.run_reference_bin(files, tmp_path / "ref", flags)
+    BF.host_chain(files, tmp_path / "ours", flags, BF.oracle_producer, merge_titles=True)
+    BF.assert_bin_files_equal(tmp_path / "ours", tmp_path / "ref", True)
