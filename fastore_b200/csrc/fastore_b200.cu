@@ -115,7 +115,7 @@ struct Batch
     DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats, d_chunk_sums, d_sort_tiles;
     PinBuf h_stage_stats, h_chunk_sums;
     DevBuf d_out[4], d_desc, d_summary, d_sig, d_info;
-    cudaEvent_t ev_h2d = nullptr, ev_run = nullptr, ev_d2h = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_chk = nullptr, ev_run = nullptr, ev_d2h = nullptr;
 };
 
 // Pinned host memory holding the results of one (sub-)batch until the next call on the context.
@@ -312,8 +312,10 @@ HostOut* host_out(fsb_ctx* c, size_t g)
 // check of the record tables (offsets inside the chunk, lengths, PE mate-length equality - the
 // things the reference only ASSERTs: FastqRecord.h:87, FastqParser.cpp:130) together with the batch
 // statistics that size the buffers, and the copy of those statistics back.  The batch's input
-// buffers must not be in use.  `split` = sub-batches of whole chunks the kernels will run as.
-int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, uint32_t split, bool profile = false)
+// buffers must not be in use.  `split` = sub-batches of whole chunks the kernels will run as.  The copies go to `st`, the
+// check kernels and the copy of their results to `st_check` (which then waits for the copies; b.ev_chk fires when the results
+// are on the host): the pipeline keeps its copy stream free of kernels, so that the next sub-batch's text follows at once.
+int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, cudaStream_t st_check, uint32_t split, bool profile = false)
 {
     b.staged = false; b.ran = false;
     const int nfiles = c->dp.paired ? 2 : 1;
@@ -425,6 +427,12 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
         CUDA_TRY(c, cudaMemcpyAsync(b.d_sort_tiles.p, b.tiles_host.data(), b.tiles_host.size() * sizeof(SortTile), cudaMemcpyHostToDevice, st));
     h2d += b.tiles_host.size() * sizeof(SortTile);
 
+    if (st_check != st)
+    {
+        CUDA_TRY(c, cudaEventRecord(b.ev_h2d, st));
+        CUDA_TRY(c, cudaStreamWaitEvent(st_check, b.ev_h2d, 0));
+        st = st_check;                                               // everything below: the check stream
+    }
     CUDA_TRY(c, b.d_stage_stats.ensure(sizeof(StageStats)));
     CUDA_TRY(c, b.h_stage_stats.ensure(2 * sizeof(StageStats)));
     CUDA_TRY(c, b.d_chunk_sums.ensure((size_t)n_chunks * 2 * sizeof(uint64_t)));
@@ -458,6 +466,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     }
     CUDA_TRY(c, cudaMemcpyAsync(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaMemcpyAsync(b.h_chunk_sums.p, b.d_chunk_sums.p, (size_t)n_chunks * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaEventRecord(b.ev_chk, st));
     b.h2d_bytes = h2d;
     c->stats.h2d_bytes += h2d;
     return FSB_OK;
@@ -905,7 +914,8 @@ extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fs
     if (const char* e = std::getenv("FSB_K4_R")) c->k4_tiles_per_block = (uint32_t)std::max(0, std::atoi(e));
     for (Batch& b : c->batch)
     {
-        if (cudaEventCreateWithFlags(&b.ev_h2d, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b.ev_run, cudaEventDisableTiming) != cudaSuccess ||
+        if (cudaEventCreateWithFlags(&b.ev_h2d, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b.ev_chk, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b.ev_run, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&b.ev_d2h, cudaEventDisableTiming) != cudaSuccess)
         {
             fsb_destroy(c);
@@ -932,6 +942,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
         for (DevBuf* d : dev) d->release();
         b.h_stage_stats.release(); b.h_chunk_sums.release();
         if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
+        if (b.ev_chk) cudaEventDestroy(b.ev_chk);
         if (b.ev_run) cudaEventDestroy(b.ev_run);
         if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);
     }
@@ -1024,7 +1035,7 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // nothing may still be using the batch's buffers
     Batch& b = c->batch[0];
-    int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream, c->run_split, c->profile);
+    int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream, c->stream, c->run_split, c->profile);
     if (rc != FSB_OK) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // pageable user buffers must outlive the copies; the statistics are back
     return stage_complete(c, b);
@@ -1061,7 +1072,7 @@ extern "C" int fsb_fetch(fsb_ctx* c, fsb_block* blocks, uint32_t n_blocks)
 // The chunk list is cut into sub-batches of at least sub_batch_records records (whole chunks) which
 // run as a pipeline over the two device buffer sets:
 //     s_h2d   : copy in g+1 ......... (waits until the kernels of g-1 have released that buffer set)
-//     stream  : kernels of g ........ (wait for copy in g, and for copy out g-2 to release the result buffers)
+//     stream  : input check of g (after its copy), kernels of g (the host has waited for copy out g-2 to release the result buffers)
 //     s_d2h   : copy out g-1
 // The host only blocks on small things: the staging statistics of a sub-batch (they size the
 // buffers and carry the input validation) and its chunk summary (the stream sizes).
@@ -1111,15 +1122,13 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         return FSB_OK;
     };
 
-    rc = stage_enqueue(c, c->batch[0], chunks + first[0], first[1] - first[0], c->s_h2d, 1);
-    if (rc == FSB_OK) { cudaError_t e = cudaEventRecord(c->batch[0].ev_h2d, c->s_h2d); if (e != cudaSuccess) rc = fail(c, FSB_ERR_CUDA, cudaGetErrorString(e)); }
+    rc = stage_enqueue(c, c->batch[0], chunks + first[0], first[1] - first[0], c->s_h2d, c->stream, 1);
     for (uint32_t g = 0; g < G && rc == FSB_OK; ++g)
     {
         Batch& b = c->batch[g & 1];
-        if (cudaEventSynchronize(b.ev_h2d) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy to the device failed"); break; }
+        if (cudaEventSynchronize(b.ev_chk) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy to the device failed"); break; }    // text on the device, check results on the host
         if (g >= 2 && cudaEventSynchronize(b.ev_d2h) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy from the device failed"); break; }   // result buffers of g-2 are free
         if ((rc = stage_complete(c, b)) != FSB_OK) break;
-        if (cudaStreamWaitEvent(c->stream, b.ev_h2d, 0) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
         if ((rc = run_enqueue(c, b, false)) != FSB_OK) break;
         if ((rc = summary_enqueue(c, b, *c->host[g], c->stream)) != FSB_OK) break;
         if (cudaEventRecord(b.ev_run, c->stream) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
@@ -1128,8 +1137,7 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         if (g + 1 < G)
         {
             Batch& nx = c->batch[(g + 1) & 1];
-            if ((rc = stage_enqueue(c, nx, chunks + first[g + 1], first[g + 2] - first[g + 1], c->s_h2d, 1)) != FSB_OK) break;
-            if (cudaEventRecord(nx.ev_h2d, c->s_h2d) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
+            if ((rc = stage_enqueue(c, nx, chunks + first[g + 1], first[g + 2] - first[g + 1], c->s_h2d, c->stream, 1)) != FSB_OK) break;
         }
     }
     if (rc == FSB_OK) rc = finish(G - 1);

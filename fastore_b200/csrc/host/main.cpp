@@ -151,15 +151,9 @@ int main(int argc, const char** argv)
     Pipeline P;
     const int nbuf = NWK * K + a.parsers + 1;
     std::vector<Chunk> chunks((size_t)nbuf);
-    for (Chunk& c : chunks)
-    {
-        for (int m = 0; m < (pe ? 2 : 1); ++m)
-        {
-            c.text[m] = (uint8_t*)fsb_host_alloc(a.cfg.fastq_block_size + 64);
-            if (!c.text[m]) { std::fprintf(stderr, "Error: cannot allocate pinned chunk buffers\n"); return -1; }
-        }
-        P.pool.push_back(&c);
-    }
+    // the chunk buffers (pinned host memory) are allocated when the reader first uses them: a short input pins a few, a long one
+    // all of them, and pinning -- about a second per few GB -- overlaps with the parsers and the GPU workers
+    for (Chunk& c : chunks) P.pool.insert(P.pool.begin(), &c);
 
     // ---- reader: one chunk after the other, exactly the reference's cuts ------------------------------------
     std::thread t_read([&] {
@@ -170,8 +164,12 @@ int main(int argc, const char** argv)
                 std::unique_lock<std::mutex> l(P.mu);
                 P.cv.wait(l, [&] { return !P.pool.empty() || P.failed; });
                 if (P.failed) break;
-                c = P.pool.back(); P.pool.pop_back();
+                c = P.pool.back(); P.pool.pop_back();               // last in, first out: buffers that exist are reused before new ones are pinned
             }
+            bool have = true;
+            for (int m = 0; m < (pe ? 2 : 1) && have; ++m)
+                if (!c->text[m]) { c->text[m] = (uint8_t*)fsb_host_alloc(a.cfg.fastq_block_size + 64); have = c->text[m] != nullptr; }
+            if (!have) { P.fail("cannot allocate pinned chunk buffers"); break; }
             const int rc = fsh_reader_next(reader, c->text[0], &c->size[0], c->text[1], &c->size[1]);
             std::unique_lock<std::mutex> l(P.mu);
             if (rc <= 0) { P.pool.push_back(c); P.read_done = true; if (rc < 0 && !P.failed) { P.failed = true; P.error = "read error"; } P.cv.notify_all(); break; }
@@ -229,6 +227,8 @@ int main(int argc, const char** argv)
         t_gpu.emplace_back([&, w] {
             fsb_ctx* ctx = nullptr;
             if (fsb_create(&a.cfg.params, w % G, nullptr, &ctx) != FSB_OK) { P.fail(std::string("GPU ") + std::to_string(w % G) + ": " + fsb_last_error(nullptr)); return; }
+            auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+            if (a.verbose) std::fprintf(stderr, "[%.2f s] worker %d: context on GPU %d ready\n", since(), w, w % G);
             std::vector<Chunk*> mine;
             std::vector<fsb_chunk> in;
             bool stop = false;
@@ -258,8 +258,10 @@ int main(int argc, const char** argv)
                 }
                 if (stop) break;
                 std::vector<fsb_block> out(in.size());
+                const double t_call = since();
                 if (!in.empty() && fsb_bin_chunks(ctx, in.data(), (uint32_t)in.size(), out.data()) != FSB_OK)
                 { P.fail(std::string("chunk ") + std::to_string(idx) + ": " + fsb_last_error(ctx)); break; }
+                if (a.verbose) std::fprintf(stderr, "[%.2f s] worker %d: chunks %llu.. (%zu in one call) binned in %.3f s\n", since(), w, (unsigned long long)idx, in.size(), since() - t_call);
                 for (size_t q = 0; q < mine.size() && !stop; ++q, idx += (uint64_t)NWK)
                 {
                     Chunk* c = mine[q];
@@ -293,16 +295,18 @@ int main(int argc, const char** argv)
         });
 
     t_read.join();
+    const double t_read_done = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (auto& t : t_parse) t.join();
     for (auto& t : t_gpu) t.join();
     fsh_reader_close(reader);
     const int wrc = fsh_writer_close(writer);
-    for (Chunk& c : chunks) { for (uint8_t* p : c.text) fsb_host_free(p); if (c.titles) fsh_titles_free(c.titles); }
+    for (Chunk& c : chunks) { for (uint8_t* p : c.text) if (p) fsb_host_free(p); if (c.titles) fsh_titles_free(c.titles); }
     if (P.failed) { std::fprintf(stderr, "Error: %s\n", P.error.c_str()); return -1; }
     if (wrc != FSB_OK) { std::fprintf(stderr, "Error: %s\n", fsh_last_error()); return -1; }
     if (a.verbose)
     {
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::fprintf(stderr, "\nreader finished after %.2f s", t_read_done);
         std::fprintf(stderr, "\n%llu records in %llu chunks on %d GPU(s) x %d worker(s): %.2f s, %.0f records/s\n", (unsigned long long)total_records.load(),
                      (unsigned long long)P.next_write, G, a.workers, s, total_records.load() / std::max(s, 1e-9));
     }

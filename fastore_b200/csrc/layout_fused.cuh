@@ -5,8 +5,8 @@
 // position inside its K4 tile for the four streams, the tiles' first bits, the per-record bin info --
 // plus the bin descriptors and the per-chunk summary.  The arithmetic is layout_core.cuh's scan.
 //
-// Mapping: a thread owns four consecutive sorted records -- one 16-byte vector of every array it reads or writes, so a
-// warp's accesses are fully coalesced -- and a block of 512 threads owns 2048 records.
+// Mapping: a thread owns one K4 tile (32 consecutive sorted records) and walks over it sequentially; a block
+// of 128 threads owns 4096 records.
 //   lay_reduce   every block's LayState                              -> tile_states[block]
 //   lay_scan     one block: exclusive scan over the block states      (in place; [nblocks] = the whole batch)
 //   lay_apply    thread prefix = block prefix (+) threads in front; absolute walk that writes loc / binfo / tbase,
@@ -22,11 +22,10 @@
 
 namespace fsb {
 
-constexpr uint32_t kLayThreads = 512;
-constexpr uint32_t kLayPerThread = 4;                               // a thread walks over four consecutive records: one 16-byte vector of every array
-constexpr uint32_t kLayBlock = kLayThreads * kLayPerThread;         // 2048 records per block
-constexpr uint32_t kLayTileLanes = kPlaceTile / kLayPerThread;      // threads that share a K4 tile (8 neighbouring lanes)
-static_assert(kLayPerThread == 4 && kPlaceTile % kLayPerThread == 0 && 32 % kLayTileLanes == 0, "a K4 tile is a whole group of lanes of one warp");
+constexpr uint32_t kLayThreads = 128;
+constexpr uint32_t kLayPerThread = kPlaceTile;                      // a thread walks over one K4 tile
+constexpr uint32_t kLayBlock = kLayThreads * kLayPerThread;         // 4096 records per block
+static_assert(kLayPerThread == 32, "lay_apply stores a thread's values as 16-byte vectors of four");
 
 // ---- moving a LayState between lanes ---------------------------------------------------------------------------
 constexpr int kLayWords = (int)(sizeof(LayState) / 4);
@@ -53,9 +52,7 @@ __device__ __forceinline__ LayState lay_warp_scan(LayState s)
     return s;
 }
 // Exclusive prefix of `mine` over the threads of the block (thread order = record order); `total` = the block's state.
-// THREADS / 32 entries of shared memory.
-template <uint32_t THREADS>
-__device__ __forceinline__ LayState lay_block_scan(const LayState& mine, LayState& total, LayState* sm)
+__device__ __forceinline__ LayState lay_block_scan(const LayState& mine, LayState& total, LayState* sm /* kLayThreads / 32 entries */)
 {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const LayState inc = lay_warp_scan(mine);
@@ -63,7 +60,8 @@ __device__ __forceinline__ LayState lay_block_scan(const LayState& mine, LayStat
     __syncthreads();
     LayState before = lay_identity();                               // the warps in front of this one
     total = lay_identity();
-    for (unsigned w = 0; w < THREADS / 32; ++w)
+#pragma unroll
+    for (unsigned w = 0; w < kLayThreads / 32; ++w)
     {
         if (w == warp) before = total;
         total = lay_combine(total, sm[w]);
@@ -74,87 +72,92 @@ __device__ __forceinline__ LayState lay_block_scan(const LayState& mine, LayStat
     return lay_combine(before, excl);
 }
 
-// A thread's four sorted records (fewer at the end of the batch), the key in front of them and the key behind them.
+// A thread's run of sorted records.
 struct LayRun
 {
     uint64_t i0;             // first record
-    uint32_t cnt;            // records (0 .. 4)
-    uint32_t key[4];
-    unsigned long long card[4];
-    uint32_t prev, next;     // keys of the records i0 - 1 and i0 + cnt (any value where there is none: lay_record / the walk know)
+    uint32_t cnt;            // records (0 .. 32)
 };
-__device__ __forceinline__ LayRun lay_run(uint64_t n, const SortedView& S)
+__device__ __forceinline__ LayRun lay_run(uint64_t n)
 {
     LayRun r;
-    const unsigned lane = threadIdx.x & 31;
     r.i0 = ((uint64_t)blockIdx.x * kLayThreads + threadIdx.x) * kLayPerThread;
     r.cnt = r.i0 < n ? (uint32_t)min((uint64_t)kLayPerThread, n - r.i0) : 0u;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { r.key[u] = 0; r.card[u] = 0; }
-    if (r.cnt == kLayPerThread)
+    return r;
+}
+// the state of a thread's run (keys and cards are read as 16-byte vectors: the run is 128 / 256 contiguous bytes)
+__device__ __forceinline__ LayState lay_run_state(const DeviceParams& P, const SortedView& S, const LayRun& run, uint32_t uniform_len)
+{
+    LayState st = lay_identity();
+    if (run.cnt == 0) return st;
+    uint32_t prev = run.i0 ? S.skeys[run.i0 - 1] : 0u;
+    if (run.cnt == kLayPerThread)
     {
-        const uint4 kk = *reinterpret_cast<const uint4*>(S.skeys + r.i0);
-        const ulonglong2 ca = *reinterpret_cast<const ulonglong2*>(S.cards + r.i0), cb = *reinterpret_cast<const ulonglong2*>(S.cards + r.i0 + 2);
-        r.key[0] = kk.x; r.key[1] = kk.y; r.key[2] = kk.z; r.key[3] = kk.w;
-        r.card[0] = ca.x; r.card[1] = ca.y; r.card[2] = cb.x; r.card[3] = cb.y;
+        const uint4* k4 = reinterpret_cast<const uint4*>(S.skeys + run.i0);
+        const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(S.cards + run.i0);
+#pragma unroll 2
+        for (uint32_t q = 0; q < kLayPerThread / 4; ++q)
+        {
+            const uint4 kk = k4[q];
+            const ulonglong2 ca = c2[2 * q], cb = c2[2 * q + 1];
+            const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+            const unsigned long long card[4] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                lay_push(st, lay_record(P, run.i0 + 4 * q + u == 0, key[u], prev, card[u], uniform_len));
+                prev = key[u];
+            }
+        }
     }
     else
     {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if ((uint32_t)u < r.cnt) { r.key[u] = S.skeys[r.i0 + u]; r.card[u] = S.cards[r.i0 + u]; }
-    }
-    // neighbours: from the lanes next door, from memory at the ends of the warp
-    uint32_t last = r.key[0];
-#pragma unroll
-    for (int u = 1; u < 4; ++u) if ((uint32_t)u < r.cnt) last = r.key[u];
-    r.prev = __shfl_up_sync(0xFFFFFFFFu, last, 1);
-    r.next = __shfl_down_sync(0xFFFFFFFFu, r.key[0], 1);
-    if (lane == 0) r.prev = (r.cnt && r.i0) ? S.skeys[r.i0 - 1] : 0u;
-    if (lane == 31) r.next = (r.cnt == kLayPerThread && r.i0 + kLayPerThread < n) ? S.skeys[r.i0 + kLayPerThread] : 0u;
-    return r;
-}
-__device__ __forceinline__ LayState lay_run_state(const DeviceParams& P, const LayRun& run, uint32_t uniform_len)
-{
-    LayState st = lay_identity();
-    uint32_t prev = run.prev;
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-        if ((uint32_t)u < run.cnt)
+        for (uint32_t j = 0; j < run.cnt; ++j)
         {
-            lay_push(st, lay_record(P, run.i0 + u == 0, run.key[u], prev, run.card[u], uniform_len));
-            prev = run.key[u];
+            const uint32_t key = S.skeys[run.i0 + j];
+            lay_push(st, lay_record(P, run.i0 + j == 0, key, prev, S.cards[run.i0 + j], uniform_len));
+            prev = key;
         }
+    }
     return st;
 }
 
 __global__ void __launch_bounds__(kLayThreads) lay_reduce_kernel(uint64_t n, DeviceParams P, SortedView S, uint32_t uniform_len, LayState* __restrict__ tile_states)
 {
     __shared__ LayState sm[kLayThreads / 32];
-    const LayState mine = lay_run_state(P, lay_run(n, S), uniform_len);
+    const LayState mine = lay_run_state(P, S, lay_run(n), uniform_len);
     LayState total;
-    lay_block_scan<kLayThreads>(mine, total, sm);
+    lay_block_scan(mine, total, sm);
     if (threadIdx.x == 0) tile_states[blockIdx.x] = total;
 }
 
-// one block: states[j] <- combination of states[0 .. j)  (j = 0 .. count; entry [count] is the whole batch).  Every thread takes
-// a run of consecutive states, so one block-wide scan covers any count.
-constexpr uint32_t kLayScanThreads = 512;
+// one block: states[j] <- combination of states[0 .. j)  (j = 0 .. count; entry [count] is the whole batch)
+constexpr uint32_t kLayScanThreads = 256;
 __global__ void __launch_bounds__(kLayScanThreads) lay_scan_kernel(LayState* __restrict__ states, uint32_t count)
 {
     __shared__ LayState sm[kLayScanThreads / 32];
-    const uint32_t per = (count + kLayScanThreads - 1) / kLayScanThreads;
-    const uint32_t j0 = min(count, threadIdx.x * per), j1 = min(count, j0 + per);
-    LayState mine = lay_identity();
-    for (uint32_t j = j0; j < j1; ++j) mine = lay_combine(mine, states[j]);
-    LayState total;
-    LayState run = lay_block_scan<kLayScanThreads>(mine, total, sm);
-    for (uint32_t j = j0; j < j1; ++j)
+    __shared__ LayState carry_sm;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sm = lay_identity();
+    __syncthreads();
+    for (uint32_t base = 0; base < count; base += kLayScanThreads)
     {
-        const LayState s = states[j];
-        states[j] = run;
-        run = lay_combine(run, s);
+        const uint32_t j = base + threadIdx.x;
+        const LayState mine = j < count ? states[j] : lay_identity();
+        const LayState inc = lay_warp_scan(mine);
+        if (lane == 31) sm[warp] = inc;
+        __syncthreads();
+        LayState before = carry_sm;                                 // everything in front of this round, then the warps in front
+        for (unsigned w = 0; w < warp; ++w) before = lay_combine(before, sm[w]);
+        LayState excl = lay_shfl_up(inc, 1);
+        if (lane == 0) excl = lay_identity();
+        const LayState pre = lay_combine(before, excl);
+        if (j < count) states[j] = pre;
+        __syncthreads();
+        if (threadIdx.x == kLayScanThreads - 1) carry_sm = lay_combine(pre, mine);
+        __syncthreads();
     }
-    if (threadIdx.x == 0) states[count] = total;
+    if (threadIdx.x == 0) states[count] = carry_sm;
 }
 
 // first bin and first stream bytes of every chunk that holds records; entry [n_chunks] = bins and stream bytes of the whole batch
@@ -177,86 +180,102 @@ __global__ void __launch_bounds__(kLayThreads) lay_apply_kernel(uint64_t n, uint
                                                                 const LayState* __restrict__ tile_prefix, LayOut out)
 {
     __shared__ LayState sm[kLayThreads / 32];
-    const unsigned lane = threadIdx.x & 31;
-    const LayRun run = lay_run(n, S);
-    const LayState mine = lay_run_state(P, run, uniform_len);
+    const LayRun run = lay_run(n);
+    const LayState mine = lay_run_state(P, S, run, uniform_len);
     LayState total;
-    const LayState excl = lay_combine(tile_prefix[blockIdx.x], lay_block_scan<kLayThreads>(mine, total, sm));
+    const LayState excl = lay_combine(tile_prefix[blockIdx.x], lay_block_scan(mine, total, sm));
+    if (run.cnt == 0) return;
     LayCursor cur = lay_cursor(excl);
+    const uint64_t tile = run.i0 / kPlaceTile;                      // the thread's K4 tile
     const uint32_t key_mask = (1u << P.key_bits) - 1u;
     const bool has_head = P.has_headers != 0;
-    // ---- the walk over the thread's records -------------------------------------------------------------------------
-    uint64_t at[4][4];                                              // [record][stream]
-    uint32_t binfo[4] = {0, 0, 0, 0};
-    unsigned long long first_b0[4] = {0, 0, 0, 0};                  // first bit of a K4 tile whose first record is this thread's first record
-    uint32_t prev = run.prev;
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
+    uint32_t prev = run.i0 ? S.skeys[run.i0 - 1] : 0u;
+    unsigned long long b0[4] = {0, 0, 0, 0};                        // first bit of the tile in every stream
+    uint32_t base_bits_lo[4] = {0, 0, 0, 0};
+    uint32_t loc[4][4], binfo[4];
+    for (uint32_t q = 0; 4u * q < run.cnt; ++q)
     {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) at[u][k] = 0;
-        if ((uint32_t)u < run.cnt)
+        // the round's four keys and cards as vectors (a warp-wide scalar load here would touch 32 lines for 4 bytes each)
+        uint32_t gk[4] = {0, 0, 0, 0};
+        unsigned long long gc[4] = {0, 0, 0, 0};
+        if (4u * q + 4u <= run.cnt)
         {
-            const uint64_t i = run.i0 + u;
-            const uint32_t key = run.key[u];
-            const uint32_t next = (uint32_t)u + 1u < run.cnt ? run.key[(u + 1) & 3] : run.next;
-            const bool last_of_batch = i + 1 == n;
-            const LayRec r = lay_record(P, i == 0, key, prev, run.card[u], uniform_len);
-            lay_step(cur, r, at[u]);
-            if (r.chunk_start)
+            const uint4 kk = *reinterpret_cast<const uint4*>(S.skeys + run.i0 + 4u * q);
+            const ulonglong2 ca = *reinterpret_cast<const ulonglong2*>(S.cards + run.i0 + 4u * q), cb = *reinterpret_cast<const ulonglong2*>(S.cards + run.i0 + 4u * q + 2u);
+            gk[0] = kk.x; gk[1] = kk.y; gk[2] = kk.z; gk[3] = kk.w;
+            gc[0] = ca.x; gc[1] = ca.y; gc[2] = cb.x; gc[3] = cb.y;
+        }
+        else
+        {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (4u * q + (uint32_t)u < run.cnt) { gk[u] = S.skeys[run.i0 + 4u * q + u]; gc[u] = S.cards[run.i0 + 4u * q + u]; }
+        }
+        const uint64_t after = run.i0 + 4u * q + 4u;                  // the record behind the round
+        const uint32_t key_after = (4u * q + 4u <= run.cnt && after < n) ? S.skeys[after] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)                                   // four records per round: their values leave as one 16-byte vector per array
+        {
+            const uint32_t j = 4u * q + (uint32_t)u;
+            if (j < run.cnt)
             {
-                ChunkStart cs;
-                cs.first_bin = cur.nb - 1u;
+                const uint64_t i = run.i0 + j;
+                const uint32_t key = gk[u];
+                // the key behind this record; the last record of the batch closes its bin whatever follows
+                const uint32_t next = i + 1 >= n ? ~key : (u < 3 ? gk[(u + 1) & 3] : key_after);
+                const LayRec r = lay_record(P, i == 0, key, prev, gc[u], uniform_len);
+                uint64_t at[4];
+                lay_step(cur, r, at);
+                if (r.chunk_start)
+                {
+                    ChunkStart cs;
+                    cs.first_bin = cur.nb - 1u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) cs.off[k] = cur.ls[k] >> 3;
-                out.chunk_start[key >> P.key_bits] = cs;
-            }
-            if (u == 0)
-            {   // a tile starts at its first record, or at the first byte of the bin that record opens (bin header and all)
+                    for (int k = 0; k < 4; ++k) cs.off[k] = cur.ls[k] >> 3;
+                    out.chunk_start[key >> P.key_bits] = cs;
+                }
+                if (j == 0)
+                {   // the tile starts at its first record, or at the first byte of the bin that record opens (bin header and all)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) first_b0[k] = r.start ? cur.ls[k] : at[0][k];
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const bool has = !(k == 3 && !has_head);
+                        b0[k] = has ? (r.start ? cur.ls[k] : at[k]) : 0ull;
+                        out.pm.tbase[4 * tile + k] = b0[k];
+                        if (b0[k] & 31u) out.O.w[k][b0[k] >> 5] = 0;  // write_out ORs into the word it shares with the tile in front
+                        base_bits_lo[k] = (uint32_t)(b0[k] & 127u);   // staging_bit: bits from the 16-byte group the tile starts in
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const bool has = !(k == 3 && !has_head);
+                    loc[k][u] = has ? (uint32_t)(at[k] - b0[k]) + base_bits_lo[k] : 0u;
+                }
+                binfo[u] = (uniform_len & 0xFFu) | ((uniform_len & 0xFFu) << 8) | (r.start ? 0x10000u : 0u) | (r.nbin ? 0x20000u : 0u);
+                if (next != key) out.desc[cur.nb - 1u] = lay_descriptor(cur, key & key_mask);   // last record of its bin
+                prev = key;
             }
-            binfo[u] = (uniform_len & 0xFFu) | ((uniform_len & 0xFFu) << 8) | (r.start ? 0x10000u : 0u) | (r.nbin ? 0x20000u : 0u);
-            if (last_of_batch || next != key) out.desc[cur.nb - 1u] = lay_descriptor(cur, key & key_mask);   // last record of its bin
-            prev = key;
+        }
+        const uint64_t g = run.i0 + 4u * q;                           // first record of the group of four
+        if (4u * q + 4u <= run.cnt)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out.pm.loc[k] + g) = make_uint4(loc[k][0], loc[k][1], loc[k][2], loc[k][3]);
+            *reinterpret_cast<uint4*>(out.pm.binfo + g) = make_uint4(binfo[0], binfo[1], binfo[2], binfo[3]);
+        }
+        else
+        {
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+                if (4u * q + (uint32_t)v < run.cnt)
+                {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) out.pm.loc[k][g + v] = loc[k][v];
+                    out.pm.binfo[g + v] = binfo[v];
+                }
         }
     }
-    // ---- K4 tiles: the eight lanes of a tile take its first bit from the first of them ------------------------------
-    const uint64_t tile = run.i0 / kPlaceTile;
-    const bool leader = (lane & (kLayTileLanes - 1u)) == 0 && run.cnt != 0;
-    uint32_t loc[4][4];                                             // [stream][record]
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-        const bool has = !(k == 3 && !has_head);
-        const unsigned long long b0 = __shfl_sync(0xFFFFFFFFu, has ? first_b0[k] : 0ull, lane & ~(kLayTileLanes - 1u));
-        if (leader)
-        {
-            out.pm.tbase[4 * tile + k] = b0;
-            if (b0 & 31u) out.O.w[k][b0 >> 5] = 0;                  // write_out ORs into the word it shares with the tile in front
-        }
-        const uint32_t lo = (uint32_t)(b0 & 127u);                  // staging_bit: bits from the 16-byte group the tile starts in
-#pragma unroll
-        for (int u = 0; u < 4; ++u) loc[k][u] = has ? (uint32_t)(at[u][k] - b0) + lo : 0u;
-    }
-    if (run.cnt == kLayPerThread)
-    {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out.pm.loc[k] + run.i0) = make_uint4(loc[k][0], loc[k][1], loc[k][2], loc[k][3]);
-        *reinterpret_cast<uint4*>(out.pm.binfo + run.i0) = make_uint4(binfo[0], binfo[1], binfo[2], binfo[3]);
-    }
-    else
-    {
-#pragma unroll
-        for (int u = 0; u < 3; ++u)
-            if ((uint32_t)u < run.cnt)
-            {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) out.pm.loc[k][run.i0 + u] = loc[k][u];
-                out.pm.binfo[run.i0 + u] = binfo[u];
-            }
-    }
-    if (run.cnt && run.i0 + run.cnt == n)
+    if (run.i0 + run.cnt == n)
     {   // end of the batch: the end of the last tile, the totals
         const uint64_t tiles = (n + kPlaceTile - 1) / kPlaceTile;
         ChunkStart cs;

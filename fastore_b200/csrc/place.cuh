@@ -131,28 +131,51 @@ __device__ __forceinline__ WritePlan make_write_plan(uint64_t b0, uint64_t b1)
 }
 // Every word that is read is cleared behind the reader, so the staging is all zero again when the next tile's
 // segments are ORed into it.
-__device__ __forceinline__ void write_out(uint32_t* stg, uint32_t* stream_words, const WritePlan& w)
+//
+// The four streams of a tile differ a lot in size (quality : DNA : titles : meta is about 450 : 150 : 30 : 3 vectors at
+// 2 x 150 bp), so the vectors of all four are dealt out together: they form one line of `total` vectors, warp w takes
+// the w-th quarter of it and works through the (one or two) streams its quarter covers.  The few words at the ends of
+// a stream's range that do not fill a vector -- and may be shared with the neighbouring tile -- go to warp s for stream s.
+__device__ __forceinline__ void write_out_all(uint32_t* const (&stg)[4], const OutStreams& O, const WritePlan* __restrict__ wplan)
 {
-    if (!(w.shared & 4u)) return;
-    const uint32_t tid = threadIdx.x;
-    uint32_t* g = stream_words + w.base;
-    uint4* sv = reinterpret_cast<uint4*>(stg);
-    uint4* gv = reinterpret_cast<uint4*>(g);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t nvec[4], total = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { nvec[s] = (wplan[s].shared & 4u) ? wplan[s].ve - min(wplan[s].vs, wplan[s].ve) : 0u; total += nvec[s]; }
+    const uint32_t lo = total * warp / kPlaceRoles, hi = total * (warp + 1u) / kPlaceRoles;      // this warp's part of the line
+    uint32_t first = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+    {
+        const uint32_t a = max(lo, first), b = min(hi, first + nvec[s]);                           // the part of it that lies in stream s
+        if (a < b)
+        {
+            uint4* sv = reinterpret_cast<uint4*>(stg[s]);
+            uint4* gv = reinterpret_cast<uint4*>(O.w[s] + wplan[s].base);
+            const uint32_t shift = wplan[s].vs - first;
 #pragma unroll 1
-    for (uint32_t j = w.vs + tid; j < w.ve; j += kPlaceThreads)
-    {
-        uint4 v = sv[j];
-        sv[j] = make_uint4(0, 0, 0, 0);
-        v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
-        gv[j] = v;
+            for (uint32_t j = a + lane + shift; j < b + shift; j += 32)
+            {
+                uint4 v = sv[j];
+                sv[j] = make_uint4(0, 0, 0, 0);
+                v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
+                gv[j] = v;
+            }
+        }
+        first += nvec[s];
     }
-    if (tid < w.nlo + w.nhi)
     {
-        const uint32_t j = tid < w.nlo ? w.ws + tid : w.hi_begin + (tid - w.nlo);
-        const uint32_t v = bswap32(stg[j]);
-        stg[j] = 0;
-        if ((j == w.ws && (w.shared & 1u)) || (j == w.we && (w.shared & 2u))) atomicOr(g + j, v);
-        else g[j] = v;
+        const WritePlan w = wplan[warp];                              // stream `warp`: its leftover words
+        if ((w.shared & 4u) && lane < w.nlo + w.nhi)
+        {
+            uint32_t* st = warp == 0 ? stg[0] : (warp == 1 ? stg[1] : (warp == 2 ? stg[2] : stg[3]));
+            uint32_t* g = (warp == 0 ? O.w[0] : (warp == 1 ? O.w[1] : (warp == 2 ? O.w[2] : O.w[3]))) + w.base;
+            const uint32_t j = lane < w.nlo ? w.ws + lane : w.hi_begin + (lane - w.nlo);
+            const uint32_t v = bswap32(st[j]);
+            st[j] = 0;
+            if ((j == w.ws && (w.shared & 1u)) || (j == w.we && (w.shared & 2u))) atomicOr(g + j, v);
+            else g[j] = v;
+        }
     }
 }
 // bit offset of a global stream position inside the tile's staging buffer
@@ -422,8 +445,7 @@ __global__ void __launch_bounds__(kPlaceRoles * kPlaceTile) place_kernel(PlaceAr
         __syncthreads();
 
         // ---- 3. out ------------------------------------------------------------------------------------------------------------
-#pragma unroll
-        for (int s = 0; s < 4; ++s) write_out(stg[s], a.O.w[s], wplan[s]);
+        write_out_all(stg, a.O, wplan);
         // no barrier here: the next round only touches the other plan buffer before its own barrier, and nothing is
         // ORed into the staging before every warp has passed that barrier, i.e. has finished writing this tile out
         cur = nxt; nxt = nn; buf ^= 1u;

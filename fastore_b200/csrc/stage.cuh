@@ -126,52 +126,98 @@ __device__ __forceinline__ bool qua_word_ok(uint32_t w, uint32_t m, uint32_t off
     return (bad & 0x80808080u) == 0;
 }
 
+// one aligned 16-byte piece of a span: `lo`/`hi` = the span's byte range counted from the aligned address a0
+template <int KIND>     // 0 sequence, 1 quality, 2 title characters
+__device__ __forceinline__ bool piece_ok(const uint4& q, int32_t piece, int32_t lo, int32_t hi, uint32_t off4, bool need_range)
+{
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    const bool inner = piece * 16 >= lo && piece * 16 + 16 <= hi;     // every byte of the piece belongs to the span (all but the first and last piece)
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        const uint32_t msk = inner ? 0xFFFFFFFFu : bytes_in_range_mask(lo, hi, piece * 16 + 4 * j);
+        if (KIND == 0) ok = ok && dna_word_ok(w[j], msk);
+        else if (KIND == 1) ok = ok && qua_word_ok(w[j], msk, off4, need_range);
+        else ok = ok && ((w[j] & msk & 0x80808080u) == 0);
+    }
+    return ok;
+}
+
+struct CheckSpan { uintptr_t a0; int32_t lo, hi; };
+__device__ __forceinline__ CheckSpan check_span(const uint8_t* p0, uint32_t len)
+{
+    CheckSpan s;
+    s.a0 = reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)15;          // the text buffers are padded: aligned pieces stay inside
+    s.lo = (int32_t)(reinterpret_cast<uintptr_t>(p0) - s.a0);
+    s.hi = len ? s.lo + (int32_t)len : 0;                             // hi = 0: nothing to check
+    return s;
+}
+
+// A half warp per mate: lane j checks the j-th aligned 16-byte piece of the sequence, of the quality and of the title (the
+// three loads are issued together; reads longer than ~240 bases take a second round).  The chunk tables sit in shared
+// memory, and the next mate's record is fetched while the current one is checked.
 __global__ void __launch_bounds__(256) validate_text_kernel(BatchView B, DeviceParams P, const uint64_t* __restrict__ text_size0,
                                                             const uint64_t* __restrict__ text_size1, StageStats* __restrict__ st)
 {
-    const uint32_t half = threadIdx.x >> 4, l16 = threadIdx.x & 15u;                  // 16 half warps per block
+    constexpr uint32_t kMaxChunks = 256;
+    __shared__ uint64_t s_first[kMaxChunks + 1], s_base[2][kMaxChunks], s_size[2][kMaxChunks];
+    for (uint32_t c = threadIdx.x; c <= B.n_chunks && c <= kMaxChunks; c += blockDim.x)
+    {
+        s_first[c] = B.chunk_first_rec[c];
+        if (c < B.n_chunks)
+        {
+            s_base[0][c] = B.chunk_text_base[0][c]; s_size[0][c] = text_size0[c];
+            s_base[1][c] = P.paired ? B.chunk_text_base[1][c] : 0ull; s_size[1][c] = P.paired ? text_size1[c] : 0ull;
+        }
+    }
+    __syncthreads();
+    const uint32_t half = threadIdx.x >> 4;                                              // 16 half warps per block
+    const int32_t l16 = (int32_t)(threadIdx.x & 15u);
     const uint64_t n_mates = P.paired ? 2 * B.n_records : B.n_records;
     const bool need_range = P.qua_bits != 1;                                            // 1-bit mode: only q >= offset (the threshold compare takes any value)
     const uint32_t off4 = (P.qua_offset & 0x7Fu) * 0x01010101u;
-    for (uint64_t g = (uint64_t)blockIdx.x * 16u + half; g < n_mates; g += (uint64_t)gridDim.x * 16u)
+    const uint64_t stride = (uint64_t)gridDim.x * 16u;
+    uint64_t g = (uint64_t)blockIdx.x * 16u + half;
+    auto load_rec = [&](uint64_t gg) -> uint4
     {
+        if (gg >= n_mates) return make_uint4(0, 0, 0, 0);
+        const uint64_t i = P.paired ? (gg >> 1) : gg;
+        return *reinterpret_cast<const uint4*>(((P.paired && (gg & 1u)) ? B.rec[1] : B.rec[0]) + i);
+    };
+    uint4 rw = load_rec(g);
+    for (; g < n_mates; g += stride)
+    {
+        const uint4 cur = rw;
+        rw = load_rec(g + stride);                                                       // in flight during the checks
         const uint64_t i = P.paired ? (g >> 1) : g;
         const uint32_t m = P.paired ? (uint32_t)(g & 1u) : 0u;
-        const uint32_t ch = find_chunk(B, i);
-        const fsb_record r = B.rec[m][i];
-        const uint8_t* text = B.text[m] + B.chunk_text_base[m][ch];
-        const uint64_t ts = (m ? text_size1 : text_size0)[ch];
+        uint32_t lo_c = 0, hi_c = B.n_chunks;                                            // chunk of the record: first[lo] <= i < first[hi]
+        while (hi_c - lo_c > 1) { const uint32_t mid = (lo_c + hi_c) >> 1; if (s_first[mid] <= i) lo_c = mid; else hi_c = mid; }
+        const uint32_t head_off = cur.x, seq_off = cur.y, qua_off = cur.z, L = cur.w & 0xFFFFu, head_len = (cur.w >> 16) & 0xFFu;
+        const uint64_t ts = s_size[m][lo_c];
         // records whose views leave the chunk are reported by stage_stats_kernel; never follow them
-        if (r.seq_len < 1 || r.seq_len > 255 || (uint64_t)r.seq_off + r.seq_len > ts || (uint64_t)r.qua_off + r.seq_len > ts ||
-            (uint64_t)r.head_off + r.head_len > ts) continue;
+        if (L < 1 || L > 255 || (uint64_t)seq_off + L > ts || (uint64_t)qua_off + L > ts || (uint64_t)head_off + head_len > ts) continue;
+        const uint8_t* text = B.text[m] + s_base[m][lo_c];
+        const uint32_t H = (m == 0 && P.has_headers) ? head_len : 0u;
+        const CheckSpan sq = check_span(text + seq_off, L), qu = check_span(text + qua_off, L), hd = check_span(text + head_off + 1u, H > 1u ? H - 1u : 0u);
+        // first round: pieces 0..15 of the three spans, the loads side by side
+        const bool in_s = l16 * 16 < sq.hi, in_q = l16 * 16 < qu.hi, in_h = l16 * 16 < hd.hi;
+        uint4 vs = make_uint4(0, 0, 0, 0), vq = vs, vh = vs;
+        if (in_s) vs = *reinterpret_cast<const uint4*>(sq.a0 + 16u * (uint32_t)l16);
+        if (in_q) vq = *reinterpret_cast<const uint4*>(qu.a0 + 16u * (uint32_t)l16);
+        if (in_h) vh = *reinterpret_cast<const uint4*>(hd.a0 + 16u * (uint32_t)l16);
         bool ok = true;
-        const uint32_t L = r.seq_len, H = (m == 0 && P.has_headers) ? r.head_len : 0u;
-        // spans: sequence, quality, title characters 1 .. H-1
-        const uint64_t span_at[3] = {(uint64_t)r.seq_off, (uint64_t)r.qua_off, (uint64_t)r.head_off + 1u};
-        const uint32_t span_len[3] = {L, L, H > 1u ? H - 1u : 0u};
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-        {
-            if (span_len[k] == 0) continue;
-            const uint8_t* p0 = text + span_at[k];
-            const uintptr_t a0 = reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)15;    // the text buffers are padded: aligned pieces stay inside
-            const int32_t lo = (int32_t)(reinterpret_cast<uintptr_t>(p0) - a0), hi = lo + (int32_t)span_len[k];
-            for (int32_t piece = (int32_t)l16; piece * 16 < hi; piece += 16)
-            {
-                const uint4 q = *reinterpret_cast<const uint4*>(a0 + 16u * (uint32_t)piece);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    const uint32_t msk = bytes_in_range_mask(lo, hi, piece * 16 + 4 * j);
-                    if (msk == 0) continue;
-                    if (k == 0) ok = ok && dna_word_ok(w[j], msk);
-                    else if (k == 1) ok = ok && qua_word_ok(w[j], msk, off4, need_range);
-                    else ok = ok && ((w[j] & msk & 0x80808080u) == 0);
-                }
-            }
-        }
-        if (!ok) { atomicAdd(&st->n_bad_text, 1u); atomicMin(&st->first_bad_text, (unsigned long long)i); }
+        if (in_s) ok = piece_ok<0>(vs, l16, sq.lo, sq.hi, off4, need_range);
+        if (in_q) ok = ok && piece_ok<1>(vq, l16, qu.lo, qu.hi, off4, need_range);
+        if (in_h) ok = ok && piece_ok<2>(vh, l16, hd.lo, hd.hi, off4, need_range);
+        // the 17th piece of spans of more than 240 bytes
+        for (int32_t piece = l16 + 16; piece * 16 < sq.hi; piece += 16) ok = ok && piece_ok<0>(*reinterpret_cast<const uint4*>(sq.a0 + 16u * (uint32_t)piece), piece, sq.lo, sq.hi, off4, need_range);
+        for (int32_t piece = l16 + 16; piece * 16 < qu.hi; piece += 16) ok = ok && piece_ok<1>(*reinterpret_cast<const uint4*>(qu.a0 + 16u * (uint32_t)piece), piece, qu.lo, qu.hi, off4, need_range);
+        for (int32_t piece = l16 + 16; piece * 16 < hd.hi; piece += 16) ok = ok && piece_ok<2>(*reinterpret_cast<const uint4*>(hd.a0 + 16u * (uint32_t)piece), piece, hd.lo, hd.hi, off4, need_range);
+        const unsigned half_mask = 0xFFFFu << (16u * (half & 1u));                        // the 16 lanes of this mate
+        const bool bad = __any_sync(half_mask, !ok);
+        if (bad && l16 == 0) { atomicAdd(&st->n_bad_text, 1u); atomicMin(&st->first_bad_text, (unsigned long long)i); }
     }
 }
 

@@ -61,7 +61,7 @@ def test_pack_core_matches_oracle(emul, name):
 
 
 @pytest.mark.parametrize("name", [c[0] for c in CASES])
-@pytest.mark.parametrize("per_thread,threads", [(4, 512), (3, 5), (1, 7), (32, 4)])
+@pytest.mark.parametrize("per_thread,threads", [(32, 128), (3, 5), (1, 7), (32, 4)])
 def test_one_scan_layout_matches_the_sequential_walk(emul, name, per_thread, threads):
     """layout_core.cuh: the framing rules as an associative scan (run states, block states, exclusive scan, absolute
     walk) give every record the bit positions and every bin the descriptor of the plain sequential walk, for any
