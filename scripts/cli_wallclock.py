@@ -23,6 +23,9 @@ import binfile_helpers as BF      # noqa: E402
 from fastore_b200 import synth    # noqa: E402
 
 
+TRACE = False
+
+
 def timed(cmd):
     t0 = time.perf_counter()
     r = subprocess.run([str(c) for c in cmd], capture_output=True, text=True)
@@ -57,6 +60,9 @@ def run_case(name, w, n, tmp, threads):
     for rep in range(2):                                        # second run: CUDA context creation and pinned allocation are what they are; take the better
         t = timed([BF.CLI, "e", inp, f"-o{tmp / 'gpu'}", "-P" + str(max(4, min(16, threads // 2)))] + args)
         best = t if best is None else min(best, t)
+    if TRACE:
+        r = subprocess.run([str(BF.CLI), "e", inp, f"-o{tmp / 'gpu_trace'}", "-v", "-P" + str(max(4, min(16, threads // 2)))] + args, capture_output=True, text=True)
+        sys.stderr.write(f"---- {name}: fastore_bin_b200 -v ----\n" + r.stderr.replace("\r", "\n") + "\n")
     out["fastore_bin_b200"] = {"seconds": best, "reads_per_s": n * mates / best, "gpus": "all", "parser_threads": max(4, min(16, threads // 2))}
     BF.assert_bin_files_equal(tmp / "gpu", tmp / "ref1", flags["headers"])
     out["byte_identical_to_reference_t1"] = True
@@ -71,7 +77,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=2_000_000)
     ap.add_argument("--configs", default="c1,c2")
+    ap.add_argument("--trace", action="store_true", help="one more run of the GPU tool with -v, its phase trace to stderr")
     a = ap.parse_args()
+    global TRACE
+    TRACE = a.trace
     threads = bench.host_threads()
     base = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
     tmp = Path(tempfile.mkdtemp(prefix="fsb_wall_", dir=base))
