@@ -303,7 +303,17 @@ def run_b200_arm(args, w, name):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved = os.dup(1)                                             # NCCL prints its version banner to stdout when the communicator comes up
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from fastore_b200 import _native as N
     from fastore_b200 import build

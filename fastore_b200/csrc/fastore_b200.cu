@@ -131,13 +131,13 @@ struct fsb_ctx
     DeviceParams dp{};
     int device = 0;
     cudaStream_t stream = nullptr;               // kernels
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined fsb_bin_chunks (created on first use)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_chk = nullptr;   // copy and input-check streams of the pipelined fsb_bin_chunks (created on first use)
     bool own_stream = false;
     std::string err;
     bool per_read = false, profile = false, validate = true;
     uint64_t sub_batch_records = 400000;         // fsb_bin_chunks cuts its chunk list into sub-batches of at least this many records
 
-    Batch batch[2];                              // [0] is the batch of fsb_stage / fsb_run / fsb_fetch
+    Batch batch[3];                              // [0] is the batch of fsb_stage / fsb_run / fsb_fetch; fsb_bin_chunks cycles through all three
     std::vector<HostOut*> host;                  // [g] results of sub-batch g ([0] for the resident interface)
 
     // the pipeline's intermediates; lane 0 runs on `stream`, lane 1 (second stream) only when fsb_run splits a batch
@@ -348,7 +348,8 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     // ---- sub-batches: runs of whole chunks with about n / split records each --------------------------------------
     b.subs.clear();
     {
-        const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(split, n_chunks));
+        // (K1 keeps the chunk tables of up to 32 chunks in registers; a batch of more chunks is cut so that every sub-batch qualifies)
+        const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(split, (n_chunks + 31u) / 32u), n_chunks));
         uint32_t c0 = 0;
         for (uint32_t j = 0; j < S && c0 < n_chunks; ++j)
         {
@@ -933,6 +934,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     cudaStreamSynchronize(c->stream);
     if (c->s_h2d) { cudaStreamSynchronize(c->s_h2d); cudaStreamDestroy(c->s_h2d); }
     if (c->s_d2h) { cudaStreamSynchronize(c->s_d2h); cudaStreamDestroy(c->s_d2h); }
+    if (c->s_chk) { cudaStreamSynchronize(c->s_chk); cudaStreamDestroy(c->s_chk); }
     for (auto& e : c->events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_check) if (e) cudaEventDestroy(e);
     for (Batch& b : c->batch)
@@ -1070,12 +1072,14 @@ extern "C" int fsb_fetch(fsb_ctx* c, fsb_block* blocks, uint32_t n_blocks)
 
 // ---- host buffers in, host blocks out ----------------------------------------------------------------------------
 // The chunk list is cut into sub-batches of at least sub_batch_records records (whole chunks) which
-// run as a pipeline over the two device buffer sets:
-//     s_h2d   : copy in g+1 ......... (waits until the kernels of g-1 have released that buffer set)
-//     stream  : input check of g (after its copy), kernels of g (the host has waited for copy out g-2 to release the result buffers)
+// run as a pipeline over three sets of device buffers:
+//     s_h2d   : copies in of g+1, g+2 ... back to back (a set is reused once the kernels that read it are done)
+//     s_chk   : input check of every sub-batch as soon as its copy has landed
+//     stream  : kernels of g (the host has seen g's check results, and that copy out g-3 has released the result buffers)
 //     s_d2h   : copy out g-1
-// The host only blocks on small things: the staging statistics of a sub-batch (they size the
-// buffers and carry the input validation) and its chunk summary (the stream sizes).
+// Two sub-batches are always staged ahead, so the copy stream -- the PCIe link is what bounds this call -- never waits for
+// the host.  The host only blocks on small things: the check results of a sub-batch (they size the buffers and carry the
+// input validation) and its chunk summary (the stream sizes).
 extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks, fsb_block* blocks)
 {
     if (!c || !blocks || (!chunks && n_chunks)) return FSB_ERR_PARAM;
@@ -1101,43 +1105,46 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
     const uint32_t G = (uint32_t)first.size() - 1;
     if (!c->s_h2d) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     if (!c->s_d2h) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    if (!c->s_chk) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_chk, cudaStreamNonBlocking));
+    constexpr uint32_t kSets = 3, kAhead = 2;
+    auto set_of = [&](uint32_t g) -> Batch& { return c->batch[g % kSets]; };
     for (uint32_t g = 0; g < G; ++g) if (!host_out(c, g)) return fail(c, FSB_ERR_NOMEM, "out of host memory");
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // earlier work on the context (resident interface) is done
     CUDA_TRY(c, cudaStreamSynchronize(c->s_d2h));
 
     int rc = FSB_OK;
-    auto drain = [&]() { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h); };
+    auto drain = [&]() { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_chk); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h); };
     // copy out of sub-batch g: its summary is on the host once ev_run has fired
     auto finish = [&](uint32_t g) -> int
     {
-        Batch& b = c->batch[g & 1];
+        Batch& b = set_of(g);
         CUDA_TRY(c, cudaEventSynchronize(b.ev_run));
         CUDA_TRY(c, cudaStreamWaitEvent(c->s_d2h, b.ev_run, 0));
         int r = fetch_enqueue(c, b, *c->host[g], c->s_d2h);
         if (r != FSB_OK) return r;
         CUDA_TRY(c, cudaEventRecord(b.ev_d2h, c->s_d2h));
-        // the batch object is reused two sub-batches later: describe the blocks now (the pointers are final,
+        // the batch object is reused three sub-batches later: describe the blocks now (the pointers are final,
         // the bytes arrive before the call returns)
         fill_blocks(c, b, *c->host[g], blocks + first[g]);
         return FSB_OK;
     };
 
-    rc = stage_enqueue(c, c->batch[0], chunks + first[0], first[1] - first[0], c->s_h2d, c->stream, 1);
+    for (uint32_t g = 0; g < std::min(G, kAhead) && rc == FSB_OK; ++g)
+        rc = stage_enqueue(c, set_of(g), chunks + first[g], first[g + 1] - first[g], c->s_h2d, c->s_chk, 1);
     for (uint32_t g = 0; g < G && rc == FSB_OK; ++g)
     {
-        Batch& b = c->batch[g & 1];
+        Batch& b = set_of(g);
         if (cudaEventSynchronize(b.ev_chk) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy to the device failed"); break; }    // text on the device, check results on the host
-        if (g >= 2 && cudaEventSynchronize(b.ev_d2h) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy from the device failed"); break; }   // result buffers of g-2 are free
+        if (g >= kSets && cudaEventSynchronize(b.ev_d2h) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy from the device failed"); break; }   // result buffers of g-3 are free
         if ((rc = stage_complete(c, b)) != FSB_OK) break;
         if ((rc = run_enqueue(c, b, false)) != FSB_OK) break;
         if ((rc = summary_enqueue(c, b, *c->host[g], c->stream)) != FSB_OK) break;
         if (cudaEventRecord(b.ev_run, c->stream) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
-        // copy out g-1 first: staging g+1 below reuses that batch object (and, once its kernels are done, its input buffers)
+        // copy out g-1 first: it waits for the kernels of g-1, after which staging g+2 may reuse that set's input buffers
         if (g >= 1 && (rc = finish(g - 1)) != FSB_OK) break;
-        if (g + 1 < G)
+        if (g + kAhead < G)
         {
-            Batch& nx = c->batch[(g + 1) & 1];
-            if ((rc = stage_enqueue(c, nx, chunks + first[g + 1], first[g + 2] - first[g + 1], c->s_h2d, c->stream, 1)) != FSB_OK) break;
+            if ((rc = stage_enqueue(c, set_of(g + kAhead), chunks + first[g + kAhead], first[g + kAhead + 1] - first[g + kAhead], c->s_h2d, c->s_chk, 1)) != FSB_OK) break;
         }
     }
     if (rc == FSB_OK) rc = finish(G - 1);

@@ -134,7 +134,15 @@ int main(int argc, const char** argv)
     const bool pe = a.cfg.params.paired_end != 0;
     const int ndev = fsb_device_count();
     if (ndev == 0) { std::fprintf(stderr, "Error: no sm_100 GPU available (this tool has no CPU fallback)\n"); return -1; }
-    const int G = a.gpus > 0 ? std::min(a.gpus, ndev) : ndev;
+    int G = a.gpus > 0 ? std::min(a.gpus, ndev) : ndev;
+    if (a.gpus <= 0)
+    {   // a CUDA context costs about half a second per device: do not open more devices than the input has pairs of chunks
+        uint64_t bytes = 0;
+        const size_t half_n = a.cfg.params.paired_end ? a.in.size() / 2 : a.in.size();
+        for (size_t i = 0; i < half_n; ++i) { FILE* f = std::fopen(a.in[i].c_str(), "rb"); if (f) { std::fseek(f, 0, SEEK_END); const long long sz = ftello(f); if (sz > 0) bytes += (uint64_t)sz; std::fclose(f); } }
+        const uint64_t n_chunks = bytes / std::max<uint64_t>(a.cfg.fastq_block_size, 1) + 1;
+        G = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)G, (n_chunks + 1) / 2));
+    }
 
     std::vector<const char*> f1, f2;
     const size_t half = pe ? a.in.size() / 2 : a.in.size();
