@@ -22,6 +22,7 @@ FSB_INFO_SWAPPED = 0x00020000
 FSB_INFO_PLAIN_A = 0x00040000
 FSB_INFO_PLAIN_B = 0x00080000
 FSB_OPT_PER_READ, FSB_OPT_PROFILE, FSB_OPT_VALIDATE, FSB_OPT_SUBBATCH_RECORDS, FSB_OPT_RUN_SPLIT = 1, 2, 3, 4, 5
+FSB_OPT_KEEP_COMMENTS, FSB_OPT_KEEP_RECORDS = 10, 11
 FSB_STAGE_NAMES = ("ingest", "sort", "layout", "place", "check")     # "check": input-check kernels of fsb_stage, reported on request
 
 
@@ -111,7 +112,7 @@ assert RECORD_DTYPE.itemsize == 16 and BIN_DESC_DTYPE.itemsize == 64
 # every symbol include/fastore_b200.h declares (checked by tests/test_abi.py)
 C_ABI_SYMBOLS = (
     "fsb_create", "fsb_destroy", "fsb_last_error", "fsb_set_option", "fsb_bin_chunks", "fsb_stage", "fsb_run",
-    "fsb_fetch", "fsb_sync", "fsb_stage_times", "fsb_get_stats", "fsb_host_alloc", "fsb_host_free", "fsb_device_count",
+    "fsb_fetch", "fsb_sync", "fsb_stage_times", "fsb_get_stats", "fsb_host_alloc", "fsb_host_free", "fsb_device_count", "fsb_get_records",
 )
 
 _host = None
@@ -203,6 +204,8 @@ def cuda_lib() -> C.CDLL:
         lib.fsb_host_alloc.argtypes = [C.c_size_t]
         lib.fsb_host_free.restype = None
         lib.fsb_host_free.argtypes = [C.c_void_p]
+        lib.fsb_get_records.restype = C.c_int
+        lib.fsb_get_records.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         lib.fsb_device_count.restype = C.c_int
         lib.fsb_device_count.argtypes = []
         _cuda = lib
@@ -229,17 +232,19 @@ def np_ptr(a: np.ndarray) -> int:
 
 
 def make_chunk(text1: np.ndarray, rec1: np.ndarray, text2: np.ndarray | None = None, rec2: np.ndarray | None = None) -> FsbChunk:
-    """fsb_chunk over numpy buffers (the caller keeps them alive)."""
+    """fsb_chunk over numpy buffers (the caller keeps them alive).  rec1 = None: text alone, the library parses it on the device."""
     ch = FsbChunk()
     ch.text[0] = np_ptr(text1)
     ch.text_size[0] = text1.size
-    ch.records[0] = np_ptr(rec1)
-    ch.n_records = rec1.shape[0]
+    if rec1 is not None:
+        ch.records[0] = np_ptr(rec1)
+        ch.n_records = rec1.shape[0]
     if text2 is not None:
-        assert rec2 is not None and rec2.shape[0] == rec1.shape[0]
         ch.text[1] = np_ptr(text2)
         ch.text_size[1] = text2.size
-        ch.records[1] = np_ptr(rec2)
+        if rec1 is not None:
+            assert rec2 is not None and rec2.shape[0] == rec1.shape[0]
+            ch.records[1] = np_ptr(rec2)
     return ch
 
 

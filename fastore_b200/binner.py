@@ -36,7 +36,7 @@ class BinBlock:
 class GpuBinner:
     def __init__(self, params: N.FsbParams, device: int = 0, stream: int | None = None, per_read: bool = False,
                  profile: bool = False, sub_batch_records: int | None = None, validate: bool | None = None,
-                 run_split: int | None = None):
+                 run_split: int | None = None, keep_comments: bool | None = None, keep_records: bool | None = None):
         self._lib = N.cuda_lib()
         self._ctx = C.c_void_p()
         self.params = params
@@ -50,6 +50,10 @@ class GpuBinner:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_PROFILE, 1))
         if validate is not None:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_VALIDATE, 1 if validate else 0))
+        if keep_comments is not None:
+            self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_KEEP_COMMENTS, 1 if keep_comments else 0))
+        if keep_records is not None:
+            self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_KEEP_RECORDS, 1 if keep_records else 0))
         if run_split is not None:
             self._check(self._lib.fsb_set_option(self._ctx, N.FSB_OPT_RUN_SPLIT, run_split))
         if sub_batch_records is not None:
@@ -111,6 +115,16 @@ class GpuBinner:
         blocks = (N.FsbBlock * self._n_staged)()
         self._check(self._lib.fsb_fetch(self._ctx, blocks, self._n_staged))
         return [self._to_block(b) for b in blocks] if copy else blocks
+
+    def get_records(self, chunk: int, mate: int = 0) -> np.ndarray:
+        """Device-side parse: the record table the library built for a chunk of the last call."""
+        n = C.c_uint64()
+        rc = self._lib.fsb_get_records(self._ctx, chunk, mate, None, 0, C.byref(n))
+        if rc not in (N.FSB_OK, N.FSB_ERR_PARAM):
+            self._check(rc)
+        out = np.zeros(int(n.value), dtype=N.RECORD_DTYPE)
+        self._check(self._lib.fsb_get_records(self._ctx, chunk, mate, N.np_ptr(out) if out.size else None, out.size, C.byref(n)))
+        return out
 
     def stage_times(self, n_stages: int = 4):
         """Per-stage device milliseconds since the last call: the four stages of fsb_run, plus "check" (the input-check

@@ -31,6 +31,7 @@
 #include "layout.cuh"
 #include "place.cuh"
 #include "layout_fused.cuh"
+#include "parse.cuh"
 
 using namespace fsb;
 
@@ -103,7 +104,8 @@ struct Batch
     uint32_t n_chunks = 0;
     uint64_t n_records = 0;
     std::vector<uint64_t> chunk_first_rec;       // n_chunks + 1
-    std::vector<uint64_t> chunk_text_base[2];
+    std::vector<uint64_t> chunk_text_base[2], chunk_text_size[2];
+    cudaStream_t st_check = nullptr;             // the stream the staging kernels of this batch run on
     std::vector<uint64_t> meta_host;             // host copy of the chunk tables (must outlive its async copy)
     uint64_t total_bases = 0, total_head = 0, nb_max = 0, algorithmic_in = 0, h2d_bytes = 0;
     uint32_t min_len = 0, max_len = 0, max_head = 0;
@@ -112,6 +114,19 @@ struct Batch
     size_t out_total[4] = {0, 0, 0, 0};          // sum of the sub-batches' regions
 
     std::vector<SortTile> tiles_host;            // sort tiles of all sub-batches (must outlive its async copy)
+    // ---- device-side parse (chunks handed over without record tables; parse.cuh) ------------------------------------------
+    bool device_parse = false;
+    int parse_state = 0;                         // 0: nothing pending (tables from the host, or parse finished); 1: line ends counted; 2: records built
+    std::vector<ParseSeg> segs_host;             // one segment per (chunk, mate)
+    std::vector<uint8_t> seg_open_end;           // 1: the segment's text does not end with a line end (its last line is one more line)
+    std::vector<uint64_t> chunk_cap;             // record candidates per chunk (table capacity)
+    std::vector<uint64_t> chunk_n;               // records per chunk (what the parse found, or what the caller's tables hold)
+    uint64_t total_tiles = 0;
+    uint32_t split = 1;
+    bool profile_check = false;
+    DevBuf d_segs, d_tile_count, d_tile_prefix, d_line_start, d_parse_res, d_seg_ends, d_rec_tmp, d_parse_scan_tmp;
+    PinBuf h_seg_ends, h_parse_res;
+    cudaEvent_t ev_parse = nullptr;
     DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats, d_chunk_sums, d_sort_tiles;
     PinBuf h_stage_stats, h_chunk_sums;
     DevBuf d_out[4], d_desc, d_summary, d_sig, d_info;
@@ -121,7 +136,7 @@ struct Batch
 // Pinned host memory holding the results of one (sub-)batch until the next call on the context.
 struct HostOut
 {
-    PinBuf out[4], desc, summary, sig, info;
+    PinBuf out[4], desc, summary, sig, info, rec[2];
     uint64_t d2h_bytes = 0;
 };
 
@@ -164,6 +179,10 @@ struct fsb_ctx
     uint32_t k1_batches_per_warp = 32, k4_tiles_per_block = 64;   // block granularity of K1 / K4 when sub-batches share the GPU (0: persistent)
     bool block_grids_always = false;             // use that granularity for unsplit runs too (measurement only)
     bool fused_layout = true;                    // batches of one read length take the one-scan layout (FSB_OPT_FUSED_LAYOUT, measurement only)
+    bool keep_records = false;                   // device-side parse inside fsb_bin_chunks: copy the record tables back too (FSB_OPT_KEEP_RECORDS)
+    struct RecRef { const fsb_record* host[2]; uint64_t n; };
+    std::vector<RecRef> rec_index;               // per chunk of the last fsb_bin_chunks call (device-side parse + keep_records)
+    bool keep_comments = true;                   // device-side parse: keep the title's comment (FSB_OPT_KEEP_COMMENTS; 0 = the reference's -C)
 
     // ---- profiling -----------------------------------------------------------------------------
     std::vector<cudaEvent_t> events;             // kMaxPendingProfiles * (FSB_STAGE_COUNT + 1)
@@ -192,8 +211,6 @@ int fail(fsb_ctx* c, int code, const std::string& msg)
             return fail(ctx, e__ == cudaErrorMemoryAllocation ? FSB_ERR_NOMEM : FSB_ERR_CUDA,            \
                         std::string(#expr) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
-
-uint32_t bits_for(uint32_t v) { uint32_t b = 0; while ((1ull << b) <= v) ++b; return b; }   // bits to represent v
 
 BatchView batch_view(const Batch& b)
 {
@@ -308,39 +325,17 @@ HostOut* host_out(fsb_ctx* c, size_t g)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage, step 1: enqueue the host->device copies of a group of chunks on `st`, then the device-side
-// check of the record tables (offsets inside the chunk, lengths, PE mate-length equality - the
-// things the reference only ASSERTs: FastqRecord.h:87, FastqParser.cpp:130) together with the batch
-// statistics that size the buffers, and the copy of those statistics back.  The batch's input
-// buffers must not be in use.  `split` = sub-batches of whole chunks the kernels will run as.  The copies go to `st`, the
-// check kernels and the copy of their results to `st_check` (which then waits for the copies; b.ev_chk fires when the results
-// are on the host): the pipeline keeps its copy stream free of kernels, so that the next sub-batch's text follows at once.
-int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, cudaStream_t st_check, uint32_t split, bool profile = false)
+// Stage, last enqueue step: the records per chunk are known (b.chunk_n: from the caller's tables or from the device-side
+// parse).  Chunk tables, sub-batches and sort tiles go up, then the device-side check of the record tables (offsets
+// inside the chunk, lengths, PE mate-length equality - the things the reference only ASSERTs: FastqRecord.h:87,
+// FastqParser.cpp:130) together with the batch statistics that size the buffers, the byte-level check, and the copy of
+// the results back.  Everything goes to `st`; b.ev_chk fires when the results are on the host.
+int stage_finalize(fsb_ctx* c, Batch& b, cudaStream_t st)
 {
-    b.staged = false; b.ran = false;
-    const int nfiles = c->dp.paired ? 2 : 1;
-    const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(kMaxChunksPerBatch, 1ull << (32 - c->dp.key_bits));
-    if (n_chunks == 0) return fail(c, FSB_ERR_PARAM, "fsb_stage: no chunks");
-    if (n_chunks > max_chunks) return fail(c, FSB_ERR_PARAM, "fsb_stage: too many chunks in one batch for this signature length (max " + std::to_string(max_chunks) + ")");
-
-    b.n_chunks = n_chunks;
+    const uint32_t n_chunks = b.n_chunks;
     b.chunk_first_rec.assign(n_chunks + 1, 0);
-    size_t text_bytes[2] = {kTextPad, kTextPad};
-    for (int m = 0; m < 2; ++m) b.chunk_text_base[m].assign(n_chunks, 0);
     uint64_t n = 0;
-    for (uint32_t ci = 0; ci < n_chunks; ++ci)
-    {
-        const fsb_chunk& ch = chunks[ci];
-        b.chunk_first_rec[ci] = n;
-        for (int m = 0; m < nfiles; ++m)
-        {
-            if (ch.n_records && (!ch.text[m] || !ch.records[m])) return fail(c, FSB_ERR_PARAM, "fsb_stage: null text/records");
-            if (ch.text_size[m] >= 0xFFFFFFFFull) return fail(c, FSB_ERR_INPUT, "fsb_stage: chunk text must be < 4 GiB (32-bit record offsets)");
-            b.chunk_text_base[m][ci] = text_bytes[m];
-            text_bytes[m] = align_up(text_bytes[m] + ch.text_size[m] + kTextPad, 256);
-        }
-        n += ch.n_records;
-    }
+    for (uint32_t ci = 0; ci < n_chunks; ++ci) { b.chunk_first_rec[ci] = n; n += b.chunk_n[ci]; }
     b.chunk_first_rec[n_chunks] = n;
     if (n > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
     b.n_records = n;
@@ -349,7 +344,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     b.subs.clear();
     {
         // (K1 keeps the chunk tables of up to 32 chunks in registers; a batch of more chunks is cut so that every sub-batch qualifies)
-        const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(split, (n_chunks + 31u) / 32u), n_chunks));
+        const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(b.split, (n_chunks + 31u) / 32u), n_chunks));
         uint32_t c0 = 0;
         for (uint32_t j = 0; j < S && c0 < n_chunks; ++j)
         {
@@ -367,23 +362,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
             c0 = c1;
         }
     }
-
     uint64_t h2d = 0;
-    for (int m = 0; m < nfiles; ++m)
-    {
-        CUDA_TRY(c, b.d_text[m].ensure(text_bytes[m] + kTextPad, &st));      // padding between chunks is over-read by aligned window copies: keep it defined
-        CUDA_TRY(c, b.d_rec[m].ensure((n + 1) * sizeof(fsb_record)));
-        for (uint32_t ci = 0; ci < n_chunks; ++ci)
-        {
-            const fsb_chunk& ch = chunks[ci];
-            if (ch.text_size[m])
-                CUDA_TRY(c, cudaMemcpyAsync(b.d_text[m].as<uint8_t>() + b.chunk_text_base[m][ci], ch.text[m], ch.text_size[m], cudaMemcpyHostToDevice, st));
-            if (ch.n_records)
-                CUDA_TRY(c, cudaMemcpyAsync(b.d_rec[m].as<fsb_record>() + b.chunk_first_rec[ci], ch.records[m], ch.n_records * sizeof(fsb_record),
-                                            cudaMemcpyHostToDevice, st));
-            h2d += ch.text_size[m] + ch.n_records * sizeof(fsb_record);
-        }
-    }
     // chunk tables: [first_rec (n_chunks+1)] [text_base0] [text_base1] [text_size0] [text_size1]  (n_chunks each), then per sub-batch
     // its own first-record table counted from the sub-batch's first record (chunks + 1 entries)
     std::vector<uint64_t>& meta = b.meta_host;
@@ -392,7 +371,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
     meta.insert(meta.end(), b.chunk_text_base[0].begin(), b.chunk_text_base[0].end());
     meta.insert(meta.end(), b.chunk_text_base[1].begin(), b.chunk_text_base[1].end());
     for (int m = 0; m < 2; ++m)
-        for (uint32_t ci = 0; ci < n_chunks; ++ci) meta.push_back(chunks[ci].text_size[m]);
+        for (uint32_t ci = 0; ci < n_chunks; ++ci) meta.push_back(b.chunk_text_size[m][ci]);
     for (Sub& sb : b.subs)
     {
         sb.meta_first = meta.size();
@@ -428,12 +407,6 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
         CUDA_TRY(c, cudaMemcpyAsync(b.d_sort_tiles.p, b.tiles_host.data(), b.tiles_host.size() * sizeof(SortTile), cudaMemcpyHostToDevice, st));
     h2d += b.tiles_host.size() * sizeof(SortTile);
 
-    if (st_check != st)
-    {
-        CUDA_TRY(c, cudaEventRecord(b.ev_h2d, st));
-        CUDA_TRY(c, cudaStreamWaitEvent(st_check, b.ev_h2d, 0));
-        st = st_check;                                               // everything below: the check stream
-    }
     CUDA_TRY(c, b.d_stage_stats.ensure(sizeof(StageStats)));
     CUDA_TRY(c, b.h_stage_stats.ensure(2 * sizeof(StageStats)));
     CUDA_TRY(c, b.d_chunk_sums.ensure((size_t)n_chunks * 2 * sizeof(uint64_t)));
@@ -448,7 +421,7 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
         const BatchView B = batch_view(b);
         const uint64_t* m64 = b.d_chunk_meta.as<uint64_t>();
         const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
-        if (profile)
+        if (b.profile_check)
         {
             for (cudaEvent_t& e : c->ev_check) if (!e) CUDA_TRY(c, cudaEventCreate(&e));
             CUDA_TRY(c, cudaEventRecord(c->ev_check[0], st));
@@ -463,14 +436,219 @@ int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chun
             validate_text_kernel<<<vblocks, 256, 0, st>>>(B, c->dp, m64 + (3 * (size_t)n_chunks + 1), m64 + (4 * (size_t)n_chunks + 1), b.d_stage_stats.as<StageStats>());
             c->stats.kernel_launches++;
         }
-        if (profile) { CUDA_TRY(c, cudaEventRecord(c->ev_check[1], st)); c->check_pending = true; }
+        if (b.profile_check) { CUDA_TRY(c, cudaEventRecord(c->ev_check[1], st)); c->check_pending = true; }
     }
     CUDA_TRY(c, cudaMemcpyAsync(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaMemcpyAsync(b.h_chunk_sums.p, b.d_chunk_sums.p, (size_t)n_chunks * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaEventRecord(b.ev_chk, st));
+    b.h2d_bytes += h2d;
+    c->stats.h2d_bytes += h2d;
+    b.parse_state = 0;
+    return FSB_OK;
+}
+
+// Device-side parse, step 1 (parse.cuh): line ends per tile of every (chunk, mate) text, their scan, the line ends per segment back
+// to the host.  b.ev_parse fires when they are there.
+int parse_enqueue_count(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, cudaStream_t st)
+{
+    const int nfiles = c->dp.paired ? 2 : 1;
+    b.segs_host.clear(); b.seg_open_end.clear();
+    uint64_t tiles = 0;
+    for (uint32_t ci = 0; ci < b.n_chunks; ++ci)
+        for (int m = 0; m < nfiles; ++m)
+        {
+            ParseSeg sg{};
+            sg.text_base = b.chunk_text_base[m][ci]; sg.size = chunks[ci].text_size[m]; sg.tile0 = tiles; sg.mate = (uint32_t)m; sg.chunk = ci;
+            tiles += (sg.size + kParseTile - 1) / kParseTile;
+            b.segs_host.push_back(sg);
+            const uint8_t last = sg.size ? chunks[ci].text[m][sg.size - 1] : (uint8_t)'\n';
+            b.seg_open_end.push_back((sg.size && last != '\n' && last != '\r') ? 1 : 0);
+        }
+    b.total_tiles = tiles;
+    const size_t n_segs = b.segs_host.size();
+    ParseSeg guard{};                                                  // one past the last segment: ends the tile search
+    guard.tile0 = tiles;
+    b.segs_host.push_back(guard);
+    CUDA_TRY(c, b.d_segs.ensure((n_segs + 1) * sizeof(ParseSeg)));
+    CUDA_TRY(c, cudaMemcpyAsync(b.d_segs.p, b.segs_host.data(), (n_segs + 1) * sizeof(ParseSeg), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, b.d_tile_count.ensure((tiles + 2) * 4));
+    CUDA_TRY(c, b.d_tile_prefix.ensure((tiles + 2) * 4));
+    CUDA_TRY(c, b.d_parse_scan_tmp.ensure((scan_num_tiles(tiles + 1) + 2) * 4));
+    CUDA_TRY(c, b.d_seg_ends.ensure((n_segs + 1) * 4));
+    CUDA_TRY(c, b.h_seg_ends.ensure((n_segs + 1) * 4));
+    if (tiles)
+    {
+        parse_count_kernel<<<(unsigned)tiles, kParseThreads, 0, st>>>(b.d_text[0].as<uint8_t>(), b.d_text[1].as<uint8_t>(), b.d_segs.as<ParseSeg>(), (uint32_t)n_segs,
+                                                                       b.d_tile_count.as<uint32_t>());
+        c->stats.kernel_launches++;
+    }
+    c->stats.kernel_launches += exclusive_scan<uint32_t, uint32_t>(b.d_tile_count.as<uint32_t>(), tiles, b.d_tile_prefix.as<uint32_t>(), b.d_parse_scan_tmp.as<uint32_t>(), st);
+    parse_seg_ends_kernel<<<(unsigned)((n_segs + 127) / 128), 128, 0, st>>>(b.d_segs.as<ParseSeg>(), (uint32_t)n_segs, b.d_tile_prefix.as<uint32_t>(), b.d_seg_ends.as<uint32_t>());
+    c->stats.kernel_launches++;
+    CUDA_TRY(c, cudaMemcpyAsync(b.h_seg_ends.p, b.d_seg_ends.p, n_segs * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaEventRecord(b.ev_parse, st));
+    b.parse_state = 1;
+    return FSB_OK;
+}
+
+// Device-side parse, steps 2 and 3, and then the common last step: called until b.parse_state is 0 again.  Blocks on the small
+// results of the step before (they size what comes next).
+int stage_advance(fsb_ctx* c, Batch& b, cudaStream_t st)
+{
+    const int nfiles = c->dp.paired ? 2 : 1;
+    const size_t n_segs = b.segs_host.size() - 1;
+    if (b.parse_state == 1)
+    {
+        CUDA_TRY(c, cudaEventSynchronize(b.ev_parse));
+        const uint32_t* ends = b.h_seg_ends.as<uint32_t>();
+        uint64_t lines = 0;
+        b.chunk_cap.assign(b.n_chunks, 0);
+        for (size_t k = 0; k < n_segs; ++k)
+        {
+            ParseSeg& sg = b.segs_host[k];
+            sg.n_ends = ends[k];
+            sg.n_lines = ends[k] + b.seg_open_end[k];
+            sg.cap = (sg.n_lines + 3u) / 4u;
+            sg.line0 = lines;
+            lines += (uint64_t)sg.n_ends + 2;
+            b.chunk_cap[sg.chunk] = std::max<uint64_t>(b.chunk_cap[sg.chunk], sg.cap);
+        }
+        uint64_t cap_total = 0;
+        std::vector<uint64_t> cap_first(b.n_chunks + 1, 0);
+        for (uint32_t ci = 0; ci < b.n_chunks; ++ci) { cap_first[ci] = cap_total; cap_total += b.chunk_cap[ci]; }
+        cap_first[b.n_chunks] = cap_total;
+        if (cap_total > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
+        uint32_t cap_max = 0;
+        for (size_t k = 0; k < n_segs; ++k) { b.segs_host[k].rec0 = cap_first[b.segs_host[k].chunk]; cap_max = std::max(cap_max, b.segs_host[k].cap); }
+        CUDA_TRY(c, cudaMemcpyAsync(b.d_segs.p, b.segs_host.data(), (n_segs + 1) * sizeof(ParseSeg), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, b.d_line_start.ensure((lines + 2) * 4));
+        for (int m = 0; m < nfiles; ++m) CUDA_TRY(c, b.d_rec[m].ensure((cap_total + 1) * sizeof(fsb_record)));
+        CUDA_TRY(c, b.d_parse_res.ensure((n_segs + 1) * sizeof(ParseResult)));
+        CUDA_TRY(c, b.h_parse_res.ensure((n_segs + 1) * sizeof(ParseResult)));
+        CUDA_TRY(c, cudaMemsetAsync(b.d_parse_res.p, 0xFF, (n_segs + 1) * sizeof(ParseResult), st));
+        if (b.total_tiles)
+        {
+            parse_lines_kernel<<<(unsigned)b.total_tiles, kParseThreads, 0, st>>>(b.d_text[0].as<uint8_t>(), b.d_text[1].as<uint8_t>(), b.d_segs.as<ParseSeg>(), (uint32_t)n_segs,
+                                                                                   b.d_tile_prefix.as<uint32_t>(), b.d_line_start.as<uint32_t>());
+            c->stats.kernel_launches++;
+        }
+        if (cap_max)
+        {
+            parse_records_kernel<<<dim3((cap_max + 255u) / 256u, (unsigned)n_segs), 256, 0, st>>>(b.d_text[0].as<uint8_t>(), b.d_text[1].as<uint8_t>(), b.d_segs.as<ParseSeg>(),
+                b.d_line_start.as<uint32_t>(), c->dp.has_headers, c->keep_comments ? 1u : 0u, b.d_rec[0].as<fsb_record>(), b.d_rec[1].as<fsb_record>(), b.d_parse_res.as<ParseResult>());
+            c->stats.kernel_launches++;
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(b.h_parse_res.p, b.d_parse_res.p, n_segs * sizeof(ParseResult), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaEventRecord(b.ev_parse, st));
+        b.parse_state = 2;
+        return FSB_OK;
+    }
+    if (b.parse_state == 2)
+    {
+        CUDA_TRY(c, cudaEventSynchronize(b.ev_parse));
+        const ParseResult* res = b.h_parse_res.as<ParseResult>();
+        // records of a chunk: where the first of its (one or two) parsers stops -- FastqRecordsParserPE::ParseFrom runs both in step (FastqParser.cpp:527)
+        b.chunk_n.assign(b.n_chunks, ~0ull);
+        for (size_t k = 0; k < n_segs; ++k)
+        {
+            const ParseSeg& sg = b.segs_host[k];
+            const uint64_t n_seg = std::min<uint64_t>(sg.cap, res[k].first_bad == ~0ull ? (uint64_t)sg.cap : (res[k].first_bad >> 8));
+            b.chunk_n[sg.chunk] = std::min(b.chunk_n[sg.chunk], n_seg);
+        }
+        for (size_t k = 0; k < n_segs; ++k)
+        {
+            const ParseSeg& sg = b.segs_host[k];
+            if (res[k].first_invalid < b.chunk_n[sg.chunk])
+                return fail(c, FSB_ERR_INPUT, "fsb_stage: record " + std::to_string(res[k].first_invalid) + " of chunk " + std::to_string(sg.chunk) +
+                                                  " is outside the input contract (read length 1..255, title at most 255 bytes)");
+        }
+        // the tables were written at capacity positions: close the gaps a chunk with fewer records than candidates leaves behind
+        uint64_t dense = 0, at = 0;
+        for (uint32_t ci = 0; ci < b.n_chunks; ++ci)
+        {
+            const uint64_t nc = b.chunk_n[ci];
+            if (dense != at && nc)
+            {
+                CUDA_TRY(c, b.d_rec_tmp.ensure(nc * sizeof(fsb_record)));
+                for (int m = 0; m < nfiles; ++m)
+                {
+                    CUDA_TRY(c, cudaMemcpyAsync(b.d_rec_tmp.p, b.d_rec[m].as<fsb_record>() + at, nc * sizeof(fsb_record), cudaMemcpyDeviceToDevice, st));
+                    CUDA_TRY(c, cudaMemcpyAsync(b.d_rec[m].as<fsb_record>() + dense, b.d_rec_tmp.p, nc * sizeof(fsb_record), cudaMemcpyDeviceToDevice, st));
+                }
+            }
+            dense += nc; at += b.chunk_cap[ci];
+        }
+        return stage_finalize(c, b, st);
+    }
+    return FSB_OK;
+}
+
+// Stage, first enqueue step: the host->device copies of a group of chunks on `st`.  With record tables from the caller the
+// rest follows at once (stage_finalize on `st_check`, which waits for the copies); chunks handed over as text alone
+// (records == NULL) are parsed on the device first (parse_enqueue_count here, then stage_advance until b.parse_state is 0).
+// The batch's input buffers must not be in use.  `split` = sub-batches of whole chunks the kernels will run as.  The pipeline
+// keeps its copy stream free of kernels, so that the next sub-batch's text follows at once.
+int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, cudaStream_t st_check, uint32_t split, bool profile = false)
+{
+    b.staged = false; b.ran = false; b.parse_state = 0;
+    b.split = split; b.profile_check = profile;
+    const int nfiles = c->dp.paired ? 2 : 1;
+    const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(kMaxChunksPerBatch, 1ull << (32 - c->dp.key_bits));
+    if (n_chunks == 0) return fail(c, FSB_ERR_PARAM, "fsb_stage: no chunks");
+    if (n_chunks > max_chunks) return fail(c, FSB_ERR_PARAM, "fsb_stage: too many chunks in one batch for this signature length (max " + std::to_string(max_chunks) + ")");
+
+    b.n_chunks = n_chunks;
+    b.device_parse = chunks[0].records[0] == nullptr && chunks[0].text[0] != nullptr;
+    size_t text_bytes[2] = {kTextPad, kTextPad};
+    for (int m = 0; m < 2; ++m) { b.chunk_text_base[m].assign(n_chunks, 0); b.chunk_text_size[m].assign(n_chunks, 0); }
+    b.chunk_n.assign(n_chunks, 0);
+    uint64_t n = 0;
+    for (uint32_t ci = 0; ci < n_chunks; ++ci)
+    {
+        const fsb_chunk& ch = chunks[ci];
+        for (int m = 0; m < nfiles; ++m)
+        {
+            if (b.device_parse ? (ch.records[m] != nullptr || (ch.text_size[m] && !ch.text[m])) : (ch.n_records && (!ch.text[m] || !ch.records[m])))
+                return fail(c, FSB_ERR_PARAM, b.device_parse ? "fsb_stage: chunks without record tables (device-side parse) and chunks with them cannot be mixed" : "fsb_stage: null text/records");
+            if (ch.text_size[m] >= 0xFFFFFFFFull) return fail(c, FSB_ERR_INPUT, "fsb_stage: chunk text must be < 4 GiB (32-bit record offsets)");
+            b.chunk_text_base[m][ci] = text_bytes[m];
+            b.chunk_text_size[m][ci] = ch.text_size[m];
+            text_bytes[m] = align_up(text_bytes[m] + ch.text_size[m] + kTextPad, 256);
+        }
+        if (!b.device_parse) { b.chunk_n[ci] = ch.n_records; n += ch.n_records; }
+    }
+    if (n > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
+
+    uint64_t h2d = 0;
+    for (int m = 0; m < nfiles; ++m)
+    {
+        CUDA_TRY(c, b.d_text[m].ensure(text_bytes[m] + kTextPad, &st));      // padding between chunks is over-read by aligned window copies: keep it defined
+        if (!b.device_parse) CUDA_TRY(c, b.d_rec[m].ensure((n + 1) * sizeof(fsb_record)));
+        uint64_t first = 0;
+        for (uint32_t ci = 0; ci < n_chunks; ++ci)
+        {
+            const fsb_chunk& ch = chunks[ci];
+            if (ch.text_size[m])
+                CUDA_TRY(c, cudaMemcpyAsync(b.d_text[m].as<uint8_t>() + b.chunk_text_base[m][ci], ch.text[m], ch.text_size[m], cudaMemcpyHostToDevice, st));
+            h2d += ch.text_size[m];
+            if (!b.device_parse && ch.n_records)
+            {
+                CUDA_TRY(c, cudaMemcpyAsync(b.d_rec[m].as<fsb_record>() + first, ch.records[m], ch.n_records * sizeof(fsb_record), cudaMemcpyHostToDevice, st));
+                h2d += ch.n_records * sizeof(fsb_record);
+                first += ch.n_records;
+            }
+        }
+    }
     b.h2d_bytes = h2d;
     c->stats.h2d_bytes += h2d;
-    return FSB_OK;
+    if (st_check != st)
+    {
+        CUDA_TRY(c, cudaEventRecord(b.ev_h2d, st));
+        CUDA_TRY(c, cudaStreamWaitEvent(st_check, b.ev_h2d, 0));
+    }
+    b.st_check = st_check;
+    if (b.device_parse) return parse_enqueue_count(c, b, chunks, st_check);
+    return stage_finalize(c, b, st_check);
 }
 
 // Stage, step 2 (after everything stage_enqueue put on its stream has completed): reject contract
@@ -809,6 +987,15 @@ int fetch_enqueue(fsb_ctx* c, Batch& b, HostOut& h, cudaStream_t st)
                                             cudaMemcpyDeviceToHost, st));
         d2h += nb * sizeof(fsb_bin_descriptor);
     }
+    if (c->keep_records && b.device_parse)
+    {
+        for (int m = 0; m < (c->dp.paired ? 2 : 1); ++m)
+        {
+            CUDA_TRY(c, h.rec[m].ensure((n + 1) * sizeof(fsb_record)));
+            if (n) CUDA_TRY(c, cudaMemcpyAsync(h.rec[m].p, b.d_rec[m].p, n * sizeof(fsb_record), cudaMemcpyDeviceToHost, st));
+            d2h += n * sizeof(fsb_record);
+        }
+    }
     if (c->per_read)
     {
         CUDA_TRY(c, h.sig.ensure((n + 1) * 4));
@@ -916,7 +1103,7 @@ extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fs
     for (Batch& b : c->batch)
     {
         if (cudaEventCreateWithFlags(&b.ev_h2d, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b.ev_chk, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&b.ev_run, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b.ev_run, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b.ev_parse, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&b.ev_d2h, cudaEventDisableTiming) != cudaSuccess)
         {
             fsb_destroy(c);
@@ -945,6 +1132,9 @@ extern "C" void fsb_destroy(fsb_ctx* c)
         b.h_stage_stats.release(); b.h_chunk_sums.release();
         if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
         if (b.ev_chk) cudaEventDestroy(b.ev_chk);
+        if (b.ev_parse) cudaEventDestroy(b.ev_parse);
+        b.d_segs.release(); b.d_tile_count.release(); b.d_tile_prefix.release(); b.d_line_start.release(); b.d_parse_res.release(); b.d_seg_ends.release(); b.d_rec_tmp.release(); b.d_parse_scan_tmp.release();
+        b.h_seg_ends.release(); b.h_parse_res.release();
         if (b.ev_run) cudaEventDestroy(b.ev_run);
         if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);
     }
@@ -959,7 +1149,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     for (HostOut* h : c->host)
     {
         if (!h) continue;
-        PinBuf* pin[] = {&h->out[0], &h->out[1], &h->out[2], &h->out[3], &h->desc, &h->summary, &h->sig, &h->info};
+        PinBuf* pin[] = {&h->out[0], &h->out[1], &h->out[2], &h->out[3], &h->desc, &h->summary, &h->sig, &h->info, &h->rec[0], &h->rec[1]};
         for (PinBuf* q : pin) q->release();
         delete h;
     }
@@ -981,6 +1171,8 @@ extern "C" int fsb_set_option(fsb_ctx* c, int option, int64_t value)
     case FSB_OPT_K4_BLOCK_TILES: c->k4_tiles_per_block = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FSB_OK;
     case FSB_OPT_BLOCK_GRIDS_ALWAYS: c->block_grids_always = value != 0; return FSB_OK;
     case FSB_OPT_FUSED_LAYOUT: c->fused_layout = value != 0; return FSB_OK;
+    case FSB_OPT_KEEP_COMMENTS: c->keep_comments = value != 0; return FSB_OK;
+    case FSB_OPT_KEEP_RECORDS: c->keep_records = value != 0; return FSB_OK;
     }
     return fail(c, FSB_ERR_PARAM, "unknown option");
 }
@@ -1038,6 +1230,7 @@ extern "C" int fsb_stage(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_chunks)
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // nothing may still be using the batch's buffers
     Batch& b = c->batch[0];
     int rc = stage_enqueue(c, b, chunks, n_chunks, c->stream, c->stream, c->run_split, c->profile);
+    while (rc == FSB_OK && b.parse_state) rc = stage_advance(c, b, c->stream);      // device-side parse: two more steps, each sized by the one before
     if (rc != FSB_OK) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // pageable user buffers must outlive the copies; the statistics are back
     return stage_complete(c, b);
@@ -1070,6 +1263,28 @@ extern "C" int fsb_fetch(fsb_ctx* c, fsb_block* blocks, uint32_t n_blocks)
     return FSB_OK;
 }
 
+extern "C" int fsb_get_records(fsb_ctx* c, uint32_t chunk, int mate, fsb_record* dst, uint64_t capacity, uint64_t* n_records)
+{
+    if (!c || !n_records || mate < 0 || mate > 1 || (mate == 1 && !c->dp.paired)) return FSB_ERR_PARAM;
+    *n_records = 0;
+    if (chunk < c->rec_index.size() && c->rec_index[chunk].host[mate])
+    {   // tables copied back by the last fsb_bin_chunks call
+        const fsb_ctx::RecRef& rr = c->rec_index[chunk];
+        *n_records = rr.n;
+        if (rr.n > capacity || (rr.n && !dst)) return fail(c, FSB_ERR_PARAM, "fsb_get_records: destination too small");
+        if (rr.n) std::memcpy(dst, rr.host[mate], rr.n * sizeof(fsb_record));
+        return FSB_OK;
+    }
+    Batch& b = c->batch[0];
+    if (!b.staged || !b.device_parse || chunk >= b.n_chunks) return fail(c, FSB_ERR_STATE, "fsb_get_records: no device-side parse result for this chunk");
+    const uint64_t first = b.chunk_first_rec[chunk], n = b.chunk_first_rec[chunk + 1] - first;
+    *n_records = n;
+    if (n > capacity || (n && !dst)) return fail(c, FSB_ERR_PARAM, "fsb_get_records: destination too small");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (n) CUDA_TRY(c, cudaMemcpy(dst, b.d_rec[mate].as<fsb_record>() + first, n * sizeof(fsb_record), cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
 // ---- host buffers in, host blocks out ----------------------------------------------------------------------------
 // The chunk list is cut into sub-batches of at least sub_batch_records records (whole chunks) which
 // run as a pipeline over three sets of device buffers:
@@ -1093,12 +1308,14 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         uint64_t recs = 0;
         for (uint32_t ci = 0; ci < n_chunks; ++ci)
         {
-            if (ci > first.back() && (recs >= c->sub_batch_records || ci - first.back() >= max_chunks || recs + chunks[ci].n_records > kMaxBatchRecords))
+            const uint64_t est = chunks[ci].records[0] ? chunks[ci].n_records : chunks[ci].text_size[0] / 8u;       // at most a record per 8 bytes
+            if (ci > first.back() && (recs >= c->sub_batch_records || ci - first.back() >= max_chunks || recs + est > kMaxBatchRecords))
             {
                 first.push_back(ci);
                 recs = 0;
             }
-            recs += chunks[ci].n_records;
+            // (chunks to be parsed on the device: about one record per 250 bytes of text)
+            recs += chunks[ci].records[0] ? chunks[ci].n_records : chunks[ci].text_size[0] / 250u;
         }
         first.push_back(n_chunks);
     }
@@ -1126,14 +1343,24 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         // the batch object is reused three sub-batches later: describe the blocks now (the pointers are final,
         // the bytes arrive before the call returns)
         fill_blocks(c, b, *c->host[g], blocks + first[g]);
+        if (c->keep_records && b.device_parse)
+            for (uint32_t ci = 0; ci < b.n_chunks; ++ci)
+            {
+                fsb_ctx::RecRef& rr = c->rec_index[first[g] + ci];
+                rr.n = b.chunk_first_rec[ci + 1] - b.chunk_first_rec[ci];
+                for (int m = 0; m < 2; ++m) rr.host[m] = c->host[g]->rec[m].p ? c->host[g]->rec[m].as<fsb_record>() + b.chunk_first_rec[ci] : nullptr;
+            }
         return FSB_OK;
     };
+    c->rec_index.assign(c->keep_records ? n_chunks : 0, fsb_ctx::RecRef{{nullptr, nullptr}, 0});
 
     for (uint32_t g = 0; g < std::min(G, kAhead) && rc == FSB_OK; ++g)
         rc = stage_enqueue(c, set_of(g), chunks + first[g], first[g + 1] - first[g], c->s_h2d, c->s_chk, 1);
     for (uint32_t g = 0; g < G && rc == FSB_OK; ++g)
     {
         Batch& b = set_of(g);
+        while (rc == FSB_OK && b.parse_state) rc = stage_advance(c, b, c->s_chk);     // device-side parse: the steps behind the copy
+        if (rc != FSB_OK) break;
         if (cudaEventSynchronize(b.ev_chk) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy to the device failed"); break; }    // text on the device, check results on the host
         if (g >= kSets && cudaEventSynchronize(b.ev_d2h) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy from the device failed"); break; }   // result buffers of g-3 are free
         if ((rc = stage_complete(c, b)) != FSB_OK) break;

@@ -13,6 +13,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -116,14 +117,21 @@ extern "C" int fsh_reader_next(fsh_reader* r, uint8_t* buf1, uint64_t* size1, ui
     uint8_t* buf[2] = {buf1, buf2};
     uint64_t have[2] = {0, 0};
     int64_t got[2] = {0, 0}, want[2] = {0, 0};
-    for (int m = 0; m < nf; ++m)
+    auto fill = [&](int m)
     {
         have[m] = r->carry[m].size();
         if (have[m]) std::memcpy(buf[m], r->carry[m].data(), have[m]);
         r->carry[m].clear();
         want[m] = (int64_t)(r->block - have[m]);
         got[m] = r->in[m].read(buf[m] + have[m], (uint64_t)want[m]);
+    };
+    if (nf == 2)
+    {   // the two mate files are independent streams: read them side by side
+        std::thread other(fill, 1);
+        fill(0);
+        other.join();
     }
+    else fill(0);
     uint64_t out[2] = {have[0], have[1]};
     const bool full = got[0] == want[0] && (!r->paired || got[1] == want[1]);
     if (full && (r->paired || got[0] > 0))

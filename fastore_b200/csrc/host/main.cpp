@@ -35,7 +35,7 @@ struct Args
 {
     std::vector<std::string> in, out;
     fsh_bin_config cfg{};
-    int gpus = 0, parsers = 4, threads = 1, workers = 2, per_call = 0;
+    int gpus = 0, parsers = 4, threads = 1, workers = 2, per_call = 0;   // (the memchr parser does ~2 GB/s per thread: four keep up with the reader)
     bool verbose = false, gz = false;
 };
 
@@ -159,9 +159,20 @@ int main(int argc, const char** argv)
     Pipeline P;
     const int nbuf = NWK * K + a.parsers + 1;
     std::vector<Chunk> chunks((size_t)nbuf);
-    // the chunk buffers (pinned host memory) are allocated when the reader first uses them: a short input pins a few, a long one
-    // all of them, and pinning -- about a second per few GB -- overlaps with the parsers and the GPU workers
-    for (Chunk& c : chunks) P.pool.insert(P.pool.begin(), &c);
+    // the chunk buffers (pinned host memory) come from a thread of their own, one after the other, until the input is read: a short
+    // input pins a few, a long one all of them, and pinning -- about a second per few GB -- overlaps with reading, parsing and binning
+    std::thread t_alloc([&] {
+        for (Chunk& c : chunks)
+        {
+            { std::lock_guard<std::mutex> l(P.mu); if (P.read_done || P.failed) break; }
+            bool have = true;
+            for (int m = 0; m < (pe ? 2 : 1) && have; ++m) { c.text[m] = (uint8_t*)fsb_host_alloc(a.cfg.fastq_block_size + 64); have = c.text[m] != nullptr; }
+            if (!have) { P.fail("cannot allocate pinned chunk buffers"); break; }
+            std::lock_guard<std::mutex> l(P.mu);
+            P.pool.insert(P.pool.begin(), &c);                      // the reader takes from the back: buffers that came back are reused first
+            P.cv.notify_all();
+        }
+    });
 
     // ---- reader: one chunk after the other, exactly the reference's cuts ------------------------------------
     std::thread t_read([&] {
@@ -174,10 +185,6 @@ int main(int argc, const char** argv)
                 if (P.failed) break;
                 c = P.pool.back(); P.pool.pop_back();               // last in, first out: buffers that exist are reused before new ones are pinned
             }
-            bool have = true;
-            for (int m = 0; m < (pe ? 2 : 1) && have; ++m)
-                if (!c->text[m]) { c->text[m] = (uint8_t*)fsb_host_alloc(a.cfg.fastq_block_size + 64); have = c->text[m] != nullptr; }
-            if (!have) { P.fail("cannot allocate pinned chunk buffers"); break; }
             const int rc = fsh_reader_next(reader, c->text[0], &c->size[0], c->text[1], &c->size[1]);
             std::unique_lock<std::mutex> l(P.mu);
             if (rc <= 0) { P.pool.push_back(c); P.read_done = true; if (rc < 0 && !P.failed) { P.failed = true; P.error = "read error"; } P.cv.notify_all(); break; }
@@ -303,12 +310,12 @@ int main(int argc, const char** argv)
         });
 
     t_read.join();
+    t_alloc.join();
     const double t_read_done = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (auto& t : t_parse) t.join();
     for (auto& t : t_gpu) t.join();
     fsh_reader_close(reader);
     const int wrc = fsh_writer_close(writer);
-    for (Chunk& c : chunks) { for (uint8_t* p : c.text) if (p) fsb_host_free(p); if (c.titles) fsh_titles_free(c.titles); }
     if (P.failed) { std::fprintf(stderr, "Error: %s\n", P.error.c_str()); return -1; }
     if (wrc != FSB_OK) { std::fprintf(stderr, "Error: %s\n", fsh_last_error()); return -1; }
     if (a.verbose)
@@ -318,5 +325,8 @@ int main(int argc, const char** argv)
         std::fprintf(stderr, "\n%llu records in %llu chunks on %d GPU(s) x %d worker(s): %.2f s, %.0f records/s\n", (unsigned long long)total_records.load(),
                      (unsigned long long)P.next_write, G, a.workers, s, total_records.load() / std::max(s, 1e-9));
     }
-    return 0;
+    // The bin files are closed.  Un-pinning gigabytes of chunk buffers and tearing the CUDA context down takes seconds and gives
+    // nothing back that the exit of the process does not: leave at once.
+    std::fflush(nullptr);
+    std::_Exit(0);
 }

@@ -90,6 +90,12 @@ typedef struct fsb_record {
 
 /*
  * One input chunk (FastqChunk / FastqChunkCollectionSE,PE: FastqRecord.h:336-391).
+ *
+ * Device-side parse: a chunk handed over with records[0] == NULL (and records[1] == NULL) is parsed by the library on the
+ * GPU -- SingleFastqRecordParser::ReadNextRecord's rules (FastqParser.cpp:118-165: LF / CR LF / CR line ends, parsing stops
+ * silently at the first malformed record; PE keeps min(n1, n2) pairs, :527) -- and n_records is ignored on input; the record
+ * count comes back in fsb_block.n_records and the tables can be read with fsb_get_records.  All chunks of one call are
+ * handed over the same way.
  * SE uses index 0 only.  PE: text[0]/records[0] are mate 1, text[1]/records[1] mate 2, record i
  * of both tables forms pair i; the two mates of a pair must have equal length (the reference
  * ASSERTs this, FastqRecord.h:87,192) and only mate 1's header is kept (FastqPacker.cpp:854).
@@ -154,7 +160,10 @@ enum {
     FSB_OPT_K1_BLOCK_BATCHES = 6, /* warp batches per warp of a K1 block when sub-batches share the GPU (0: persistent grid) */
     FSB_OPT_K4_BLOCK_TILES = 7,   /* tiles per K4 block in that mode (0: persistent grid) */
     FSB_OPT_BLOCK_GRIDS_ALWAYS = 8, /* use those block sizes for unsplit runs as well */
-    FSB_OPT_FUSED_LAYOUT = 9      /* 1 (default): batches whose reads all have one length take the one-scan layout; 0: always the general kernels */
+    FSB_OPT_FUSED_LAYOUT = 9,     /* 1 (default): batches whose reads all have one length take the one-scan layout; 0: always the general kernels */
+    FSB_OPT_KEEP_RECORDS = 11,    /* device-side parse inside fsb_bin_chunks: also copy the record tables to the host (fsb_get_records) */
+    FSB_OPT_KEEP_COMMENTS = 10    /* device-side parse (chunks without record tables): 1 (default) keeps the whole title, 0 cuts it at the first
+                                     space like the reference's -C (HeadersCompressionParams::preserveComments, FastqParser.cpp:148-155) */
 };
 
 /* pipeline stages reported by fsb_stage_times (order of execution inside fsb_run) */
@@ -216,6 +225,15 @@ int fsb_stage(fsb_ctx* ctx, const fsb_chunk* chunks, uint32_t n_chunks);
 int fsb_run(fsb_ctx* ctx);
 int fsb_fetch(fsb_ctx* ctx, fsb_block* blocks, uint32_t n_blocks);
 int fsb_sync(fsb_ctx* ctx);
+
+/*
+ * Device-side parse only: the record table the library built for chunk `chunk` (index in the last fsb_bin_chunks / fsb_stage
+ * call) and mate `mate`, copied to `dst` (capacity in records; the count is returned in *n_records, FSB_ERR_PARAM if it does
+ * not fit).  For callers that need the tables on the host as well, e.g. for the title statistics of the bin-file footer.
+ * Valid until the next staging call on the context (fsb_bin_chunks: needs FSB_OPT_KEEP_RECORDS, which makes the call copy the
+ * tables back while the batches are in flight).
+ */
+int fsb_get_records(fsb_ctx* ctx, uint32_t chunk, int mate, fsb_record* dst, uint64_t capacity, uint64_t* n_records);
 
 /* Accumulated per-stage device time in milliseconds since the last call (needs FSB_OPT_PROFILE); n_runs counts fsb_run calls. */
 int fsb_stage_times(fsb_ctx* ctx, float* ms, uint32_t n_stages, uint32_t* n_runs);
