@@ -93,6 +93,7 @@ struct Sub
     uint64_t r0 = 0, r1 = 0;                     // records [r0, r1)
     uint64_t nb_max = 0, bin_off = 0;            // bound of the number of bins; first entry in the batch's descriptor array
     uint64_t tile_off = 0, n_tiles = 0;          // its sort tiles in the batch's tile table
+    uint64_t ctile_off = 0;                      // its table "sort tiles in front of every chunk" (chunks + 1 entries)
     size_t out_off[4] = {0, 0, 0, 0}, out_cap[4] = {0, 0, 0, 0};   // its region of the batch's output streams (bytes, 64-byte aligned)
     size_t meta_first = 0;                       // index of its relative first-record table in the device chunk tables
 };
@@ -114,6 +115,8 @@ struct Batch
     size_t out_total[4] = {0, 0, 0, 0};          // sum of the sub-batches' regions
 
     std::vector<SortTile> tiles_host;            // sort tiles of all sub-batches (must outlive its async copy)
+    std::vector<uint32_t> ctiles_host;           // per sub-batch: sort tiles in front of every chunk
+    DevBuf d_chunk_tiles;
     // ---- device-side parse (chunks handed over without record tables; parse.cuh) ------------------------------------------
     bool device_parse = false;
     int parse_state = 0;                         // 0: nothing pending (tables from the host, or parse finished); 1: line ends counted; 2: records built
@@ -179,6 +182,7 @@ struct fsb_ctx
     uint32_t k1_batches_per_warp = 32, k4_tiles_per_block = 64;   // block granularity of K1 / K4 when sub-batches share the GPU (0: persistent)
     bool block_grids_always = false;             // use that granularity for unsplit runs too (measurement only)
     bool fused_layout = true;                    // batches of one read length take the one-scan layout (FSB_OPT_FUSED_LAYOUT, measurement only)
+    bool fused_hist = true;                      // K1 / every scatter pass count the digits of the next radix pass (FSB_OPT_FUSED_HIST, measurement only)
     bool keep_records = false;                   // device-side parse inside fsb_bin_chunks: copy the record tables back too (FSB_OPT_KEEP_RECORDS)
     struct RecRef { const fsb_record* host[2]; uint64_t n; };
     std::vector<RecRef> rec_index;               // per chunk of the last fsb_bin_chunks call (device-side parse + keep_records)
@@ -238,7 +242,7 @@ BatchView sub_view(const Batch& b, const Sub& s)
 
 template <int NW, int Q>
 cudaError_t launch_ingest_q(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t R, uint32_t* keys, unsigned long long* cards,
-                            uint32_t* slots, uint32_t* sig, uint32_t* info, cudaStream_t st)
+                            uint32_t* slots, uint32_t* sig, uint32_t* info, const SortSeed& seed, cudaStream_t st)
 {
     IngestPlan pl = make_ingest_plan<NW>(P, G, max_head);
     pl.batches_per_warp = R;
@@ -254,16 +258,16 @@ cudaError_t launch_ingest_q(const BatchView& B, const DeviceParams& P, const Slo
     // persistent: as many blocks as fit on the device at once; otherwise every block owns R warp batches per warp
     const unsigned blocks = R ? (unsigned)std::max<uint64_t>(1, (need + R - 1) / R)
                               : (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sms * (uint64_t)std::max(per_sm, 1)));
-    ingest_kernel<NW, Q><<<blocks, pl.warps * 32, pl.total_bytes, st>>>(B, P, G, pl, keys, cards, slots, sig, info);
+    ingest_kernel<NW, Q><<<blocks, pl.warps * 32, pl.total_bytes, st>>>(B, P, G, pl, keys, cards, slots, sig, info, seed);
     return cudaGetLastError();
 }
 template <int NW>
 cudaError_t launch_ingest(const BatchView& B, const DeviceParams& P, const SlotGeom& G, uint32_t max_head, uint32_t R, uint32_t* keys, unsigned long long* cards,
-                          uint32_t* slots, uint32_t* sig, uint32_t* info, cudaStream_t st)
+                          uint32_t* slots, uint32_t* sig, uint32_t* info, const SortSeed& seed, cudaStream_t st)
 {
-    if (P.qua_bits == 6) return launch_ingest_q<NW, 6>(B, P, G, max_head, R, keys, cards, slots, sig, info, st);
-    if (P.qua_bits == 3) return launch_ingest_q<NW, 3>(B, P, G, max_head, R, keys, cards, slots, sig, info, st);
-    return launch_ingest_q<NW, 1>(B, P, G, max_head, R, keys, cards, slots, sig, info, st);
+    if (P.qua_bits == 6) return launch_ingest_q<NW, 6>(B, P, G, max_head, R, keys, cards, slots, sig, info, seed, st);
+    if (P.qua_bits == 3) return launch_ingest_q<NW, 3>(B, P, G, max_head, R, keys, cards, slots, sig, info, seed, st);
+    return launch_ingest_q<NW, 1>(B, P, G, max_head, R, keys, cards, slots, sig, info, seed, st);
 }
 
 cudaError_t launch_place(const PlaceArgs& pa, const Placement& pm, uint32_t max_len, uint32_t max_head, uint32_t R, bool tables_ready, cudaStream_t st, int* launches)
@@ -381,13 +385,15 @@ int stage_finalize(fsb_ctx* c, Batch& b, cudaStream_t st)
     CUDA_TRY(c, cudaMemcpyAsync(b.d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     h2d += meta.size() * sizeof(uint64_t);
     // sort tiles: every tile lies inside one chunk (scan_sort.cuh)
-    b.tiles_host.clear();
+    b.tiles_host.clear(); b.ctiles_host.clear();
     for (Sub& sb : b.subs)
     {
         sb.tile_off = b.tiles_host.size();
+        sb.ctile_off = b.ctiles_host.size();
         uint32_t cblk = 0;
         for (uint32_t ci = sb.c0; ci < sb.c1; ++ci)
         {
+            b.ctiles_host.push_back(cblk);
             const uint64_t first = b.chunk_first_rec[ci] - sb.r0, cnt = b.chunk_first_rec[ci + 1] - b.chunk_first_rec[ci];
             const uint32_t nblk = (uint32_t)((cnt + kSortTile - 1) / kSortTile);
             for (uint32_t k = 0; k < nblk; ++k)
@@ -400,8 +406,11 @@ int stage_finalize(fsb_ctx* c, Batch& b, cudaStream_t st)
             }
             cblk += nblk;
         }
+        b.ctiles_host.push_back(cblk);
         sb.n_tiles = b.tiles_host.size() - sb.tile_off;
     }
+    CUDA_TRY(c, b.d_chunk_tiles.ensure((b.ctiles_host.size() + 1) * 4));
+    CUDA_TRY(c, cudaMemcpyAsync(b.d_chunk_tiles.p, b.ctiles_host.data(), b.ctiles_host.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(c, b.d_sort_tiles.ensure((b.tiles_host.size() + 1) * sizeof(SortTile)));
     if (!b.tiles_host.empty())
         CUDA_TRY(c, cudaMemcpyAsync(b.d_sort_tiles.p, b.tiles_host.data(), b.tiles_host.size() * sizeof(SortTile), cudaMemcpyHostToDevice, st));
@@ -783,6 +792,18 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
     const unsigned tpb = 256;
     const unsigned grid_n = (unsigned)std::max<uint64_t>(1, (n + tpb - 1) / tpb);
 
+    // digit plan of the sort; K1 counts the first pass's digits while it writes the keys (scan_sort.cuh, ingest.cuh: SortSeed)
+    int width[8];
+    const int passes = sort_plan((int)c->dp.key_bits, width);
+    const bool seeded = c->fused_hist && n && sub_chunks <= 32u;
+    SortSeed seed{nullptr, nullptr, 0, 0, (uint32_t)kSortTile};
+    if (seeded)
+    {
+        seed.counts = L.d_counts.as<uint32_t>();
+        seed.chunk_tiles = b.d_chunk_tiles.as<uint32_t>() + sb.ctile_off;
+        seed.radix = 1u << width[0]; seed.mask = seed.radix - 1u;
+        CUDA_TRY(c, cudaMemsetAsync(L.d_counts.p, 0, (size_t)seed.radix * sb.n_tiles * 4, st));
+    }
     // ---- K1: ingest (signature + prepacked slots) -----------------------------------------------------------
     if (n)
     {
@@ -795,14 +816,14 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
         cudaError_t e = cudaSuccess;
         switch ((b.max_len + 31) / 32)              // words of 32 bases per mate
         {
-        case 0: case 1: e = launch_ingest<1>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
-        case 2: e = launch_ingest<2>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
-        case 3: e = launch_ingest<3>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
-        case 4: e = launch_ingest<4>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
-        case 5: e = launch_ingest<5>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
-        case 6: e = launch_ingest<6>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
-        case 7: e = launch_ingest<7>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
-        default: e = launch_ingest<8>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, st); break;
+        case 0: case 1: e = launch_ingest<1>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
+        case 2: e = launch_ingest<2>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
+        case 3: e = launch_ingest<3>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
+        case 4: e = launch_ingest<4>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
+        case 5: e = launch_ingest<5>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
+        case 6: e = launch_ingest<6>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
+        case 7: e = launch_ingest<7>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
+        default: e = launch_ingest<8>(B, P, G, b.max_head, R1, keys, cards, slots, sig, info, seed, st); break;
         }
         CUDA_TRY(c, e);
         launches++;
@@ -815,18 +836,26 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
     {
         const SortTile* tiles = b.d_sort_tiles.as<SortTile>() + sb.tile_off;
         const uint32_t nblocks = (uint32_t)sb.n_tiles;
-        int width[8];
-        const int passes = sort_plan((int)c->dp.key_bits, width);
         int shift = 0;
+        bool counted = seeded;                                       // the pass's digit counts are in d_counts already
         for (int pass = 0; pass < passes; ++pass)
         {
             const uint32_t radix = 1u << width[pass], mask = radix - 1u;
             const uint64_t ncounts = (uint64_t)radix * nblocks;
-            sort_histogram<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), tiles, shift, mask, radix, L.d_counts.as<uint32_t>());
-            launches++;
+            if (!counted)
+            {
+                sort_histogram<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), tiles, shift, mask, radix, L.d_counts.as<uint32_t>());
+                launches++;
+            }
             launches += exclusive_scan<uint32_t, uint32_t>(L.d_counts.as<uint32_t>(), ncounts, L.d_counts_scan.as<uint32_t>(), L.d_scan_tmp.as<uint32_t>(), st);
+            // the scatter counts the digits of the next pass: a key's destination is the tile it will be read from
+            const bool count_next = c->fused_hist && pass + 1 < passes;
+            const uint32_t next_radix = count_next ? (1u << width[pass + 1]) : 0u;
+            if (count_next) CUDA_TRY(c, cudaMemsetAsync(L.d_counts.p, 0, (size_t)next_radix * nblocks * 4, st));
             sort_scatter<<<nblocks, kSortThreads, 0, st>>>(L.d_keys[cur].as<uint32_t>(), L.d_cards[cur].as<unsigned long long>(), tiles, shift, mask, radix,
-                                                            L.d_counts_scan.as<uint32_t>(), L.d_keys[cur ^ 1].as<uint32_t>(), L.d_cards[cur ^ 1].as<unsigned long long>());
+                                                            L.d_counts_scan.as<uint32_t>(), L.d_keys[cur ^ 1].as<uint32_t>(), L.d_cards[cur ^ 1].as<unsigned long long>(),
+                                                            count_next ? L.d_counts.as<uint32_t>() : nullptr, shift + width[pass], next_radix ? next_radix - 1u : 0u, next_radix);
+            counted = count_next;
             shift += width[pass];
             launches++;
             cur ^= 1;
@@ -1126,7 +1155,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     for (cudaEvent_t e : c->ev_check) if (e) cudaEventDestroy(e);
     for (Batch& b : c->batch)
     {
-        DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_chunk_sums, &b.d_sort_tiles, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
+        DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_chunk_sums, &b.d_sort_tiles, &b.d_chunk_tiles, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
                          &b.d_desc, &b.d_summary, &b.d_sig, &b.d_info};
         for (DevBuf* d : dev) d->release();
         b.h_stage_stats.release(); b.h_chunk_sums.release();
@@ -1173,6 +1202,7 @@ extern "C" int fsb_set_option(fsb_ctx* c, int option, int64_t value)
     case FSB_OPT_FUSED_LAYOUT: c->fused_layout = value != 0; return FSB_OK;
     case FSB_OPT_KEEP_COMMENTS: c->keep_comments = value != 0; return FSB_OK;
     case FSB_OPT_KEEP_RECORDS: c->keep_records = value != 0; return FSB_OK;
+    case FSB_OPT_FUSED_HIST: c->fused_hist = value != 0; return FSB_OK;
     }
     return fail(c, FSB_ERR_PARAM, "unknown option");
 }

@@ -161,10 +161,18 @@ int main(int argc, const char** argv)
     std::vector<Chunk> chunks((size_t)nbuf);
     // the chunk buffers (pinned host memory) come from a thread of their own, one after the other, until the input is read: a short
     // input pins a few, a long one all of them, and pinning -- about a second per few GB -- overlaps with reading, parsing and binning
+    std::atomic<int> contexts_ready{0};
     std::thread t_alloc([&] {
+        bool first = true;
         for (Chunk& c : chunks)
         {
-            { std::lock_guard<std::mutex> l(P.mu); if (P.read_done || P.failed) break; }
+            {   // the first chunk's buffers at once (the reader starts on them); the others once the CUDA contexts exist -- pinning
+                // memory and creating a context fight over the same driver lock, and the contexts are what the first result waits for
+                std::unique_lock<std::mutex> l(P.mu);
+                if (!first) P.cv.wait(l, [&] { return contexts_ready.load() >= NWK || P.read_done || P.failed; });
+                if (P.read_done || P.failed) break;
+            }
+            first = false;
             bool have = true;
             for (int m = 0; m < (pe ? 2 : 1) && have; ++m) { c.text[m] = (uint8_t*)fsb_host_alloc(a.cfg.fastq_block_size + 64); have = c.text[m] != nullptr; }
             if (!have) { P.fail("cannot allocate pinned chunk buffers"); break; }
@@ -244,6 +252,7 @@ int main(int argc, const char** argv)
             if (fsb_create(&a.cfg.params, w % G, nullptr, &ctx) != FSB_OK) { P.fail(std::string("GPU ") + std::to_string(w % G) + ": " + fsb_last_error(nullptr)); return; }
             auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
             if (a.verbose) std::fprintf(stderr, "[%.2f s] worker %d: context on GPU %d ready\n", since(), w, w % G);
+            { std::lock_guard<std::mutex> l(P.mu); contexts_ready++; P.cv.notify_all(); }
             std::vector<Chunk*> mine;
             std::vector<fsb_chunk> in;
             bool stop = false;

@@ -78,6 +78,16 @@ template <int NW> constexpr uint32_t win_slot_bytes() { return win_pieces<NW>() 
 #endif
 constexpr uint32_t kIngestMaxWarps = FSB_K1_WARPS;      // warps per block (launch bound)
 
+// The first radix pass of the sort needs the digit counts of every sort tile (scan_sort.cuh).  K1 knows every key the moment
+// it writes it, so it counts them itself (one L2 reduction per record) and the pass needs no histogram kernel: counts (zeroed by
+// the caller, null = off) in the layout [chunk][digit][tile of the chunk]; chunk_tiles[c] = sort tiles of the chunks in front of c.
+struct SortSeed
+{
+    uint32_t* counts;
+    const uint32_t* chunk_tiles;     // [n_chunks + 1]
+    uint32_t mask, radix, tile;      // digit mask and radix of the first pass, keys per sort tile
+};
+
 struct IngestPlan
 {
     uint32_t warps;          // warps per block
@@ -204,7 +214,7 @@ __device__ __forceinline__ uint32_t chunk_of(const ChunkTables& T, uint64_t i)
 template <int NW, int Q>
 __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest_kernel(BatchView B, DeviceParams P, SlotGeom G, IngestPlan pl, uint32_t* __restrict__ keys,
                                                                       unsigned long long* __restrict__ cards, uint32_t* __restrict__ slots,
-                                                                      uint32_t* __restrict__ sig_out, uint32_t* __restrict__ info_out)
+                                                                      uint32_t* __restrict__ sig_out, uint32_t* __restrict__ info_out, SortSeed seed)
 {
     constexpr uint32_t SB = win_slot_bytes<NW>();
     extern __shared__ uint4 ingest_smem[];
@@ -229,6 +239,9 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
     T.n_chunks = B.n_chunks; T.first = B.chunk_first_rec; T.text_base[0] = B.chunk_text_base[0]; T.text_base[1] = B.chunk_text_base[1];
     const bool chunks_in_lanes = B.n_chunks <= 32u;
     uint64_t c_first = ~0ull, c_tb0 = 0, c_tb1 = 0;
+    uint32_t c_tiles0 = 0, c_tiles1 = 0;                                              // sort tiles in front of the lane's chunk / up to its end
+    const bool seed_sort = seed.counts != nullptr && chunks_in_lanes;
+    if (seed_sort && lane < B.n_chunks) { c_tiles0 = seed.chunk_tiles[lane]; c_tiles1 = seed.chunk_tiles[lane + 1]; }
     if (chunks_in_lanes && lane < B.n_chunks)
     {
         c_first = B.chunk_first_rec[lane];
@@ -387,6 +400,14 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
             keys[i] = (cur.ch << P.key_bits) | sig;
             cards[i] = card_make((uint32_t)i, inf, lenA, lenB, H);
             if (sig_out) { sig_out[i] = sig; info_out[i] = inf; }
+        }
+        if (seed_sort)
+        {   // the record's sort tile: its place inside its chunk / keys per tile (the chunk's tables sit in lane cur.ch)
+            const uint32_t ch = live ? cur.ch : 0u;
+            const uint64_t first = __shfl_sync(0xFFFFFFFFu, c_first, ch);
+            const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, c_tiles0, ch), t1 = __shfl_sync(0xFFFFFFFFu, c_tiles1, ch);
+            if (live && m == 0)
+                atomicAdd(&seed.counts[(uint64_t)seed.radix * t0 + (uint64_t)(sig & seed.mask) * (t1 - t0) + (uint32_t)((i - first) / seed.tile)], 1u);
         }
         cp_async_wait_all();
         __syncwarp();

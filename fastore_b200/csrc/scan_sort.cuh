@@ -305,11 +305,14 @@ __global__ void __launch_bounds__(kSortThreads) sort_histogram(const uint32_t* _
 }
 
 // offsets: exclusive scan of counts (same layout).  The 64-bit values are the records' cards (core.cuh).
+// next_counts (may be null): the count table of the NEXT pass, zeroed by the caller -- a key's destination tells the tile it
+// will sit in, so the next pass needs no histogram kernel of its own (one L2 reduction per key, spread over tiles x digits counters).
 // (launch bound of 4 blocks per SM: the kernel lives on scattered stores in flight, not on registers)
 __global__ void __launch_bounds__(kSortThreads, 4) sort_scatter(const uint32_t* __restrict__ keys_in, const unsigned long long* __restrict__ vals_in,
                                                               const SortTile* __restrict__ tiles, int shift, uint32_t mask, uint32_t radix,
                                                               const uint32_t* __restrict__ offsets, uint32_t* __restrict__ keys_out,
-                                                              unsigned long long* __restrict__ vals_out)
+                                                              unsigned long long* __restrict__ vals_out,
+                                                              uint32_t* __restrict__ next_counts, int next_shift, uint32_t next_mask, uint32_t next_radix)
 {
     __shared__ uint32_t warp_hist[kSortThreads / 32][kMaxRadix];   // 16 KB
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -360,6 +363,12 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_scatter(const uint32_t* 
             const uint32_t dst = warp_hist[warp][d] + rank[i];
             keys_out[dst] = key[i];
             vals_out[dst] = vals_in[t.first + local];
+            if (next_counts)
+            {   // the chunk's keys stay inside the chunk: destination - first key of the chunk = place inside the chunk
+                const uint32_t chunk_first = t.first - t.blk * (uint32_t)kSortTile;
+                const uint32_t nt = (dst - chunk_first) / (uint32_t)kSortTile;
+                atomicAdd(&next_counts[(uint64_t)next_radix * t.cblk + (uint64_t)((key[i] >> next_shift) & next_mask) * t.nblk + nt], 1u);
+            }
         }
     }
 }
