@@ -536,8 +536,8 @@ def main():
     ap.add_argument("--total-records", "--total-pairs", "--pairs", dest="total_records", type=int, default=0,
                     help="override the workload's record count (c3: total over all ranks; others: per rank)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--run-split", type=int, default=int(os.environ.get("FSB_BENCH_SPLIT", "1")),
-                    help="sub-batches fsb_run overlaps on two streams in the timed resident steps (1 = one pass)")
+    ap.add_argument("--run-split", type=int, default=int(os.environ.get("FSB_BENCH_SPLIT", "2")),
+                    help="sub-batches fsb_run overlaps on two streams in the timed resident steps (FSB_OPT_RUN_SPLIT; 1 = one pass on one stream)")
     ap.add_argument("--parity-chunks", type=int, default=1, help="whole chunks per rank compared with the compiled reference (1 or 2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

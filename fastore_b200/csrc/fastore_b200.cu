@@ -182,7 +182,8 @@ struct fsb_ctx
     uint32_t k1_batches_per_warp = 32, k4_tiles_per_block = 64;   // block granularity of K1 / K4 when sub-batches share the GPU (0: persistent)
     bool block_grids_always = false;             // use that granularity for unsplit runs too (measurement only)
     bool fused_layout = true;                    // batches of one read length take the one-scan layout (FSB_OPT_FUSED_LAYOUT, measurement only)
-    bool fused_hist = true;                      // K1 / every scatter pass count the digits of the next radix pass (FSB_OPT_FUSED_HIST, measurement only)
+    bool fused_hist = false;                     // K1 / every scatter pass count the digits of the next radix pass (FSB_OPT_FUSED_HIST).  Measured SLOWER than the
+                                                 // histogram kernels (sort 0.79 vs 0.44 ms per 10M pairs, r02l): 10M scattered L2 reductions cost more than re-reading the keys
     bool keep_records = false;                   // device-side parse inside fsb_bin_chunks: copy the record tables back too (FSB_OPT_KEEP_RECORDS)
     struct RecRef { const fsb_record* host[2]; uint64_t n; };
     std::vector<RecRef> rec_index;               // per chunk of the last fsb_bin_chunks call (device-side parse + keep_records)

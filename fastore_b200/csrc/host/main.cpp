@@ -12,6 +12,7 @@
 // them in arrival order, which is why only its -t1 output is reproducible).  Extra options:
 //     -G<n>  GPUs to use (default: all sm_100 devices)      -P<n>  parser threads (default 4)
 //     -W<n>  workers (contexts) per GPU (default 2: one worker's copies overlap the other's kernels)
+//     -D     parse the chunks on the GPU as well (the record tables come back for the title statistics; no parser threads)
 //     -K<n>  chunks a worker hands to one fsb_bin_chunks call when that many are already parsed
 //            (default 256 MiB / block size, 1..16: small -b chunks are batched into full-size launches)
 #include <algorithm>
@@ -36,7 +37,7 @@ struct Args
     std::vector<std::string> in, out;
     fsh_bin_config cfg{};
     int gpus = 0, parsers = 4, threads = 1, workers = 2, per_call = 0;   // (the memchr parser does ~2 GB/s per thread: four keep up with the reader)
-    bool verbose = false, gz = false;
+    bool verbose = false, gz = false, device_parse = false;
 };
 
 void split_list(const char* s, std::vector<std::string>& out)                  // main.cpp:198-232
@@ -88,6 +89,7 @@ bool parse_args(int argc, const char** argv, Args& a)
         case 'I': p.quality_offset = 64; break;
         case 'G': a.gpus = (int)v; break;
         case 'P': a.parsers = (int)std::max(1L, v); break;
+        case 'D': a.device_parse = true; break;
         case 'W': a.workers = (int)std::min(8L, std::max(1L, v)); break;
         case 'K': a.per_call = (int)std::min(64L, std::max(1L, v)); break;
         }
@@ -130,7 +132,7 @@ struct Pipeline
 int main(int argc, const char** argv)
 {
     Args a;
-    if (argc < 2 || !parse_args(argc, argv, a)) { std::fprintf(stderr, "usage: fastore_bin_b200 e -i<files> -o<out> [-z] [-H] [-C] [-q<0-2>] [-w<n>] [-I] [-p<n>] [-s<n>] [-m<n>] [-b<MB>] [-G<gpus>] [-W<workers per GPU>] [-K<chunks per call>] [-P<parser threads>] [-v]\n"); return -1; }
+    if (argc < 2 || !parse_args(argc, argv, a)) { std::fprintf(stderr, "usage: fastore_bin_b200 e -i<files> -o<out> [-z] [-H] [-C] [-q<0-2>] [-w<n>] [-I] [-p<n>] [-s<n>] [-m<n>] [-b<MB>] [-G<gpus>] [-W<workers per GPU>] [-K<chunks per call>] [-P<parser threads>] [-D] [-v]\n"); return -1; }
     const bool pe = a.cfg.params.paired_end != 0;
     const int ndev = fsb_device_count();
     if (ndev == 0) { std::fprintf(stderr, "Error: no sm_100 GPU available (this tool has no CPU fallback)\n"); return -1; }
@@ -216,6 +218,15 @@ int main(int argc, const char** argv)
                     c = P.raw.front(); P.raw.erase(P.raw.begin());
                 }
                 c->bad = false;
+                if (a.device_parse)
+                {   // the library parses the text on the GPU: hand the chunk on as it is
+                    for (int m = 0; m < 2; ++m) c->rec[m].clear();
+                    if (c->titles) { fsh_titles_free(c->titles); c->titles = nullptr; }
+                    std::lock_guard<std::mutex> l(P.mu);
+                    P.parsed[c->idx] = c;
+                    P.cv.notify_all();
+                    continue;
+                }
                 for (int m = 0; m < (pe ? 2 : 1); ++m)
                 {
                     c->rec[m].resize(fsh_max_records(c->text[m], c->size[m]));
@@ -250,6 +261,7 @@ int main(int argc, const char** argv)
         t_gpu.emplace_back([&, w] {
             fsb_ctx* ctx = nullptr;
             if (fsb_create(&a.cfg.params, w % G, nullptr, &ctx) != FSB_OK) { P.fail(std::string("GPU ") + std::to_string(w % G) + ": " + fsb_last_error(nullptr)); return; }
+            if (a.device_parse) { fsb_set_option(ctx, FSB_OPT_KEEP_RECORDS, 1); fsb_set_option(ctx, FSB_OPT_KEEP_COMMENTS, a.cfg.keep_comments ? 1 : 0); }
             auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
             if (a.verbose) std::fprintf(stderr, "[%.2f s] worker %d: context on GPU %d ready\n", since(), w, w % G);
             { std::lock_guard<std::mutex> l(P.mu); contexts_ready++; P.cv.notify_all(); }
@@ -272,11 +284,11 @@ int main(int argc, const char** argv)
                 {
                     Chunk* c = mine[q];
                     if (c->bad) { P.fail(c->err); stop = true; break; }
-                    if (c->rec[0].empty()) continue;
+                    if (a.device_parse ? c->size[0] == 0 : c->rec[0].empty()) continue;
                     fsb_chunk ch;
                     std::memset(&ch, 0, sizeof(ch));
-                    for (int m = 0; m < (pe ? 2 : 1); ++m) { ch.text[m] = c->text[m]; ch.text_size[m] = c->size[m]; ch.records[m] = c->rec[m].data(); }
-                    ch.n_records = c->rec[0].size();
+                    for (int m = 0; m < (pe ? 2 : 1); ++m) { ch.text[m] = c->text[m]; ch.text_size[m] = c->size[m]; ch.records[m] = a.device_parse ? nullptr : c->rec[m].data(); }
+                    ch.n_records = a.device_parse ? 0 : c->rec[0].size();
                     slot[q] = in.size();
                     in.push_back(ch);
                 }
@@ -286,6 +298,28 @@ int main(int argc, const char** argv)
                 if (!in.empty() && fsb_bin_chunks(ctx, in.data(), (uint32_t)in.size(), out.data()) != FSB_OK)
                 { P.fail(std::string("chunk ") + std::to_string(idx) + ": " + fsb_last_error(ctx)); break; }
                 if (a.verbose) std::fprintf(stderr, "[%.2f s] worker %d: chunks %llu.. (%zu in one call) binned in %.3f s\n", since(), w, (unsigned long long)idx, in.size(), since() - t_call);
+                if (a.device_parse)
+                {   // the tables the device built, for the title statistics (FastqRawBlockStats of the chunk) -- here, outside the writer turn
+                    for (size_t q = 0; q < mine.size() && !stop; ++q)
+                    {
+                        Chunk* c = mine[q];
+                        if (slot[q] == (size_t)-1) continue;
+                        const uint64_t n = out[slot[q]].n_records;
+                        for (int m = 0; m < (pe ? 2 : 1) && !stop; ++m)
+                        {
+                            c->rec[m].resize(n);
+                            uint64_t got = 0;
+                            if (fsb_get_records(ctx, (uint32_t)slot[q], m, c->rec[m].data(), n, &got) != FSB_OK || got != n)
+                            { P.fail(std::string("chunk ") + std::to_string(c->idx) + ": " + fsb_last_error(ctx)); stop = true; }
+                        }
+                        if (!stop && a.cfg.params.reads_have_headers)
+                        {
+                            c->titles = fsh_titles_new();
+                            for (int m = 0; m < (pe ? 2 : 1); ++m) fsh_titles_add(c->titles, c->text[m], c->rec[m].data(), c->rec[m].size());
+                        }
+                    }
+                    if (stop) break;
+                }
                 for (size_t q = 0; q < mine.size() && !stop; ++q, idx += (uint64_t)NWK)
                 {
                     Chunk* c = mine[q];

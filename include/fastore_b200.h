@@ -161,7 +161,8 @@ enum {
     FSB_OPT_K4_BLOCK_TILES = 7,   /* tiles per K4 block in that mode (0: persistent grid) */
     FSB_OPT_BLOCK_GRIDS_ALWAYS = 8, /* use those block sizes for unsplit runs as well */
     FSB_OPT_FUSED_LAYOUT = 9,     /* 1 (default): batches whose reads all have one length take the one-scan layout; 0: always the general kernels */
-    FSB_OPT_FUSED_HIST = 12,      /* 1 (default): K1 and every scatter pass count the digits of the next radix pass; 0: histogram kernels */
+    FSB_OPT_FUSED_HIST = 12,      /* 1: K1 and every scatter pass count the digits of the next radix pass; 0 (default): histogram kernels -- the fused
+                                     form measured slower on B200 (one scattered L2 reduction per record and pass) */
     FSB_OPT_KEEP_RECORDS = 11,    /* device-side parse inside fsb_bin_chunks: also copy the record tables to the host (fsb_get_records) */
     FSB_OPT_KEEP_COMMENTS = 10    /* device-side parse (chunks without record tables): 1 (default) keeps the whole title, 0 cuts it at the first
                                      space like the reference's -C (HeadersCompressionParams::preserveComments, FastqParser.cpp:148-155) */

@@ -54,10 +54,11 @@ def run_reference_bin(files, out_prefix: Path, flags: dict, threads: int = 1):
     subprocess.run(cmd, check=True, capture_output=True, timeout=600)
 
 
-def run_cli(files, out_prefix: Path, flags: dict, gpus: int = 1, workers: int | None = None, per_call: int | None = None):
+def run_cli(files, out_prefix: Path, flags: dict, gpus: int = 1, workers: int | None = None, per_call: int | None = None, device_parse: bool = False):
     cmd = [str(CLI), "e", "-i" + " ".join(str(f) for f in files), f"-o{out_prefix}", f"-G{gpus}"] + flags_to_args(flags)
     if workers is not None: cmd.append(f"-W{workers}")
     if per_call is not None: cmd.append(f"-K{per_call}")
+    if device_parse: cmd.append("-D")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     return r

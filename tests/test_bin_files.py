@@ -37,6 +37,17 @@ def test_cli_reproduces_reference_files(tmp_path, name, gen, flags):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,gen,flags", CASES, ids=[c[0] for c in CASES])
+def test_cli_with_device_side_parse_reproduces_reference_files(tmp_path, name, gen, flags):
+    """-D: the chunks go to the library as text alone and are parsed on the GPU (parse.cuh); the tables come back for the title
+    statistics.  Same files as `fastore_bin e -t1`, CRLF and -C included."""
+    files = BF.write_fastq(tmp_path, name, gen["n"], gen["L"], gen["paired"], gen["seed"], **{k: v for k, v in gen.items() if k not in ("n", "L", "paired", "seed")})
+    BF.run_reference_bin(files, tmp_path / "ref", flags)
+    BF.run_cli(files, tmp_path / "ours", flags, device_parse=True, per_call=3)
+    BF.assert_bin_files_equal(tmp_path / "ours", tmp_path / "ref", flags.get("headers", True))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("paired", [False, True])
 def test_reference_decoder_reads_our_files(tmp_path, paired):
     """Mode C: the reference's `fastore_bin d` reconstructs the input records from the CLI's bin files."""
