@@ -112,7 +112,7 @@ assert RECORD_DTYPE.itemsize == 16 and BIN_DESC_DTYPE.itemsize == 64
 # every symbol include/fastore_b200.h declares (checked by tests/test_abi.py)
 C_ABI_SYMBOLS = (
     "fsb_create", "fsb_destroy", "fsb_last_error", "fsb_set_option", "fsb_bin_chunks", "fsb_stage", "fsb_run",
-    "fsb_fetch", "fsb_sync", "fsb_stage_times", "fsb_get_stats", "fsb_host_alloc", "fsb_host_free", "fsb_device_count", "fsb_get_records",
+    "fsb_fetch", "fsb_sync", "fsb_stage_times", "fsb_get_stats", "fsb_host_alloc", "fsb_host_free", "fsb_device_count", "fsb_get_records", "fsb_find_new_minimizers",
 )
 
 _host = None
@@ -206,6 +206,8 @@ def cuda_lib() -> C.CDLL:
         lib.fsb_host_free.argtypes = [C.c_void_p]
         lib.fsb_get_records.restype = C.c_int
         lib.fsb_get_records.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        lib.fsb_find_new_minimizers.restype = C.c_int
+        lib.fsb_find_new_minimizers.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.fsb_device_count.restype = C.c_int
         lib.fsb_device_count.argtypes = []
         _cuda = lib

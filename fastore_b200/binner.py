@@ -126,6 +126,15 @@ class GpuBinner:
         self._check(self._lib.fsb_get_records(self._ctx, chunk, mate, N.np_ptr(out) if out.size else None, out.size, C.byref(n)))
         return out
 
+    def find_new_minimizers(self, text: np.ndarray, records: np.ndarray, cur_signature: int, signature_parity: int):
+        """DnaRebalancer::FindNewMinimizer for a table of reads (fastore_rebin's scan): (signature, info) arrays."""
+        n = records.shape[0]
+        sig = np.zeros(n, dtype=np.uint32)
+        info = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.fsb_find_new_minimizers(self._ctx, N.np_ptr(text), text.size, N.np_ptr(records), n, cur_signature, signature_parity,
+                                                      N.np_ptr(sig), N.np_ptr(info)))
+        return sig, info
+
     def stage_times(self, n_stages: int = 4):
         """Per-stage device milliseconds since the last call: the four stages of fsb_run, plus "check" (the input-check
         kernels of fsb_stage) when n_stages is 5."""

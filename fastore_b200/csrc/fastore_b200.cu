@@ -32,6 +32,7 @@
 #include "place.cuh"
 #include "layout_fused.cuh"
 #include "parse.cuh"
+#include "rebin_sig.cuh"
 
 using namespace fsb;
 
@@ -1314,6 +1315,69 @@ extern "C" int fsb_get_records(fsb_ctx* c, uint32_t chunk, int mate, fsb_record*
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (n) CUDA_TRY(c, cudaMemcpy(dst, b.d_rec[mate].as<fsb_record>() + first, n * sizeof(fsb_record), cudaMemcpyDeviceToHost));
     return FSB_OK;
+}
+
+// ---- fastore_rebin's signature scan ---------------------------------------------------------------------------
+namespace {
+template <int NW>
+void launch_new_minimizer(const uint8_t* text, const fsb_record* rec, uint64_t n, const DeviceParams& P, uint32_t cur, uint32_t* sig, uint32_t* info, cudaStream_t st)
+{
+    find_new_minimizer_kernel<NW><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(text, rec, n, P, cur, sig, info);
+}
+} // namespace
+
+extern "C" int fsb_find_new_minimizers(fsb_ctx* c, const uint8_t* text, uint64_t text_size, const fsb_record* records, uint64_t n_records,
+                                       uint32_t cur_signature, uint32_t signature_parity, uint32_t* signature, uint32_t* info)
+{
+    if (!c || (n_records && (!text || !records || !signature || !info))) return FSB_ERR_PARAM;
+    if (signature_parity < 2 || (signature_parity & (signature_parity - 1)) != 0 || signature_parity > c->dp.nbin)
+        return fail(c, FSB_ERR_PARAM, "fsb_find_new_minimizers: signature_parity must be a power of two in [2, 4^k]");
+    if (text_size >= 0xFFFFFFFFull) return fail(c, FSB_ERR_INPUT, "fsb_find_new_minimizers: text must be < 4 GiB (32-bit record offsets)");
+    if (n_records == 0) return FSB_OK;
+    uint32_t max_len = 0;
+    for (uint64_t i = 0; i < n_records; ++i)
+    {
+        const fsb_record& r = records[i];
+        if (r.seq_len < 1 || r.seq_len > 255 || (uint64_t)r.seq_off + r.seq_len > text_size)
+            return fail(c, FSB_ERR_INPUT, "fsb_find_new_minimizers: record " + std::to_string(i) + " violates the input contract (length 1..255, offsets inside the text)");
+        max_len = std::max<uint32_t>(max_len, r.seq_len);
+    }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    fsb_ctx::Lane& L = c->lane[0];                                   // scratch: the lane's key arrays take the results
+    DevBuf d_text, d_rec;
+    CUDA_TRY(c, d_text.ensure(text_size + 2 * kTextPad, &st));
+    int rc = FSB_OK;
+    auto done = [&](int code) { d_text.release(); d_rec.release(); return code; };
+    if (d_rec.ensure(n_records * sizeof(fsb_record)) != cudaSuccess) return done(fail(c, FSB_ERR_NOMEM, "out of device memory"));
+    if (ensure_shared(st, L.d_keys[0], (n_records + 1) * 4) != cudaSuccess || ensure_shared(st, L.d_keys[1], (n_records + 1) * 4) != cudaSuccess)
+        return done(fail(c, FSB_ERR_NOMEM, "out of device memory"));
+    DeviceParams P = c->dp;
+    uint32_t lg = 0;
+    while ((1u << lg) < signature_parity) ++lg;
+    P.cutoff_bits = std::max(P.cutoff_bits, lg);                     // m % divisor == 0: the low log2(divisor) bits are zero
+    cudaMemcpyAsync(d_text.as<uint8_t>(), text, text_size, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_rec.p, records, n_records * sizeof(fsb_record), cudaMemcpyHostToDevice, st);
+    uint32_t* d_sig = L.d_keys[0].as<uint32_t>();
+    uint32_t* d_info = L.d_keys[1].as<uint32_t>();
+    switch ((max_len + 31) / 32)
+    {
+    case 0: case 1: launch_new_minimizer<1>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    case 2: launch_new_minimizer<2>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    case 3: launch_new_minimizer<3>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    case 4: launch_new_minimizer<4>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    case 5: launch_new_minimizer<5>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    case 6: launch_new_minimizer<6>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    case 7: launch_new_minimizer<7>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    default: launch_new_minimizer<8>(d_text.as<uint8_t>(), d_rec.as<fsb_record>(), n_records, P, cur_signature, d_sig, d_info, st); break;
+    }
+    c->stats.kernel_launches++;
+    cudaMemcpyAsync(signature, d_sig, n_records * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(info, d_info, n_records * 4, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(c, FSB_ERR_CUDA, std::string("fsb_find_new_minimizers: ") + cudaGetErrorString(e));
+    return done(rc);
 }
 
 // ---- host buffers in, host blocks out ----------------------------------------------------------------------------

@@ -161,28 +161,11 @@ int main(int argc, const char** argv)
     Pipeline P;
     const int nbuf = NWK * K + a.parsers + 1;
     std::vector<Chunk> chunks((size_t)nbuf);
-    // the chunk buffers (pinned host memory) come from a thread of their own, one after the other, until the input is read: a short
-    // input pins a few, a long one all of them, and pinning -- about a second per few GB -- overlaps with reading, parsing and binning
+    // the chunk buffers (pinned host memory) are allocated when the reader first uses them: a short input pins a few, a long one all
+    // of them.  (A thread of its own for the pinning was measured slower: it fights the context creation and the workers' first
+    // allocations for the driver lock, r02j / r02k.)
+    for (Chunk& c : chunks) P.pool.insert(P.pool.begin(), &c);
     std::atomic<int> contexts_ready{0};
-    std::thread t_alloc([&] {
-        bool first = true;
-        for (Chunk& c : chunks)
-        {
-            {   // the first chunk's buffers at once (the reader starts on them); the others once the CUDA contexts exist -- pinning
-                // memory and creating a context fight over the same driver lock, and the contexts are what the first result waits for
-                std::unique_lock<std::mutex> l(P.mu);
-                if (!first) P.cv.wait(l, [&] { return contexts_ready.load() >= NWK || P.read_done || P.failed; });
-                if (P.read_done || P.failed) break;
-            }
-            first = false;
-            bool have = true;
-            for (int m = 0; m < (pe ? 2 : 1) && have; ++m) { c.text[m] = (uint8_t*)fsb_host_alloc(a.cfg.fastq_block_size + 64); have = c.text[m] != nullptr; }
-            if (!have) { P.fail("cannot allocate pinned chunk buffers"); break; }
-            std::lock_guard<std::mutex> l(P.mu);
-            P.pool.insert(P.pool.begin(), &c);                      // the reader takes from the back: buffers that came back are reused first
-            P.cv.notify_all();
-        }
-    });
 
     // ---- reader: one chunk after the other, exactly the reference's cuts ------------------------------------
     std::thread t_read([&] {
@@ -195,6 +178,10 @@ int main(int argc, const char** argv)
                 if (P.failed) break;
                 c = P.pool.back(); P.pool.pop_back();               // last in, first out: buffers that exist are reused before new ones are pinned
             }
+            bool have = true;
+            for (int m = 0; m < (pe ? 2 : 1) && have; ++m)
+                if (!c->text[m]) { c->text[m] = (uint8_t*)fsb_host_alloc(a.cfg.fastq_block_size + 64); have = c->text[m] != nullptr; }
+            if (!have) { P.fail("cannot allocate pinned chunk buffers"); break; }
             const int rc = fsh_reader_next(reader, c->text[0], &c->size[0], c->text[1], &c->size[1]);
             std::unique_lock<std::mutex> l(P.mu);
             if (rc <= 0) { P.pool.push_back(c); P.read_done = true; if (rc < 0 && !P.failed) { P.failed = true; P.error = "read error"; } P.cv.notify_all(); break; }
@@ -353,7 +340,6 @@ int main(int argc, const char** argv)
         });
 
     t_read.join();
-    t_alloc.join();
     const double t_read_done = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (auto& t : t_parse) t.join();
     for (auto& t : t_gpu) t.join();

@@ -293,4 +293,46 @@ FSB_HD void select_pe(const StrandMin& f1, const StrandMin& f2, const StrandMin&
     info = pos | flags;
 }
 
+// fastore_rebin's second scan (DnaRebalancer::FindMinimizerHR, fastore_rebin/DnaRebalancer.cpp:570-601) is FindMinimizer with two more
+// conditions per k-mer: m != curSignature and m % divisor == 0 (divisor a power of two: the low log2(divisor) bits are zero -- the
+// same test as signatureMaskCutoffBits, taken by candidate_masks).  This removes the positions whose k-mer IS `cur` from both
+// candidate sets: symbol d of the forward k-mer at p is base p+d, symbol d of the reverse-strand k-mer at forward position p is the
+// complement of base p+k-1-d.
+template <int NW>
+FSB_HD void exclude_signature(const BV<NW>& H, const BV<NW>& Lo, uint32_t k, uint32_t cur, BV<NW>& Cf, BV<NW>& Cr)
+{
+    BV<NW> eqF = Cf, eqR = Cr;                                   // positions that still equal `cur` on every symbol looked at so far
+    for (uint32_t d = 0; d < k; ++d)
+    {
+        const uint32_t sym = (cur >> (2u * (k - 1u - d))) & 3u, hi = sym >> 1, lo = sym & 1u;
+        const BV<NW> hf = bv_shr(H, d), lf = bv_shr(Lo, d);
+        const BV<NW> hr = bv_shr(H, k - 1u - d), lr = bv_shr(Lo, k - 1u - d);
+#pragma unroll
+        for (int j = 0; j < NW; ++j)
+        {
+            eqF.w[j] &= (hi ? hf.w[j] : ~hf.w[j]) & (lo ? lf.w[j] : ~lf.w[j]);
+            eqR.w[j] &= (hi ? ~hr.w[j] : hr.w[j]) & (lo ? ~lr.w[j] : lr.w[j]);      // complement: 3 - base
+        }
+    }
+    Cf = bv_andn(Cf, eqF);
+    Cr = bv_andn(Cr, eqR);
+}
+
+// FindNewMinimizer (DnaRebalancer.cpp:604-616) of one read from its bit planes: FindMinimizerHR on the read and on its reverse
+// complement, the reverse strand only if its signature is strictly smaller.  P.cutoff_bits must already include log2(divisor).
+template <int NW>
+FSB_HD void plane_new_minimizer(const BV<NW>& H, const BV<NW>& Lo, const BV<NW>& Nm, uint32_t L, const DeviceParams& P, uint32_t cur,
+                                uint32_t& sig, uint32_t& info)
+{
+    const uint32_t nN = bv_popc(Nm);
+    BV<NW> Cf, Cr;
+    candidate_masks<NW>(H, Lo, Nm, L, P, Cf, Cr);
+    exclude_signature<NW>(H, Lo, P.k, cur, Cf, Cr);
+    StrandMin f, r;
+    f.sig = r.sig = P.nbin; f.pos = r.pos = 0;
+    if (!(nN >= L / 3) && (bv_any(Cf) || bv_any(Cr))) descend_joint<NW>(Cf, Cr, H, Lo, L, P, f, r);
+    select_se(f, r, nN, P, sig, info);
+    info &= (FSB_INFO_POS_MASK | FSB_INFO_REVERSE);
+}
+
 } // namespace fsb

@@ -237,6 +237,18 @@ int fsb_sync(fsb_ctx* ctx);
  */
 int fsb_get_records(fsb_ctx* ctx, uint32_t chunk, int mate, fsb_record* dst, uint64_t capacity, uint64_t* n_records);
 
+/*
+ * fastore_rebin's signature scan: DnaRebalancer::FindNewMinimizer (fastore_rebin/DnaRebalancer.cpp:570-616) for a
+ * table of reads.  For every read: the smallest valid signature on either strand that differs from `cur_signature` and is a
+ * multiple of `signature_parity` (a power of two, fastore_rebin -p), with the context's signature_len / skip_zone_len; ties go
+ * to the forward strand.  signature[i] = 4^k when there is none (or the read has >= len/3 N); info[i] = position in the chosen
+ * orientation | FSB_INFO_REVERSE.  records: seq_off / seq_len into `text` (the other fields are ignored).  Host buffers in and
+ * out, synchronous.  The variant that admits only signatures present in the input bin file (BinBalanceParameters::
+ * validBinSignatures filled from the file, RebinModule.cpp:62-68) is not covered.
+ */
+int fsb_find_new_minimizers(fsb_ctx* ctx, const uint8_t* text, uint64_t text_size, const fsb_record* records, uint64_t n_records,
+                            uint32_t cur_signature, uint32_t signature_parity, uint32_t* signature, uint32_t* info);
+
 /* Accumulated per-stage device time in milliseconds since the last call (needs FSB_OPT_PROFILE); n_runs counts fsb_run calls. */
 int fsb_stage_times(fsb_ctx* ctx, float* ms, uint32_t n_stages, uint32_t* n_runs);
 

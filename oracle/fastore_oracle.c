@@ -110,6 +110,37 @@ void orc_find_minimizer(const fsb_params* p, const uint8_t* seq, uint32_t len, u
     *sig = minimizer; *pos_out = pos;
 }
 
+/* DnaRebalancer::FindMinimizerHR (fastore_rebin/DnaRebalancer.cpp:570-601): FindMinimizer with m != curSignature and
+ * m % curDivisor == 0 added (binParams.validBinSignatures is all true by default, RebinModule.cpp:72) */
+static void find_minimizer_hr(const fsb_params* p, const uint8_t* seq, uint32_t len, uint32_t cur, uint32_t divisor, uint32_t* sig, uint32_t* pos_out)
+{
+    const uint32_t nbin = nbin_value(p);
+    uint32_t minimizer = nbin;                                              /* maxLongMinimValue = 4^k */
+    uint32_t pos = 0;
+    const int32_t end = (int32_t)len - (int32_t)p->signature_len - (int32_t)p->skip_zone_len;  /* :580 */
+    for (int32_t i = 0; i < end; ++i) {
+        uint32_t m = compute_minimizer(p, seq + i, p->signature_len);
+        if (m < minimizer && m != cur && m % divisor == 0 && orc_signature_valid(p, m)) { minimizer = m; pos = (uint32_t)i; }  /* :584-592 */
+    }
+    uint32_t ncount = 0;
+    for (uint32_t i = 0; i < len; ++i) ncount += (seq[i] == 'N');
+    if (minimizer >= nbin || ncount >= len / 3) { *sig = nbin; *pos_out = 0; return; }          /* :597-599 */
+    *sig = minimizer; *pos_out = pos;
+}
+
+static uint8_t rc_code(uint8_t c);
+/* DnaRebalancer::FindNewMinimizer (:604-616): the scan on the read and on its reverse complement; the reverse strand only
+ * if its signature is strictly smaller */
+void orc_find_new_minimizer(const fsb_params* p, const uint8_t* seq, uint32_t len, uint32_t cur, uint32_t divisor, uint32_t* sig, uint32_t* pos, uint32_t* is_rev)
+{
+    uint8_t rc[256];
+    for (uint32_t i = 0; i < len; ++i) rc[len - 1 - i] = rc_code(seq[i]);
+    uint32_t fs, fp, rs, rp;
+    find_minimizer_hr(p, seq, len, cur, divisor, &fs, &fp);
+    find_minimizer_hr(p, rc, len, cur, divisor, &rs, &rp);
+    if (fs > rs) { *sig = rs; *pos = rp; *is_rev = 1; } else { *sig = fs; *pos = fp; *is_rev = 0; }
+}
+
 /* FastqRecord::ComputeRC (FastqRecord.h:80-111): reverse-complement of the whole span, quality
  * reversed alongside. */
 static uint8_t rc_code(uint8_t c)

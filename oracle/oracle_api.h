@@ -46,6 +46,11 @@ double orc_time_bin_chunk(const fsb_params* p, const fsb_chunk* chunk, int threa
 int  ref_bin_chunk(const fsb_params* p, const fsb_chunk* chunk, orc_block* out);
 void ref_block_free(orc_block* b);
 void ref_find_minimizer(const fsb_params* p, const uint8_t* seq, uint32_t len, uint32_t* sig, uint32_t* pos);
+
+/* DnaRebalancer::FindNewMinimizer (fastore_rebin/DnaRebalancer.cpp:570-616) of one read: the port, and the reference's own
+ * member function called through oracle/ref_rebin_harness.cpp (oracle/_ref/libfastore_ref_rebin.so) */
+void orc_find_new_minimizer(const fsb_params* p, const uint8_t* seq, uint32_t len, uint32_t cur, uint32_t divisor, uint32_t* sig, uint32_t* pos, uint32_t* is_rev);
+void refrebin_find_new_minimizer(const fsb_params* p, const uint8_t* seq, uint32_t len, uint32_t cur, uint32_t divisor, uint32_t* sig, uint32_t* pos, uint32_t* is_rev);
 double ref_time_bin_chunk(const fsb_params* p, const fsb_chunk* chunk, int threads, int reps);
 
 #ifdef __cplusplus

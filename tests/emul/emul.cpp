@@ -394,3 +394,43 @@ extern "C" long emul_layout_fused(const fsb_params* p, const fsb_chunk* ch, uint
     for (size_t b = 0; b < want_desc.size(); ++b) if (std::memcmp(&got_desc[b], &want_desc[b], sizeof(fsb_bin_descriptor)) != 0) bad++;
     return bad;
 }
+
+// ================================================================================================
+// fastore_rebin's scan (sig_core.cuh: plane_new_minimizer) "thread" by "thread" over a record table.
+template <int NW>
+static void run_new_minimizers(const DeviceParams& P, const uint8_t* text, uint64_t text_size, const fsb_record* rec, uint64_t n, uint32_t cur, uint32_t* sig, uint32_t* info)
+{
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        uint32_t slot[(2 * NW + 1) * 4 + 4];
+        stage_slot<NW>(text, text_size, rec[i].seq_off, rec[i].seq_len, slot);
+        const uint32_t a = rec[i].seq_off & 15u;
+        BV<NW> H, Lo, Nm;
+        mate_planes<NW>(slot + (a >> 2), 8 * (a & 3u), rec[i].seq_len, H, Lo, Nm);
+        plane_new_minimizer<NW>(H, Lo, Nm, rec[i].seq_len, P, cur, sig[i], info[i]);
+    }
+}
+
+extern "C" int emul_new_minimizers(const fsb_params* p, const uint8_t* text, uint64_t text_size, const fsb_record* rec, uint64_t n, uint32_t cur, uint32_t divisor,
+                                   uint32_t* sig, uint32_t* info)
+{
+    DeviceParams P = make_device_params(*p);
+    uint32_t lg = 0;
+    while ((1u << lg) < divisor) ++lg;
+    P.cutoff_bits = std::max(P.cutoff_bits, lg);
+    uint32_t maxL = 1;
+    for (uint64_t i = 0; i < n; ++i) maxL = std::max<uint32_t>(maxL, rec[i].seq_len);
+    switch ((maxL + 31) / 32)
+    {
+    case 1: run_new_minimizers<1>(P, text, text_size, rec, n, cur, sig, info); break;
+    case 2: run_new_minimizers<2>(P, text, text_size, rec, n, cur, sig, info); break;
+    case 3: run_new_minimizers<3>(P, text, text_size, rec, n, cur, sig, info); break;
+    case 4: run_new_minimizers<4>(P, text, text_size, rec, n, cur, sig, info); break;
+    case 5: run_new_minimizers<5>(P, text, text_size, rec, n, cur, sig, info); break;
+    case 6: run_new_minimizers<6>(P, text, text_size, rec, n, cur, sig, info); break;
+    case 7: run_new_minimizers<7>(P, text, text_size, rec, n, cur, sig, info); break;
+    case 8: run_new_minimizers<8>(P, text, text_size, rec, n, cur, sig, info); break;
+    default: return FSB_ERR_INPUT;
+    }
+    return FSB_OK;
+}

@@ -95,3 +95,33 @@ def assert_blocks_equal(a: dict, b: dict, what: str = "", per_read: bool = True)
         if not np.array_equal(a["read_info"], b["read_info"]):
             i = int(np.nonzero(a["read_info"] != b["read_info"])[0][0])
             raise AssertionError(f"{what}: info of read {i}: {a['read_info'][i]:#x} vs {b['read_info'][i]:#x}")
+
+
+REBIN_REF_LIB = ROOT / "oracle" / "_ref" / "libfastore_ref_rebin.so"
+_rebin = {}
+
+
+def find_new_minimizer(kind: str, params: N.FsbParams, seq: bytes, cur: int, divisor: int):
+    """DnaRebalancer::FindNewMinimizer of one read: kind 'orc' (C port) or 'ref' (the reference's member function)."""
+    if kind not in _rebin:
+        lib = C.CDLL(str(PORT_LIB if kind == "orc" else REBIN_REF_LIB))
+        f = getattr(lib, "orc_find_new_minimizer" if kind == "orc" else "refrebin_find_new_minimizer")
+        f.restype = None
+        f.argtypes = [C.POINTER(N.FsbParams), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        _rebin[kind] = f
+    s, p, r = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    buf = np.frombuffer(seq, dtype=np.uint8).copy()
+    _rebin[kind](C.byref(params), N.np_ptr(buf), len(seq), cur, divisor, C.byref(s), C.byref(p), C.byref(r))
+    return s.value, p.value, r.value
+
+
+def new_minimizers_port(params: N.FsbParams, text: np.ndarray, recs: np.ndarray, cur: int, divisor: int):
+    """(signature, info) arrays of the port for a record table, in the C ABI's format (info = pos | FSB_INFO_REVERSE)."""
+    sig = np.zeros(len(recs), dtype=np.uint32)
+    info = np.zeros(len(recs), dtype=np.uint32)
+    raw = text.tobytes()
+    for i, r in enumerate(recs):
+        s, p, rev = find_new_minimizer("orc", params, raw[int(r["seq_off"]): int(r["seq_off"]) + int(r["seq_len"])], cur, divisor)
+        sig[i] = s
+        info[i] = p | (N.FSB_INFO_REVERSE if rev else 0)
+    return sig, info
