@@ -450,11 +450,33 @@ def run_b200_arm(args, w, name):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None       # sampled through both timed regions (resident steps and end-to-end steps)
     st1 = g.stats()
     e2e_value = mates * n_all * e2e_steps / e2e_s
     h2d = (st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps
     d2h = (st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps
+    # the same call with the chunks handed over as text alone: the library parses them on the device (no record tables over PCIe)
+    dp = None
+    if w.get("keep_comments", True) and bool(w["params"].get("reads_have_headers", True)):
+        text_chunks = []
+        for t1, t2, r1, r2 in keep:
+            text_chunks.append(N.make_chunk(t1, None, t2))
+        blocks_c = (N.FsbBlock * len(chunks))()
+        g._check(lib.fsb_bin_chunks(g._ctx, g._chunk_array(text_chunks), len(chunks), blocks_c))     # untimed pass: parse buffers get allocated
+        n_parsed = sum(int(b.n_records) for b in blocks_c)
+        st2 = g.stats()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            blocks_c = (N.FsbBlock * len(chunks))()
+            g._check(lib.fsb_bin_chunks(g._ctx, g._chunk_array(text_chunks), len(chunks), blocks_c))
+        torch.cuda.synchronize()
+        dp_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        st3 = g.stats()
+        dp = {"value": mates * n_all * e2e_steps / dp_s, "unit": UNIT, "ms_per_step": 1e3 * dp_s / e2e_steps,
+              "h2d_bytes_per_step": int((st3["h2d_bytes"] - st2["h2d_bytes"]) // e2e_steps), "records_parsed_equal_tables": bool(n_parsed == n_rank),
+              "what": "fsb_bin_chunks with fsb_chunk.records == NULL: FASTQ text in, parsed on the device (parse.cuh), blocks out"}
+    clocks = sampler.stop() if rank == 0 else None       # sampled through the timed regions (resident steps and end-to-end steps)
 
     # ---- roofline -----------------------------------------------------------------------------------------
     peak, peak_src = load_peaks()
@@ -492,6 +514,7 @@ def run_b200_arm(args, w, name):
                         "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                         "h2d_ms": h2d_ms, "h2d_gbs": h2d_leg_bytes / (h2d_ms / 1e3) / 1e9, "kernel_ms": ms_per_step, "d2h_ms": d2h_ms,
                         "d2h_gbs": d2h_leg_bytes / (d2h_ms / 1e3) / 1e9,
+                        "device_parse": dp,
                         "legs": "h2d_ms = fsb_stage alone (copies + input check), kernel_ms = fsb_run alone, d2h_ms = fsb_fetch alone, per rank shard, "
                                 "max over ranks; ms_per_step = the pipelined fsb_bin_chunks call"},
                 "input_check": {"ms": check_ms, "in_timed_region": "e2e yes (inside fsb_bin_chunks); value no (fsb_stage, before the resident steps)",
