@@ -18,9 +18,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
+
+#include <sys/mman.h>
 
 #include <cuda_runtime.h>
 
@@ -60,6 +65,63 @@ struct DevBuf
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Page-locked host memory.  On the B200 hosts cudaHostAlloc pins at 2.4 GB/s under the driver's lock, while pages the process
+// has already touched are registered at 45 GB/s and touching them costs 7 GB/s (profiles/r02n_pinning.json): a one-shot tool
+// that pins a few GB feels the difference.  So large buffers are anonymous mappings (transparent huge pages where the kernel
+// grants them), touched here and then registered; small ones and FSB_PIN=alloc take cudaHostAlloc.
+struct PinRegistry
+{
+    std::mutex mu;
+    std::unordered_map<void*, size_t> mapped;        // registered mappings: pointer -> mapped bytes
+};
+PinRegistry& pin_registry() { static PinRegistry* r = new PinRegistry; return *r; }      // (never destroyed: frees may come late in exit)
+
+void* pinned_alloc(size_t bytes)
+{
+    static const bool use_register = []() { const char* e = std::getenv("FSB_PIN"); return !(e && std::strcmp(e, "alloc") == 0); }();
+    constexpr size_t kHuge = 2u << 20;
+    if (use_register && bytes >= (8u << 20))
+    {
+        const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
+        void* m = mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m != MAP_FAILED)
+        {
+            // a 2 MB aligned window inside the mapping; what lies in front of it and behind it is given back
+            uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(m) + kHuge - 1) / kHuge * kHuge);
+            if (base != m) munmap(m, (size_t)(base - reinterpret_cast<uint8_t*>(m)));
+            const size_t tail = (size_t)(reinterpret_cast<uint8_t*>(m) + len + kHuge - (base + len));
+            if (tail) munmap(base + len, tail);
+            madvise(base, len, MADV_HUGEPAGE);
+            for (size_t o = 0; o < len; o += 4096) base[o] = 0;                           // fault the pages in outside the driver
+            if (cudaHostRegister(base, len, cudaHostRegisterPortable) == cudaSuccess)
+            {
+                PinRegistry& r = pin_registry();
+                std::lock_guard<std::mutex> l(r.mu);
+                r.mapped[base] = len;
+                return base;
+            }
+            cudaGetLastError();
+            munmap(base, len);
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pinned_free(void* p)
+{
+    if (!p) return;
+    size_t len = 0;
+    {
+        PinRegistry& r = pin_registry();
+        std::lock_guard<std::mutex> l(r.mu);
+        auto it = r.mapped.find(p);
+        if (it != r.mapped.end()) { len = it->second; r.mapped.erase(it); }
+    }
+    if (len) { cudaHostUnregister(p); munmap(p, len); }
+    else cudaFreeHost(p);
+}
+
 struct PinBuf
 {
     void* p = nullptr;
@@ -67,15 +129,30 @@ struct PinBuf
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
+        pinned_free(p);
         p = nullptr; cap = 0;
         const size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = want;
-        return e;
+        p = pinned_alloc(want);
+        if (!p) return cudaErrorMemoryAllocation;
+        cap = want;
+        return cudaSuccess;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release() { pinned_free(p); p = nullptr; cap = 0; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// FSB_TRACE=1: the host-side timeline of fsb_bin_chunks on stderr (ms since the call began)
+struct CallTrace
+{
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    CallTrace() : on(std::getenv("FSB_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what, uint32_t g) const
+    {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::fprintf(stderr, "[fsb %9.3f ms] %-28s sub-batch %u\n", ms, what, g);
+    }
 };
 
 constexpr size_t kTextPad = 64;           // slack around every chunk text: aligned vector loads may over-read
@@ -1211,11 +1288,9 @@ extern "C" int fsb_set_option(fsb_ctx* c, int option, int64_t value)
 
 extern "C" void* fsb_host_alloc(size_t bytes)
 {
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-    return p;
+    return pinned_alloc(bytes);
 }
-extern "C" void fsb_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void fsb_host_free(void* p) { pinned_free(p); }
 
 extern "C" int fsb_sync(fsb_ctx* c)
 {
@@ -1415,12 +1490,14 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         first.push_back(n_chunks);
     }
     const uint32_t G = (uint32_t)first.size() - 1;
+    const CallTrace trace;
     if (!c->s_h2d) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     if (!c->s_d2h) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     if (!c->s_chk) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_chk, cudaStreamNonBlocking));
     constexpr uint32_t kSets = 3, kAhead = 2;
     auto set_of = [&](uint32_t g) -> Batch& { return c->batch[g % kSets]; };
     for (uint32_t g = 0; g < G; ++g) if (!host_out(c, g)) return fail(c, FSB_ERR_NOMEM, "out of host memory");
+    trace.mark("host sets ready", G);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // earlier work on the context (resident interface) is done
     CUDA_TRY(c, cudaStreamSynchronize(c->s_d2h));
 
@@ -1451,19 +1528,24 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
 
     for (uint32_t g = 0; g < std::min(G, kAhead) && rc == FSB_OK; ++g)
         rc = stage_enqueue(c, set_of(g), chunks + first[g], first[g + 1] - first[g], c->s_h2d, c->s_chk, 1);
+    trace.mark("first copies enqueued", 0);
     for (uint32_t g = 0; g < G && rc == FSB_OK; ++g)
     {
         Batch& b = set_of(g);
         while (rc == FSB_OK && b.parse_state) rc = stage_advance(c, b, c->s_chk);     // device-side parse: the steps behind the copy
         if (rc != FSB_OK) break;
+        trace.mark("parsed", g);
         if (cudaEventSynchronize(b.ev_chk) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy to the device failed"); break; }    // text on the device, check results on the host
+        trace.mark("text on the device, checked", g);
         if (g >= kSets && cudaEventSynchronize(b.ev_d2h) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy from the device failed"); break; }   // result buffers of g-3 are free
         if ((rc = stage_complete(c, b)) != FSB_OK) break;
         if ((rc = run_enqueue(c, b, false)) != FSB_OK) break;
         if ((rc = summary_enqueue(c, b, *c->host[g], c->stream)) != FSB_OK) break;
         if (cudaEventRecord(b.ev_run, c->stream) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
         // copy out g-1 first: it waits for the kernels of g-1, after which staging g+2 may reuse that set's input buffers
+        trace.mark("kernels enqueued", g);
         if (g >= 1 && (rc = finish(g - 1)) != FSB_OK) break;
+        trace.mark("copy out enqueued (g - 1)", g);
         if (g + kAhead < G)
         {
             if ((rc = stage_enqueue(c, set_of(g + kAhead), chunks + first[g + kAhead], first[g + kAhead + 1] - first[g + kAhead], c->s_h2d, c->s_chk, 1)) != FSB_OK) break;
@@ -1471,6 +1553,7 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
     }
     if (rc == FSB_OK) rc = finish(G - 1);
     drain();
+    trace.mark("drained", G);
     if (rc == FSB_OK && cudaGetLastError() != cudaSuccess) rc = fail(c, FSB_ERR_CUDA, "CUDA error in the pipeline");
     c->batch[0].staged = c->batch[0].ran = false;                // the resident interface starts from a fresh fsb_stage
     return rc;
