@@ -134,7 +134,10 @@ int main(int argc, const char** argv)
     Args a;
     if (argc < 2 || !parse_args(argc, argv, a)) { std::fprintf(stderr, "usage: fastore_bin_b200 e -i<files> -o<out> [-z] [-H] [-C] [-q<0-2>] [-w<n>] [-I] [-p<n>] [-s<n>] [-m<n>] [-b<MB>] [-G<gpus>] [-W<workers per GPU>] [-K<chunks per call>] [-P<parser threads>] [-D] [-v]\n"); return -1; }
     const bool pe = a.cfg.params.paired_end != 0;
+    auto wall = [] { return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count(); };
+    if (a.verbose) std::fprintf(stderr, "[wall %.3f] main entered\n", wall());
     const int ndev = fsb_device_count();
+    if (a.verbose) std::fprintf(stderr, "[wall %.3f] CUDA driver initialised, %d device(s)\n", wall(), ndev);
     if (ndev == 0) { std::fprintf(stderr, "Error: no sm_100 GPU available (this tool has no CPU fallback)\n"); return -1; }
     int G = a.gpus > 0 ? std::min(a.gpus, ndev) : ndev;
     if (a.gpus <= 0)
@@ -356,6 +359,7 @@ int main(int argc, const char** argv)
     }
     // The bin files are closed.  Un-pinning gigabytes of chunk buffers and tearing the CUDA context down takes seconds and gives
     // nothing back that the exit of the process does not: leave at once.
+    if (a.verbose) std::fprintf(stderr, "[wall %.3f] leaving\n", wall());
     std::fflush(nullptr);
     std::_Exit(0);
 }

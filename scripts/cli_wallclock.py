@@ -63,8 +63,10 @@ def run_case(name, w, n, tmp, threads):
         t = timed([BF.CLI, "e", inp, f"-o{tmp / 'gpu'}", "-P" + str(max(4, min(16, threads // 2)))] + args)
         best = t if best is None else min(best, t)
     if TRACE:
+        w0 = time.time()
         r = subprocess.run([str(BF.CLI), "e", inp, f"-o{tmp / 'gpu_trace'}", "-v", "-P" + str(max(4, min(16, threads // 2)))] + args, capture_output=True, text=True)
-        sys.stderr.write(f"---- {name}: fastore_bin_b200 -v ----\n" + r.stderr.replace("\r", "\n") + "\n")
+        w1 = time.time()
+        sys.stderr.write(f"---- {name}: fastore_bin_b200 -v ----\n[wall {w0:.3f}] spawn\n" + r.stderr.replace("\r", "\n") + f"\n[wall {w1:.3f}] reaped\n")
     out["fastore_bin_b200"] = {"seconds": best, "reads_per_s": n * mates / best, "gpus": "all", "parser_threads": max(4, min(16, threads // 2))}
     if not SKIP_T1:
         BF.assert_bin_files_equal(tmp / "gpu", tmp / "ref1", flags["headers"])
