@@ -1542,16 +1542,17 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         if ((rc = run_enqueue(c, b, false)) != FSB_OK) break;
         if ((rc = summary_enqueue(c, b, *c->host[g], c->stream)) != FSB_OK) break;
         if (cudaEventRecord(b.ev_run, c->stream) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "cudaEventRecord failed"); break; }
-        // copy out g-1 first: it waits for the kernels of g-1, after which staging g+2 may reuse that set's input buffers
         trace.mark("kernels enqueued", g);
-        if (g >= 1 && (rc = finish(g - 1)) != FSB_OK) break;
-        trace.mark("copy out enqueued (g - 1)", g);
+        // The next copies in first (set g+2 = set g-1: its kernels were waited for one iteration ago, its results are guarded by
+        // ev_d2h), then this sub-batch's results: finish() blocks for the half millisecond the kernels take and the copy out
+        // starts the moment they end -- the host has nothing else to do until the text of g+1 has arrived.
         if (g + kAhead < G)
         {
             if ((rc = stage_enqueue(c, set_of(g + kAhead), chunks + first[g + kAhead], first[g + kAhead + 1] - first[g + kAhead], c->s_h2d, c->s_chk, 1)) != FSB_OK) break;
         }
+        if ((rc = finish(g)) != FSB_OK) break;
+        trace.mark("copy out enqueued", g);
     }
-    if (rc == FSB_OK) rc = finish(G - 1);
     drain();
     trace.mark("drained", G);
     if (rc == FSB_OK && cudaGetLastError() != cudaSuccess) rc = fail(c, FSB_ERR_CUDA, "CUDA error in the pipeline");

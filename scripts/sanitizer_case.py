@@ -1,5 +1,6 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): PE and SE multi-chunk batches through
 the pipelined call, a split resident run, the device-side parse and the rebin signature scan, each checked against the port."""
+import os
 import sys
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np
@@ -17,7 +18,8 @@ def blockdict(blk):
 for paired in (True, False):
     params = N.make_params(signature_len=8, skip_zone_len=0, paired_end=paired)
     keep, chunks, texts = [], [], []
-    for ci, (n, L) in enumerate([(3000, 150), (1, 100), (2500, 151), (700, 36)]):
+    sizes = [(3000, 150), (1, 100), (2500, 151), (700, 36)] if not os.environ.get('FSB_SAN_SMALL') else [(400, 150), (1, 100), (300, 151), (90, 36)]
+    for ci, (n, L) in enumerate(sizes):
         cfg = synth.synth_config(n, L, paired=paired, seed=900 + ci, first_index=ci * 100000, nrich=0.05, lowcomplex=0.05, alln=0.01, tie=0.02)
         t = synth.generate(cfg, threads=2); keep.append(t); chunks.append(N.make_chunk(t[0], t[2], t[1], t[3])); texts.append(N.make_chunk(t[0], None, t[1]))
     want = [O.bin_chunk("orc", params, ch) for ch in chunks]
