@@ -6,6 +6,7 @@ computes any part of the path itself.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -174,7 +175,7 @@ def cuda_lib() -> C.CDLL:
     global _cuda
     if _cuda is None:
         from . import build
-        path = build.CUDA_LIB
+        path = Path(os.environ["FSB_CUDA_LIB"]) if os.environ.get("FSB_CUDA_LIB") else build.CUDA_LIB      # (diagnostic builds)
         if not path.exists():
             raise RuntimeError(f"{path} is missing: run `python -m fastore_b200.build` (there is no CPU fallback)")
         lib = C.CDLL(str(path))

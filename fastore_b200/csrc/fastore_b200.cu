@@ -93,7 +93,7 @@ void* pinned_alloc(size_t bytes)
             if (tail) munmap(base + len, tail);
             madvise(base, len, MADV_HUGEPAGE);
             for (size_t o = 0; o < len; o += 4096) base[o] = 0;                           // fault the pages in outside the driver
-            if (cudaHostRegister(base, len, cudaHostRegisterPortable) == cudaSuccess)
+            if (cudaHostRegister(base, len, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess)
             {
                 PinRegistry& r = pin_registry();
                 std::lock_guard<std::mutex> l(r.mu);
@@ -105,7 +105,7 @@ void* pinned_alloc(size_t bytes)
         }
     }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
 void pinned_free(void* p)
@@ -154,6 +154,24 @@ struct CallTrace
         std::fprintf(stderr, "[fsb %9.3f ms] %-28s sub-batch %u\n", ms, what, g);
     }
 };
+
+// A few words from device memory straight into page-locked host memory (mapped: under unified addressing the host pointer is the
+// device pointer).  The small results the pipeline's host side waits for -- check statistics, line counts of the device-side
+// parse -- go this way and not through cudaMemcpyAsync: a copy would queue on the device-to-host copy engine behind the
+// 280 MB of a sub-batch's results (5 ms), and the host would sit out that time twice per sub-batch.
+__global__ void words_to_host_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n_words)
+{
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+}
+inline cudaError_t small_to_host(void* host_pinned, const void* dev, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return cudaSuccess;
+    void* mapped = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&mapped, host_pinned, 0);
+    if (e != cudaSuccess) return e;
+    words_to_host_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(dev), reinterpret_cast<uint32_t*>(mapped), (uint32_t)((bytes + 3) / 4));
+    return cudaGetLastError();
+}
 
 constexpr size_t kTextPad = 64;           // slack around every chunk text: aligned vector loads may over-read
 constexpr uint32_t kMaxChunksPerBatch = 256;
@@ -205,7 +223,7 @@ struct Batch
     uint64_t total_tiles = 0;
     uint32_t split = 1;
     bool profile_check = false;
-    DevBuf d_segs, d_tile_count, d_tile_prefix, d_line_start, d_parse_res, d_seg_ends, d_rec_tmp, d_parse_scan_tmp;
+    DevBuf d_segs, d_tile_count, d_tile_prefix, d_end_mask, d_line_start, d_parse_res, d_seg_ends, d_rec_tmp, d_parse_scan_tmp;
     PinBuf h_seg_ends, h_parse_res;
     cudaEvent_t ev_parse = nullptr;
     DevBuf d_text[2], d_rec[2], d_chunk_meta, d_stage_stats, d_chunk_sums, d_sort_tiles;
@@ -526,8 +544,8 @@ int stage_finalize(fsb_ctx* c, Batch& b, cudaStream_t st)
         }
         if (b.profile_check) { CUDA_TRY(c, cudaEventRecord(c->ev_check[1], st)); c->check_pending = true; }
     }
-    CUDA_TRY(c, cudaMemcpyAsync(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(c, cudaMemcpyAsync(b.h_chunk_sums.p, b.d_chunk_sums.p, (size_t)n_chunks * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, small_to_host(b.h_stage_stats.p, b.d_stage_stats.p, sizeof(StageStats), st));
+    CUDA_TRY(c, small_to_host(b.h_chunk_sums.p, b.d_chunk_sums.p, (size_t)n_chunks * 2 * sizeof(uint64_t), st));
     CUDA_TRY(c, cudaEventRecord(b.ev_chk, st));
     b.h2d_bytes += h2d;
     c->stats.h2d_bytes += h2d;
@@ -560,6 +578,7 @@ int parse_enqueue_count(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, cudaStrea
     CUDA_TRY(c, b.d_segs.ensure((n_segs + 1) * sizeof(ParseSeg)));
     CUDA_TRY(c, cudaMemcpyAsync(b.d_segs.p, b.segs_host.data(), (n_segs + 1) * sizeof(ParseSeg), cudaMemcpyHostToDevice, st));
     CUDA_TRY(c, b.d_tile_count.ensure((tiles + 2) * 4));
+    CUDA_TRY(c, b.d_end_mask.ensure((tiles + 1) * kParseTileVecs * sizeof(uint16_t)));
     CUDA_TRY(c, b.d_tile_prefix.ensure((tiles + 2) * 4));
     CUDA_TRY(c, b.d_parse_scan_tmp.ensure((scan_num_tiles(tiles + 1) + 2) * 4));
     CUDA_TRY(c, b.d_seg_ends.ensure((n_segs + 1) * 4));
@@ -567,13 +586,13 @@ int parse_enqueue_count(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, cudaStrea
     if (tiles)
     {
         parse_count_kernel<<<(unsigned)tiles, kParseThreads, 0, st>>>(b.d_text[0].as<uint8_t>(), b.d_text[1].as<uint8_t>(), b.d_segs.as<ParseSeg>(), (uint32_t)n_segs,
-                                                                       b.d_tile_count.as<uint32_t>());
+                                                                       b.d_tile_count.as<uint32_t>(), b.d_end_mask.as<uint16_t>());
         c->stats.kernel_launches++;
     }
     c->stats.kernel_launches += exclusive_scan<uint32_t, uint32_t>(b.d_tile_count.as<uint32_t>(), tiles, b.d_tile_prefix.as<uint32_t>(), b.d_parse_scan_tmp.as<uint32_t>(), st);
     parse_seg_ends_kernel<<<(unsigned)((n_segs + 127) / 128), 128, 0, st>>>(b.d_segs.as<ParseSeg>(), (uint32_t)n_segs, b.d_tile_prefix.as<uint32_t>(), b.d_seg_ends.as<uint32_t>());
     c->stats.kernel_launches++;
-    CUDA_TRY(c, cudaMemcpyAsync(b.h_seg_ends.p, b.d_seg_ends.p, n_segs * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, small_to_host(b.h_seg_ends.p, b.d_seg_ends.p, n_segs * 4, st));
     CUDA_TRY(c, cudaEventRecord(b.ev_parse, st));
     b.parse_state = 1;
     return FSB_OK;
@@ -616,7 +635,7 @@ int stage_advance(fsb_ctx* c, Batch& b, cudaStream_t st)
         CUDA_TRY(c, cudaMemsetAsync(b.d_parse_res.p, 0xFF, (n_segs + 1) * sizeof(ParseResult), st));
         if (b.total_tiles)
         {
-            parse_lines_kernel<<<(unsigned)b.total_tiles, kParseThreads, 0, st>>>(b.d_text[0].as<uint8_t>(), b.d_text[1].as<uint8_t>(), b.d_segs.as<ParseSeg>(), (uint32_t)n_segs,
+            parse_lines_kernel<<<(unsigned)b.total_tiles, kParseThreads, 0, st>>>(b.d_end_mask.as<uint16_t>(), b.d_segs.as<ParseSeg>(), (uint32_t)n_segs,
                                                                                    b.d_tile_prefix.as<uint32_t>(), b.d_line_start.as<uint32_t>());
             c->stats.kernel_launches++;
         }
@@ -626,7 +645,7 @@ int stage_advance(fsb_ctx* c, Batch& b, cudaStream_t st)
                 b.d_line_start.as<uint32_t>(), c->dp.has_headers, c->keep_comments ? 1u : 0u, b.d_rec[0].as<fsb_record>(), b.d_rec[1].as<fsb_record>(), b.d_parse_res.as<ParseResult>());
             c->stats.kernel_launches++;
         }
-        CUDA_TRY(c, cudaMemcpyAsync(b.h_parse_res.p, b.d_parse_res.p, n_segs * sizeof(ParseResult), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, small_to_host(b.h_parse_res.p, b.d_parse_res.p, n_segs * sizeof(ParseResult), st));
         CUDA_TRY(c, cudaEventRecord(b.ev_parse, st));
         b.parse_state = 2;
         return FSB_OK;
@@ -1067,7 +1086,7 @@ int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
 int summary_enqueue(fsb_ctx* c, Batch& b, HostOut& h, cudaStream_t st)
 {
     CUDA_TRY(c, h.summary.ensure((size_t)b.n_chunks * sizeof(ChunkSummary)));
-    CUDA_TRY(c, cudaMemcpyAsync(h.summary.p, b.d_summary.p, (size_t)b.n_chunks * sizeof(ChunkSummary), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, small_to_host(h.summary.p, b.d_summary.p, (size_t)b.n_chunks * sizeof(ChunkSummary), st));
     return FSB_OK;
 }
 // Results, step 2 (summary on the host): enqueue the copies of the streams and descriptors, sub-batch by sub-batch
@@ -1241,7 +1260,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
         if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
         if (b.ev_chk) cudaEventDestroy(b.ev_chk);
         if (b.ev_parse) cudaEventDestroy(b.ev_parse);
-        b.d_segs.release(); b.d_tile_count.release(); b.d_tile_prefix.release(); b.d_line_start.release(); b.d_parse_res.release(); b.d_seg_ends.release(); b.d_rec_tmp.release(); b.d_parse_scan_tmp.release();
+        b.d_segs.release(); b.d_tile_count.release(); b.d_end_mask.release(); b.d_tile_prefix.release(); b.d_line_start.release(); b.d_parse_res.release(); b.d_seg_ends.release(); b.d_rec_tmp.release(); b.d_parse_scan_tmp.release();
         b.h_seg_ends.release(); b.h_parse_res.release();
         if (b.ev_run) cudaEventDestroy(b.ev_run);
         if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);

@@ -78,6 +78,20 @@ template <int NW> constexpr uint32_t win_slot_bytes() { return win_pieces<NW>() 
 #endif
 constexpr uint32_t kIngestMaxWarps = FSB_K1_WARPS;      // warps per block (launch bound)
 
+// The lanes of a warp read windows that other lanes' cp.async requests have filled: every lane waits for its own requests
+// (cp.async.wait_group 0), then the warp synchronises.  compute-sanitizer's racecheck does not take __syncwarp() as ordering
+// for asynchronous copies and reports the reads that follow; the diagnostic build -DFSB_K1_NAMED_BARRIER replaces exactly
+// these two synchronisations by a 32-thread named barrier (bar.sync, one id per warp) to show that nothing else is flagged.
+__device__ __forceinline__ void sync_after_window_copies(unsigned warp)
+{
+#ifdef FSB_K1_NAMED_BARRIER
+    asm volatile("bar.sync %0, 32;" ::"r"(warp + 1u) : "memory");
+#else
+    (void)warp;
+    __syncwarp();
+#endif
+}
+
 // The first radix pass of the sort needs the digit counts of every sort tile (scan_sort.cuh).  K1 knows every key the moment
 // it writes it, so it counts them itself (one L2 reduction per record) and the pass needs no histogram kernel: counts (zeroed by
 // the caller, null = off) in the layout [chunk][digit][tile of the chunk]; chunk_tiles[c] = sort tiles of the chunks in front of c.
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         const uint64_t seq_at = cur.text_base + cur.rec.y, qua_at = cur.text_base + cur.rec.z;
         const uint32_t a_seq = (uint32_t)(seq_at & 15u), a_qua = (uint32_t)(qua_at & 15u), a_head = (uint32_t)((cur.text_base + cur.rec.x) & 15u);
         cp_async_wait_all();
-        __syncwarp();
+        sync_after_window_copies(warp);
 
         // ---- bit planes of the sequence; from here on the windows belong to the qualities ----------------------------
         BV<NW> Hp, Lp, Np;
@@ -410,7 +424,7 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
                 atomicAdd(&seed.counts[(uint64_t)seed.radix * t0 + (uint64_t)(sig & seed.mask) * (t1 - t0) + (uint32_t)((i - first) / seed.tile)], 1u);
         }
         cp_async_wait_all();
-        __syncwarp();
+        sync_after_window_copies(warp);
 
         // ---- quality of this mate in the stored orientation (StoreQuality): every lane packs its mate's stream as
         //      16-byte vectors into the mate's quality region of the staged slot ----------------------------------------

@@ -11,9 +11,10 @@
 // as the reference's uint16 locals do).  Nothing in those rules looks further back than the start of the
 // record, so the scan turns into three data-parallel passes over the text of every (chunk, mate) segment:
 //
-//   parse_count    line ends per 4 KB tile: a byte ends a line if it is LF, or CR not followed by LF;
+//   parse_count    a 16-bit line-end mask per 16 bytes of text (a byte ends a line if it is LF, or CR not followed by LF;
+//                  found four bytes at a time with word arithmetic) and the line ends per 16 KB tile
 //                  (exclusive scan over the tile counts: scan_sort.cuh)
-//   parse_lines    every line end writes the start of the next line at its rank: line_start[k + 1] = p + 1
+//   parse_lines    from the masks: every line end writes the start of the next line at its rank: line_start[k + 1] = p + 1
 //   parse_records  thread r takes lines 4r .. 4r+3: lengths (CR of a CR LF taken off, missing lines count as
 //                  empty, exactly what SkipLine returns at the end of the memory), the acceptance rules, the
 //                  fsb_record (-C: title cut at the first space); the lowest rejected r of a segment is where the
@@ -29,7 +30,9 @@
 namespace fsb {
 
 constexpr uint32_t kParseThreads = 256;
-constexpr uint32_t kParseTile = kParseThreads * 16;      // bytes per block: one 16-byte vector per thread
+constexpr uint32_t kParseVecs = 4;                                   // 16-byte vectors per thread
+constexpr uint32_t kParseTile = kParseThreads * kParseVecs * 16;     // bytes per block
+constexpr uint32_t kParseTileVecs = kParseTile / 16;                 // line-end masks (16 bits each) per tile
 
 // one chunk text of one mate
 struct ParseSeg
@@ -59,28 +62,46 @@ __device__ __forceinline__ uint32_t parse_seg_of_tile(const ParseSeg* __restrict
     return lo;
 }
 
-// bit b of the result: byte b of the thread's vector ends a line.  `next` = the byte behind the vector (0 if none).
+// 0x80 in every byte of w that equals the byte repeated in pattern4 (exact: no borrow crosses a byte)
+__device__ __forceinline__ uint32_t bytes_equal(uint32_t w, uint32_t pattern4)
+{
+    const uint32_t x = w ^ pattern4;
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+// The flags of two words (0x80 per byte) as eight mask bits, byte b of word j at bit 4 j + b: with c = f0 >> 7 | f1 >> 3 byte b
+// holds its two flags at bits 0 and 4, and one multiplication moves byte b down by 7 b places next to its neighbours (every
+// stray product term lands on a position of its own below bit 21 or above bit 28, so nothing carries into the result).
+__device__ __forceinline__ uint32_t gather_flags8(uint32_t f0, uint32_t f1)
+{
+    const uint32_t c = (f0 >> 7) | (f1 >> 3);
+    return ((c * ((1u << 21) | (1u << 14) | (1u << 7) | 1u)) >> 21) & 0xFFu;
+}
+// bit b of the result: byte b of the vector ends a line -- it is LF, or CR not followed by LF (FastqParser.cpp:46-68).
+// `next` = the byte behind the vector (0 if none); bytes from `valid_bytes` on do not belong to the text.
 __device__ __forceinline__ uint32_t line_end_mask(const uint4& v, uint32_t next, uint32_t valid_bytes)
 {
-    const uint32_t w[5] = {v.x, v.y, v.z, v.w, next};
-    uint32_t m = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t lf[5], e[4];
 #pragma unroll
-    for (int b = 0; b < 16; ++b)
+    for (int j = 0; j < 4; ++j) lf[j] = bytes_equal(w[j], 0x0A0A0A0Au);
+    lf[4] = next == '\n' ? 0x80u : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
     {
-        const uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-        const uint32_t d = (w[(b + 1) >> 2] >> (8 * ((b + 1) & 3))) & 0xFFu;
-        const bool end = c == '\n' || (c == '\r' && d != '\n');
-        m |= (end && (uint32_t)b < valid_bytes) ? (1u << b) : 0u;
+        const uint32_t lf_behind = __funnelshift_r(lf[j], lf[j + 1], 8);           // the LF flag of the byte behind every byte
+        e[j] = lf[j] | (bytes_equal(w[j], 0x0D0D0D0Du) & ~lf_behind);
     }
-    return m;
+    const uint32_t m = gather_flags8(e[0], e[1]) | (gather_flags8(e[2], e[3]) << 8);
+    return valid_bytes >= 16u ? m : (m & ((1u << valid_bytes) - 1u));
 }
 
-// the thread's vector of a tile, the byte behind it, and how many of its bytes belong to the segment
+// vector `vec` (0 .. kParseTileVecs) of a tile, the byte behind it, and how many of its bytes belong to the segment; must be
+// called by whole warps with consecutive `vec` in consecutive lanes
 struct ParseVec { uint4 v; uint32_t next; uint32_t valid; unsigned long long off; };
-__device__ __forceinline__ ParseVec parse_load(const uint8_t* __restrict__ text, const ParseSeg& s, unsigned long long tile)
+__device__ __forceinline__ ParseVec parse_load(const uint8_t* __restrict__ text, const ParseSeg& s, unsigned long long tile, uint32_t vec)
 {
     ParseVec r;
-    r.off = (tile - s.tile0) * kParseTile + 16ull * threadIdx.x;                  // offset inside the segment
+    r.off = (tile - s.tile0) * kParseTile + 16ull * vec;                           // offset inside the segment
     r.valid = r.off < s.size ? (uint32_t)min(16ull, s.size - r.off) : 0u;
     r.v = make_uint4(0, 0, 0, 0);
     if (r.valid) r.v = *reinterpret_cast<const uint4*>(text + s.text_base + r.off);   // segments start 256-byte aligned and are padded behind
@@ -91,14 +112,26 @@ __device__ __forceinline__ ParseVec parse_load(const uint8_t* __restrict__ text,
     return r;
 }
 
+// Pass 1: the line-end mask of every 16-byte vector (16 bits, end_mask[tile * kParseTileVecs + vector]) and the line ends per tile.
+// Thread t takes the vectors t, t + 256, ... of its tile (coalesced loads).
 __global__ void __launch_bounds__(kParseThreads) parse_count_kernel(const uint8_t* __restrict__ text0, const uint8_t* __restrict__ text1,
-                                                                    const ParseSeg* __restrict__ segs, uint32_t n_segs, uint32_t* __restrict__ tile_count)
+                                                                    const ParseSeg* __restrict__ segs, uint32_t n_segs, uint32_t* __restrict__ tile_count,
+                                                                    uint16_t* __restrict__ end_mask)
 {
     __shared__ uint32_t warp_sum[kParseThreads / 32];
     const unsigned long long tile = blockIdx.x;
     const ParseSeg s = segs[parse_seg_of_tile(segs, n_segs, tile)];
-    const ParseVec pv = parse_load(s.mate ? text1 : text0, s, tile);
-    uint32_t cnt = __popc(line_end_mask(pv.v, pv.next, pv.valid));
+    const uint8_t* text = s.mate ? text1 : text0;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kParseVecs; ++k)
+    {
+        const uint32_t vec = k * kParseThreads + threadIdx.x;
+        const ParseVec pv = parse_load(text, s, tile, vec);
+        const uint32_t m = line_end_mask(pv.v, pv.next, pv.valid);
+        end_mask[tile * kParseTileVecs + vec] = (uint16_t)m;
+        cnt += __popc(m);
+    }
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
     if ((threadIdx.x & 31u) == 0) warp_sum[threadIdx.x >> 5] = cnt;
     __syncthreads();
@@ -118,17 +151,18 @@ __global__ void parse_seg_ends_kernel(const ParseSeg* __restrict__ segs, uint32_
     if (k < n_segs) seg_ends[k] = tile_prefix[segs[k + 1].tile0] - tile_prefix[segs[k].tile0];
 }
 
-// tile_prefix: exclusive scan of tile_count over all tiles.  line_start holds, per segment, n_line_ends + 1 entries from line0.
-__global__ void __launch_bounds__(kParseThreads) parse_lines_kernel(const uint8_t* __restrict__ text0, const uint8_t* __restrict__ text1,
-                                                                    const ParseSeg* __restrict__ segs, uint32_t n_segs, const uint32_t* __restrict__ tile_prefix,
-                                                                    uint32_t* __restrict__ line_start)
+// Pass 2, from the masks alone (the text is not read again): thread t takes the four consecutive vectors 4t .. 4t+3 of its tile,
+// i.e. 64 mask bits = 64 bytes of text.  tile_prefix: exclusive scan of tile_count over all tiles.  line_start holds, per
+// segment, n_line_ends + 1 entries from line0.
+__global__ void __launch_bounds__(kParseThreads) parse_lines_kernel(const uint16_t* __restrict__ end_mask, const ParseSeg* __restrict__ segs, uint32_t n_segs,
+                                                                    const uint32_t* __restrict__ tile_prefix, uint32_t* __restrict__ line_start)
 {
+    static_assert(kParseVecs == 4, "a thread's masks are one 64-bit load");
     __shared__ uint32_t warp_sum[kParseThreads / 32];
     const unsigned long long tile = blockIdx.x;
     const ParseSeg s = segs[parse_seg_of_tile(segs, n_segs, tile)];
-    const ParseVec pv = parse_load(s.mate ? text1 : text0, s, tile);
-    const uint32_t m = line_end_mask(pv.v, pv.next, pv.valid);
-    const uint32_t cnt = __popc(m);
+    unsigned long long m = reinterpret_cast<const unsigned long long*>(end_mask + tile * kParseTileVecs)[threadIdx.x];
+    const uint32_t cnt = (uint32_t)__popcll(m);
     // exclusive rank of the thread's first line end inside the block
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t inc = cnt;
@@ -142,12 +176,12 @@ __global__ void __launch_bounds__(kParseThreads) parse_lines_kernel(const uint8_
     uint32_t k = tile_prefix[tile] - tile_prefix[s.tile0] + before + inc - cnt;
     uint32_t* ls = line_start + s.line0;
     if (tile == s.tile0 && threadIdx.x == 0) ls[0] = 0;
-    uint32_t mm = m;
-    while (mm)
+    const unsigned long long off = (tile - s.tile0) * kParseTile + 64ull * threadIdx.x;      // offset of the thread's 64 bytes inside the segment
+    while (m)
     {
-        const uint32_t b = (uint32_t)__ffs((int)mm) - 1u;
-        mm &= mm - 1u;
-        ls[++k] = (uint32_t)(pv.off + b + 1u);
+        const uint32_t b = (uint32_t)__ffsll((long long)m) - 1u;
+        m &= m - 1ull;
+        ls[++k] = (uint32_t)(off + b + 1u);
     }
 }
 

@@ -102,3 +102,32 @@ def test_records_outside_the_contract_are_errors():
             g.stage([N.make_chunk(good, None), N.make_chunk(good, r)])
         g.stage([N.make_chunk(good, None)])
         assert g.get_records(0).shape[0] == 200
+
+
+@pytest.mark.parametrize("eol", [b"\r\n", b"\r", b"\n"])
+def test_line_ends_on_vector_warp_and_tile_boundaries(eol):
+    """The line-end pass looks at 16-byte vectors, 32 of them per warp, 16 KB per block: put a line end (and the CR of a CR LF)
+    on the last byte in front of each of these boundaries, and one byte to either side."""
+    cfg = synth.synth_config(400, 100, seed=53)
+    t1, _, _, _ = synth.generate(cfg, threads=1)
+    raw = t1.tobytes()
+    params = N.make_params(signature_len=8, skip_zone_len=0)
+    with GpuBinner(params) as g:
+        for boundary in (16, 512, 16384, 32768):
+            for delta in (-1, 0, 1):
+                txt = raw.replace(b"\n", eol)
+                p = txt.find(eol, boundary - 1 - 150 if boundary > 200 else 0)      # a line end shortly in front of the boundary ...
+                pad = boundary - 1 + delta - p                                     # ... moved so that its first byte sits at boundary - 1 + delta
+                if pad < 0:
+                    p = txt.find(eol, p + 1); pad = boundary - 1 + delta - p
+                assert 0 <= pad < 200
+                txt = txt[:1] + b"x" * pad + txt[1:]                               # a longer first title shifts everything behind it
+                assert txt[boundary - 1 + delta: boundary - 1 + delta + len(eol)] == eol
+                text = np.frombuffer(txt, dtype=np.uint8).copy()
+                want = host_tables([text])[0]
+                assert want.shape[0] == 400
+                g.stage([N.make_chunk(text, None)])
+                got = g.get_records(0)
+                assert got.shape == want.shape, f"boundary {boundary}{delta:+d}: {got.shape[0]} records"
+                for f in N.RECORD_DTYPE.names:
+                    assert np.array_equal(got[f], want[f]), f"boundary {boundary}{delta:+d}: field {f}"
