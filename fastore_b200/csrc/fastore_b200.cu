@@ -155,21 +155,35 @@ struct CallTrace
     }
 };
 
-// A few words from device memory straight into page-locked host memory (mapped: under unified addressing the host pointer is the
-// device pointer).  The small results the pipeline's host side waits for -- check statistics, line counts of the device-side
-// parse -- go this way and not through cudaMemcpyAsync: a copy would queue on the device-to-host copy engine behind the
-// 280 MB of a sub-batch's results (5 ms), and the host would sit out that time twice per sub-batch.
-__global__ void words_to_host_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n_words)
+// Small tables and results move between page-locked host memory and the device through a kernel, not through cudaMemcpyAsync
+// (mapped memory: under unified addressing the device reads and writes the host buffer directly).  The copy engines work
+// through their transfers in the order of submission: a 100-byte copy submitted while the next sub-batch's 540 MB of text are
+// on their way waits 10 ms for them, a small result behind a sub-batch's 280 MB of output 5 ms -- and the host side of the
+// pipeline waits for exactly these small things (check statistics, line counts of the device-side parse).
+__global__ void words_copy_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n_words)
 {
-    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
+__global__ void words_fill_kernel(uint32_t* __restrict__ dst, uint32_t value, uint32_t n_words)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) dst[i] = value;
+}
+inline unsigned words_grid(size_t n_words) { return (unsigned)std::max<size_t>(1, std::min<size_t>(64, (n_words + 1023) / 1024)); }
 inline cudaError_t small_to_host(void* host_pinned, const void* dev, size_t bytes, cudaStream_t st)
 {
     if (bytes == 0) return cudaSuccess;
     void* mapped = nullptr;
     cudaError_t e = cudaHostGetDevicePointer(&mapped, host_pinned, 0);
     if (e != cudaSuccess) return e;
-    words_to_host_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(dev), reinterpret_cast<uint32_t*>(mapped), (uint32_t)((bytes + 3) / 4));
+    const size_t n = (bytes + 3) / 4;
+    words_copy_kernel<<<words_grid(n), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(dev), reinterpret_cast<uint32_t*>(mapped), (uint32_t)n);
+    return cudaGetLastError();
+}
+inline cudaError_t small_fill(void* dev, uint32_t value, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return cudaSuccess;
+    const size_t n = (bytes + 3) / 4;
+    words_fill_kernel<<<words_grid(n), 256, 0, st>>>(reinterpret_cast<uint32_t*>(dev), value, (uint32_t)n);
     return cudaGetLastError();
 }
 
@@ -217,6 +231,8 @@ struct Batch
     bool device_parse = false;
     int parse_state = 0;                         // 0: nothing pending (tables from the host, or parse finished); 1: line ends counted; 2: records built
     std::vector<ParseSeg> segs_host;             // one segment per (chunk, mate)
+    PinBuf h_up;                                 // page-locked arena the small tables go up from (upload_small)
+    size_t up_used = 0;
     std::vector<uint8_t> seg_open_end;           // 1: the segment's text does not end with a line end (its last line is one more line)
     std::vector<uint64_t> chunk_cap;             // record candidates per chunk (table capacity)
     std::vector<uint64_t> chunk_n;               // records per chunk (what the parse found, or what the caller's tables hold)
@@ -249,6 +265,7 @@ struct fsb_ctx
     bool own_stream = false;
     std::string err;
     bool per_read = false, profile = false, validate = true;
+    const CallTrace* trace = nullptr;            // FSB_TRACE: the timeline of the fsb_bin_chunks call in progress
     uint64_t sub_batch_records = 400000;         // fsb_bin_chunks cuts its chunk list into sub-batches of at least this many records
 
     Batch batch[3];                              // [0] is the batch of fsb_stage / fsb_run / fsb_fetch; fsb_bin_chunks cycles through all three
@@ -425,6 +442,30 @@ HostOut* host_out(fsb_ctx* c, size_t g)
     return c->host[g];
 }
 
+// `bytes` of host data to device memory on `st` without the copy engine: through the batch's page-locked arena and a kernel.
+// The arena is rewound by stage_enqueue; it grows (after waiting for `st`, so that nothing reads the old one) if it runs out.
+int upload_small(fsb_ctx* c, Batch& b, void* dev, const void* src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return FSB_OK;
+    const size_t need = align_up(bytes, 16);
+    if (b.up_used + need > b.h_up.cap)
+    {
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        b.up_used = 0;
+        CUDA_TRY(c, b.h_up.ensure(std::max<size_t>(2 * need, (size_t)1 << 20)));
+    }
+    uint8_t* slot = b.h_up.as<uint8_t>() + b.up_used;
+    std::memcpy(slot, src, bytes);
+    b.up_used += need;
+    void* mapped = nullptr;
+    CUDA_TRY(c, cudaHostGetDevicePointer(&mapped, slot, 0));
+    const size_t n = (bytes + 3) / 4;
+    words_copy_kernel<<<words_grid(n), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(mapped), reinterpret_cast<uint32_t*>(dev), (uint32_t)n);
+    CUDA_TRY(c, cudaGetLastError());
+    c->stats.kernel_launches++;
+    return FSB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Stage, last enqueue step: the records per chunk are known (b.chunk_n: from the caller's tables or from the device-side
 // parse).  Chunk tables, sub-batches and sort tiles go up, then the device-side check of the record tables (offsets
@@ -479,7 +520,7 @@ int stage_finalize(fsb_ctx* c, Batch& b, cudaStream_t st)
         for (uint32_t ci = sb.c0; ci <= sb.c1; ++ci) meta.push_back(b.chunk_first_rec[ci] - sb.r0);
     }
     CUDA_TRY(c, b.d_chunk_meta.ensure(meta.size() * sizeof(uint64_t)));
-    CUDA_TRY(c, cudaMemcpyAsync(b.d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (int rc = upload_small(c, b, b.d_chunk_meta.p, meta.data(), meta.size() * sizeof(uint64_t), st)) return rc;
     h2d += meta.size() * sizeof(uint64_t);
     // sort tiles: every tile lies inside one chunk (scan_sort.cuh)
     b.tiles_host.clear(); b.ctiles_host.clear();
@@ -507,10 +548,9 @@ int stage_finalize(fsb_ctx* c, Batch& b, cudaStream_t st)
         sb.n_tiles = b.tiles_host.size() - sb.tile_off;
     }
     CUDA_TRY(c, b.d_chunk_tiles.ensure((b.ctiles_host.size() + 1) * 4));
-    CUDA_TRY(c, cudaMemcpyAsync(b.d_chunk_tiles.p, b.ctiles_host.data(), b.ctiles_host.size() * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = upload_small(c, b, b.d_chunk_tiles.p, b.ctiles_host.data(), b.ctiles_host.size() * 4, st)) return rc;
     CUDA_TRY(c, b.d_sort_tiles.ensure((b.tiles_host.size() + 1) * sizeof(SortTile)));
-    if (!b.tiles_host.empty())
-        CUDA_TRY(c, cudaMemcpyAsync(b.d_sort_tiles.p, b.tiles_host.data(), b.tiles_host.size() * sizeof(SortTile), cudaMemcpyHostToDevice, st));
+    if (int rc = upload_small(c, b, b.d_sort_tiles.p, b.tiles_host.data(), b.tiles_host.size() * sizeof(SortTile), st)) return rc;
     h2d += b.tiles_host.size() * sizeof(SortTile);
 
     CUDA_TRY(c, b.d_stage_stats.ensure(sizeof(StageStats)));
@@ -519,9 +559,8 @@ int stage_finalize(fsb_ctx* c, Batch& b, cudaStream_t st)
     CUDA_TRY(c, b.h_chunk_sums.ensure((size_t)n_chunks * 2 * sizeof(uint64_t)));
     StageStats init{};
     init.first_bad = ~0ull; init.first_bad_text = ~0ull; init.min_len = 0xFFFFFFFFu;
-    b.h_stage_stats.as<StageStats>()[1] = init;                  // [1] initial value going up, [0] result coming back
-    CUDA_TRY(c, cudaMemcpyAsync(b.d_stage_stats.p, b.h_stage_stats.as<StageStats>() + 1, sizeof(StageStats), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(c, cudaMemsetAsync(b.d_chunk_sums.p, 0, (size_t)n_chunks * 2 * sizeof(uint64_t), st));
+    if (int rc = upload_small(c, b, b.d_stage_stats.p, &init, sizeof(StageStats), st)) return rc;
+    CUDA_TRY(c, small_fill(b.d_chunk_sums.p, 0u, (size_t)n_chunks * 2 * sizeof(uint64_t), st));
     if (n)
     {
         const BatchView B = batch_view(b);
@@ -576,7 +615,7 @@ int parse_enqueue_count(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, cudaStrea
     guard.tile0 = tiles;
     b.segs_host.push_back(guard);
     CUDA_TRY(c, b.d_segs.ensure((n_segs + 1) * sizeof(ParseSeg)));
-    CUDA_TRY(c, cudaMemcpyAsync(b.d_segs.p, b.segs_host.data(), (n_segs + 1) * sizeof(ParseSeg), cudaMemcpyHostToDevice, st));
+    if (int rc = upload_small(c, b, b.d_segs.p, b.segs_host.data(), (n_segs + 1) * sizeof(ParseSeg), st)) return rc;
     CUDA_TRY(c, b.d_tile_count.ensure((tiles + 2) * 4));
     CUDA_TRY(c, b.d_end_mask.ensure((tiles + 1) * kParseTileVecs * sizeof(uint16_t)));
     CUDA_TRY(c, b.d_tile_prefix.ensure((tiles + 2) * 4));
@@ -607,6 +646,7 @@ int stage_advance(fsb_ctx* c, Batch& b, cudaStream_t st)
     if (b.parse_state == 1)
     {
         CUDA_TRY(c, cudaEventSynchronize(b.ev_parse));
+        if (c->trace) c->trace->mark("  line ends counted", 0);
         const uint32_t* ends = b.h_seg_ends.as<uint32_t>();
         uint64_t lines = 0;
         b.chunk_cap.assign(b.n_chunks, 0);
@@ -627,12 +667,12 @@ int stage_advance(fsb_ctx* c, Batch& b, cudaStream_t st)
         if (cap_total > kMaxBatchRecords) return fail(c, FSB_ERR_PARAM, "fsb_stage: more than 2^28-1 records in one batch");
         uint32_t cap_max = 0;
         for (size_t k = 0; k < n_segs; ++k) { b.segs_host[k].rec0 = cap_first[b.segs_host[k].chunk]; cap_max = std::max(cap_max, b.segs_host[k].cap); }
-        CUDA_TRY(c, cudaMemcpyAsync(b.d_segs.p, b.segs_host.data(), (n_segs + 1) * sizeof(ParseSeg), cudaMemcpyHostToDevice, st));
+        if (int rc = upload_small(c, b, b.d_segs.p, b.segs_host.data(), (n_segs + 1) * sizeof(ParseSeg), st)) return rc;
         CUDA_TRY(c, b.d_line_start.ensure((lines + 2) * 4));
         for (int m = 0; m < nfiles; ++m) CUDA_TRY(c, b.d_rec[m].ensure((cap_total + 1) * sizeof(fsb_record)));
         CUDA_TRY(c, b.d_parse_res.ensure((n_segs + 1) * sizeof(ParseResult)));
         CUDA_TRY(c, b.h_parse_res.ensure((n_segs + 1) * sizeof(ParseResult)));
-        CUDA_TRY(c, cudaMemsetAsync(b.d_parse_res.p, 0xFF, (n_segs + 1) * sizeof(ParseResult), st));
+        CUDA_TRY(c, small_fill(b.d_parse_res.p, 0xFFFFFFFFu, (n_segs + 1) * sizeof(ParseResult), st));
         if (b.total_tiles)
         {
             parse_lines_kernel<<<(unsigned)b.total_tiles, kParseThreads, 0, st>>>(b.d_end_mask.as<uint16_t>(), b.d_segs.as<ParseSeg>(), (uint32_t)n_segs,
@@ -653,6 +693,7 @@ int stage_advance(fsb_ctx* c, Batch& b, cudaStream_t st)
     if (b.parse_state == 2)
     {
         CUDA_TRY(c, cudaEventSynchronize(b.ev_parse));
+        if (c->trace) c->trace->mark("  records parsed", 0);
         const ParseResult* res = b.h_parse_res.as<ParseResult>();
         // records of a chunk: where the first of its (one or two) parsers stops -- FastqRecordsParserPE::ParseFrom runs both in step (FastqParser.cpp:527)
         b.chunk_n.assign(b.n_chunks, ~0ull);
@@ -697,7 +738,7 @@ int stage_advance(fsb_ctx* c, Batch& b, cudaStream_t st)
 // keeps its copy stream free of kernels, so that the next sub-batch's text follows at once.
 int stage_enqueue(fsb_ctx* c, Batch& b, const fsb_chunk* chunks, uint32_t n_chunks, cudaStream_t st, cudaStream_t st_check, uint32_t split, bool profile = false)
 {
-    b.staged = false; b.ran = false; b.parse_state = 0;
+    b.staged = false; b.ran = false; b.parse_state = 0; b.up_used = 0;
     b.split = split; b.profile_check = profile;
     const int nfiles = c->dp.paired ? 2 : 1;
     const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(kMaxChunksPerBatch, 1ull << (32 - c->dp.key_bits));
@@ -1256,7 +1297,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
         DevBuf* dev[] = {&b.d_text[0], &b.d_text[1], &b.d_rec[0], &b.d_rec[1], &b.d_chunk_meta, &b.d_stage_stats, &b.d_chunk_sums, &b.d_sort_tiles, &b.d_chunk_tiles, &b.d_out[0], &b.d_out[1], &b.d_out[2], &b.d_out[3],
                          &b.d_desc, &b.d_summary, &b.d_sig, &b.d_info};
         for (DevBuf* d : dev) d->release();
-        b.h_stage_stats.release(); b.h_chunk_sums.release();
+        b.h_stage_stats.release(); b.h_chunk_sums.release(); b.h_up.release();
         if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
         if (b.ev_chk) cudaEventDestroy(b.ev_chk);
         if (b.ev_parse) cudaEventDestroy(b.ev_parse);
@@ -1510,6 +1551,8 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
     }
     const uint32_t G = (uint32_t)first.size() - 1;
     const CallTrace trace;
+    struct TraceScope { fsb_ctx* c; ~TraceScope() { c->trace = nullptr; } } trace_scope{c};
+    c->trace = &trace;
     if (!c->s_h2d) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     if (!c->s_d2h) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     if (!c->s_chk) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_chk, cudaStreamNonBlocking));
