@@ -261,7 +261,7 @@ struct fsb_ctx
     DeviceParams dp{};
     int device = 0;
     cudaStream_t stream = nullptr;               // kernels
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_chk = nullptr;   // copy and input-check streams of the pipelined fsb_bin_chunks (created on first use)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_chk[3] = {nullptr, nullptr, nullptr};   // copy streams and one input-check stream per buffer set of the pipelined fsb_bin_chunks (created on first use)
     bool own_stream = false;
     std::string err;
     bool per_read = false, profile = false, validate = true;
@@ -1289,7 +1289,7 @@ extern "C" void fsb_destroy(fsb_ctx* c)
     cudaStreamSynchronize(c->stream);
     if (c->s_h2d) { cudaStreamSynchronize(c->s_h2d); cudaStreamDestroy(c->s_h2d); }
     if (c->s_d2h) { cudaStreamSynchronize(c->s_d2h); cudaStreamDestroy(c->s_d2h); }
-    if (c->s_chk) { cudaStreamSynchronize(c->s_chk); cudaStreamDestroy(c->s_chk); }
+    for (cudaStream_t& q : c->s_chk) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); q = nullptr; }
     for (auto& e : c->events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_check) if (e) cudaEventDestroy(e);
     for (Batch& b : c->batch)
@@ -1519,7 +1519,9 @@ extern "C" int fsb_find_new_minimizers(fsb_ctx* c, const uint8_t* text, uint64_t
 // The chunk list is cut into sub-batches of at least sub_batch_records records (whole chunks) which
 // run as a pipeline over three sets of device buffers:
 //     s_h2d   : copies in of g+1, g+2 ... back to back (a set is reused once the kernels that read it are done)
-//     s_chk   : input check of every sub-batch as soon as its copy has landed
+//     s_chk[] : input check (and device-side parse) of every sub-batch as soon as its copy has landed; one stream per buffer set,
+//               because the parse of sub-batch g is enqueued in steps, and on a shared stream its later steps would sit behind
+//               the wait for the text of g+1 that stage_enqueue(g+1) has already put there
 //     stream  : kernels of g (the host has seen g's check results, and that copy out g-3 has released the result buffers)
 //     s_d2h   : copy out g-1
 // Two sub-batches are always staged ahead, so the copy stream -- the PCIe link is what bounds this call -- never waits for
@@ -1555,7 +1557,7 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
     c->trace = &trace;
     if (!c->s_h2d) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     if (!c->s_d2h) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-    if (!c->s_chk) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_chk, cudaStreamNonBlocking));
+    for (cudaStream_t& q : c->s_chk) if (!q) CUDA_TRY(c, cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
     constexpr uint32_t kSets = 3, kAhead = 2;
     auto set_of = [&](uint32_t g) -> Batch& { return c->batch[g % kSets]; };
     for (uint32_t g = 0; g < G; ++g) if (!host_out(c, g)) return fail(c, FSB_ERR_NOMEM, "out of host memory");
@@ -1564,7 +1566,7 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
     CUDA_TRY(c, cudaStreamSynchronize(c->s_d2h));
 
     int rc = FSB_OK;
-    auto drain = [&]() { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_chk); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h); };
+    auto drain = [&]() { cudaStreamSynchronize(c->s_h2d); for (cudaStream_t q : c->s_chk) cudaStreamSynchronize(q); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h); };
     // copy out of sub-batch g: its summary is on the host once ev_run has fired
     auto finish = [&](uint32_t g) -> int
     {
@@ -1589,12 +1591,12 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
     c->rec_index.assign(c->keep_records ? n_chunks : 0, fsb_ctx::RecRef{{nullptr, nullptr}, 0});
 
     for (uint32_t g = 0; g < std::min(G, kAhead) && rc == FSB_OK; ++g)
-        rc = stage_enqueue(c, set_of(g), chunks + first[g], first[g + 1] - first[g], c->s_h2d, c->s_chk, 1);
+        rc = stage_enqueue(c, set_of(g), chunks + first[g], first[g + 1] - first[g], c->s_h2d, c->s_chk[g % kSets], 1);
     trace.mark("first copies enqueued", 0);
     for (uint32_t g = 0; g < G && rc == FSB_OK; ++g)
     {
         Batch& b = set_of(g);
-        while (rc == FSB_OK && b.parse_state) rc = stage_advance(c, b, c->s_chk);     // device-side parse: the steps behind the copy
+        while (rc == FSB_OK && b.parse_state) rc = stage_advance(c, b, c->s_chk[g % kSets]);     // device-side parse: the steps behind the copy
         if (rc != FSB_OK) break;
         trace.mark("parsed", g);
         if (cudaEventSynchronize(b.ev_chk) != cudaSuccess) { rc = fail(c, FSB_ERR_CUDA, "copy to the device failed"); break; }    // text on the device, check results on the host
@@ -1610,7 +1612,7 @@ extern "C" int fsb_bin_chunks(fsb_ctx* c, const fsb_chunk* chunks, uint32_t n_ch
         // starts the moment they end -- the host has nothing else to do until the text of g+1 has arrived.
         if (g + kAhead < G)
         {
-            if ((rc = stage_enqueue(c, set_of(g + kAhead), chunks + first[g + kAhead], first[g + kAhead + 1] - first[g + kAhead], c->s_h2d, c->s_chk, 1)) != FSB_OK) break;
+            if ((rc = stage_enqueue(c, set_of(g + kAhead), chunks + first[g + kAhead], first[g + kAhead + 1] - first[g + kAhead], c->s_h2d, c->s_chk[(g + kAhead) % kSets], 1)) != FSB_OK) break;
         }
         if ((rc = finish(g)) != FSB_OK) break;
         trace.mark("copy out enqueued", g);
