@@ -483,6 +483,8 @@ def run_b200_arm(args, w, name):
     per_stage = {k: v / max(runs, 1) for k, v in stage_ms.items()}
     dom = max(per_stage, key=lambda k: per_stage[k])
     dom_ms = per_stage[dom]
+    if not dom_ms > 0:                                 # no per-stage times (should not happen): the line must still come out
+        dom, dom_ms = "whole path (per-stage times missing)", ms_per_step
     alg_in = alg_bytes - out_bytes
     # bytes each big kernel moves by itself, algorithmically: K1 consumes the input and produces the slot
     # payload (the dna / qua / head bits in stored form) + key and card; K4 consumes that payload and produces the streams

@@ -305,6 +305,7 @@ struct fsb_ctx
     // ---- profiling -----------------------------------------------------------------------------
     std::vector<cudaEvent_t> events;             // kMaxPendingProfiles * (FSB_STAGE_COUNT + 1)
     int pending_profiles = 0;
+    std::vector<uint8_t> pending_first;          // per pending profile: it is the first sub-batch of its run
     float stage_ms[FSB_STAGE_COUNT] = {0, 0, 0, 0};
     uint32_t stage_runs = 0;
     cudaEvent_t ev_check[2] = {nullptr, nullptr};   // around the input-check kernels of fsb_stage (FSB_OPT_PROFILE)
@@ -421,7 +422,7 @@ int resolve_profiles(fsb_ctx* c)
             CUDA_TRY(c, cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
             c->stage_ms[s] += ms;
         }
-        c->stage_runs++;
+        if (c->pending_first[r]) c->stage_runs++;                 // a batch with more than 32 chunks runs as several sub-batches: one run
     }
     c->pending_profiles = 0;
     return FSB_OK;
@@ -879,7 +880,7 @@ int stage_complete(fsb_ctx* c, Batch& b)
         CUDA_TRY(c, ensure_shared(L.st, L.d_scan_tmp, 4 * (scan_num_tiles(max_scan_n) + 2) * 8));
         uint32_t lchunks = 0;
         for (size_t j = l; j < b.subs.size(); j += 2) lchunks = std::max(lchunks, b.subs[j].c1 - b.subs[j].c0);
-        CUDA_TRY(c, ensure_shared(L.st, L.d_lay_states, ((ln + kLayBlock - 1) / kLayBlock + 2) * sizeof(LayState)));
+        CUDA_TRY(c, ensure_shared(L.st, L.d_lay_states, ((ln + kLayBlock - 1) / kLayBlock + 2 + ((ln + kLayBlock - 1) / kLayBlock) / kLayScanThreads + 2) * sizeof(LayState)));      // block states, the total, the scan's group totals
         CUDA_TRY(c, ensure_shared(L.st, L.d_chunk_start, ((size_t)lchunks + 2) * sizeof(ChunkStart)));
         CUDA_TRY(c, ensure_shared(L.st, L.d_nb, 64));
         CUDA_TRY(c, ensure_shared(L.st, L.d_flags, (ln + 4) * 4));
@@ -1024,10 +1025,12 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
         LayState* states = L.d_lay_states.as<LayState>();
         ChunkStart* cstart = L.d_chunk_start.as<ChunkStart>();
         lay_reduce_kernel<<<nlay, kLayThreads, 0, st>>>(n, P, S, b.min_len, states);
-        lay_scan_kernel<<<1, kLayScanThreads, 0, st>>>(states, nlay);
+        const unsigned ngroups = (nlay + kLayScanThreads - 1) / kLayScanThreads;
+        lay_scan_groups_kernel<<<ngroups, kLayScanThreads, 0, st>>>(states, nlay, states + nlay + 1);
+        lay_scan_finish_kernel<<<ngroups, kLayScanThreads, 0, st>>>(states, nlay, states + nlay + 1);
         lay_apply_kernel<<<nlay, kLayThreads, 0, st>>>(n, sub_chunks, P, S, b.min_len, states, LayOut{pm, O, desc, cstart, L.d_nb.as<uint32_t>()});
         chunk_summary_fused_kernel<<<sub_chunks, 128, 0, st>>>(B, cstart, desc, b.d_summary.as<ChunkSummary>() + sb.c0);
-        launches += 4;
+        launches += 5;
     }
     else
     {
@@ -1092,14 +1095,16 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
 // and the hardware interleaves the blocks of whatever kernels the two lanes have in flight.
 int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
 {
-    const bool split = b.subs.size() > 1;
-    cudaEvent_t* ev = nullptr;
-    if (profile && !split)
+    // FSB_OPT_PROFILE times the stages of an unsplit run: sub-batches that exist only because a batch holds more than 32 chunks
+    // then follow each other on one stream, each with its own events
+    const bool timed = profile && b.split <= 1;
+    const bool split = b.subs.size() > 1 && !timed;
+    if (timed)
     {
-        if (c->pending_profiles == kMaxPendingProfiles) { int rc = resolve_profiles(c); if (rc != FSB_OK) return rc; }
-        const size_t need = (size_t)(c->pending_profiles + 1) * (FSB_STAGE_COUNT + 1);
+        if (c->pending_profiles + (int)b.subs.size() > kMaxPendingProfiles) { int rc = resolve_profiles(c); if (rc != FSB_OK) return rc; }
+        const size_t need = (size_t)(c->pending_profiles + b.subs.size()) * (FSB_STAGE_COUNT + 1);
         while (c->events.size() < need) { cudaEvent_t e; CUDA_TRY(c, cudaEventCreate(&e)); c->events.push_back(e); }
-        ev = &c->events[(size_t)c->pending_profiles * (FSB_STAGE_COUNT + 1)];
+        c->pending_first.resize(kMaxPendingProfiles + b.subs.size(), 0);
     }
     if (split)
     {
@@ -1109,15 +1114,21 @@ int run_enqueue(fsb_ctx* c, Batch& b, bool profile)
     for (size_t j = 0; j < b.subs.size(); ++j)
     {
         const bool blocks = split || c->block_grids_always;
+        cudaEvent_t* ev = nullptr;
+        if (timed)
+        {
+            ev = &c->events[(size_t)c->pending_profiles * (FSB_STAGE_COUNT + 1)];
+            c->pending_first[c->pending_profiles] = j == 0;
+        }
         const int rc = run_sub(c, b, b.subs[j], c->lane[split ? (j & 1) : 0], ev, blocks ? c->k1_batches_per_warp : 0u, blocks ? c->k4_tiles_per_block : 0u);
         if (rc != FSB_OK) return rc;
+        if (timed) c->pending_profiles++;
     }
     if (split)
     {
         CUDA_TRY(c, cudaEventRecord(c->lane[1].ev_done, c->lane[1].st));
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->lane[1].ev_done, 0));
     }
-    if (ev) c->pending_profiles++;
     b.ran = true;
     return FSB_OK;
 }

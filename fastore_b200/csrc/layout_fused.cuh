@@ -8,7 +8,7 @@
 // Mapping: a thread owns one K4 tile (32 consecutive sorted records) and walks over it sequentially; a block
 // of 128 threads owns 4096 records.
 //   lay_reduce   every block's LayState                              -> tile_states[block]
-//   lay_scan     one block: exclusive scan over the block states      (in place; [nblocks] = the whole batch)
+//   lay_scan_groups / lay_scan_finish   exclusive scan over the block states (in place; [nblocks] = the whole batch)
 //   lay_apply    thread prefix = block prefix (+) threads in front; absolute walk that writes loc / binfo / tbase,
 //                clears the stream words two K4 tiles share, and emits the descriptor of every bin at its last record
 //   chunk_summary_fused   per chunk: first bin, stream offsets and sizes, raw sizes (block per chunk)
@@ -131,33 +131,40 @@ __global__ void __launch_bounds__(kLayThreads) lay_reduce_kernel(uint64_t n, Dev
     if (threadIdx.x == 0) tile_states[blockIdx.x] = total;
 }
 
-// one block: states[j] <- combination of states[0 .. j)  (j = 0 .. count; entry [count] is the whole batch)
+// states[j] <- combination of states[0 .. j)  (j = 0 .. count; entry [count] is the whole batch), in two launches over groups
+// of kLayScanThreads states: a group scans itself and leaves its total in group_totals[group]; then every state takes the
+// groups in front of its own (a few dozen at most: a batch of 2^28 records has 2^16 block states, i.e. 256 groups).
 constexpr uint32_t kLayScanThreads = 256;
-__global__ void __launch_bounds__(kLayScanThreads) lay_scan_kernel(LayState* __restrict__ states, uint32_t count)
+__global__ void __launch_bounds__(kLayScanThreads) lay_scan_groups_kernel(LayState* __restrict__ states, uint32_t count, LayState* __restrict__ group_totals)
 {
     __shared__ LayState sm[kLayScanThreads / 32];
-    __shared__ LayState carry_sm;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_sm = lay_identity();
+    const uint32_t j = blockIdx.x * kLayScanThreads + threadIdx.x;
+    const LayState mine = j < count ? states[j] : lay_identity();
+    const LayState inc = lay_warp_scan(mine);
+    if (lane == 31) sm[warp] = inc;
     __syncthreads();
-    for (uint32_t base = 0; base < count; base += kLayScanThreads)
+    LayState before = lay_identity();                               // the warps in front of this one
+    for (unsigned w = 0; w < warp; ++w) before = lay_combine(before, sm[w]);
+    LayState excl = lay_shfl_up(inc, 1);
+    if (lane == 0) excl = lay_identity();
+    const LayState pre = lay_combine(before, excl);
+    if (j < count) states[j] = pre;
+    if (threadIdx.x == kLayScanThreads - 1) group_totals[blockIdx.x] = lay_combine(pre, mine);
+}
+__global__ void __launch_bounds__(kLayScanThreads) lay_scan_finish_kernel(LayState* __restrict__ states, uint32_t count, const LayState* __restrict__ group_totals)
+{
+    __shared__ LayState front_sm;
+    if (threadIdx.x == 0)
     {
-        const uint32_t j = base + threadIdx.x;
-        const LayState mine = j < count ? states[j] : lay_identity();
-        const LayState inc = lay_warp_scan(mine);
-        if (lane == 31) sm[warp] = inc;
-        __syncthreads();
-        LayState before = carry_sm;                                 // everything in front of this round, then the warps in front
-        for (unsigned w = 0; w < warp; ++w) before = lay_combine(before, sm[w]);
-        LayState excl = lay_shfl_up(inc, 1);
-        if (lane == 0) excl = lay_identity();
-        const LayState pre = lay_combine(before, excl);
-        if (j < count) states[j] = pre;
-        __syncthreads();
-        if (threadIdx.x == kLayScanThreads - 1) carry_sm = lay_combine(pre, mine);
-        __syncthreads();
+        LayState f = lay_identity();
+        for (uint32_t g = 0; g < blockIdx.x; ++g) f = lay_combine(f, group_totals[g]);
+        front_sm = f;
+        if (blockIdx.x == gridDim.x - 1) states[count] = lay_combine(f, group_totals[blockIdx.x]);
     }
-    if (threadIdx.x == 0) states[count] = carry_sm;
+    __syncthreads();
+    const uint32_t j = blockIdx.x * kLayScanThreads + threadIdx.x;
+    if (blockIdx.x && j < count) states[j] = lay_combine(front_sm, states[j]);
 }
 
 // first bin and first stream bytes of every chunk that holds records; entry [n_chunks] = bins and stream bytes of the whole batch
