@@ -155,30 +155,35 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
 // Every lane copies the aligned window around its own span, one 16-byte piece per step.  (Spreading a
 // span over several lanes would coalesce the requests, but costs two shuffles and an index
 // computation per piece; and every line is still fetched from HBM exactly once.)
-// The windows of a warp are copied by the warp together: eight lanes per window, lane k of a group copies
-// pieces k and k + 8, so that one instruction requests whole 128-byte runs (four windows at a time) instead of
-// 32 separate half-used sectors -- the memory side of K1 is bound by L2 requests, not by bytes.  Must be called
-// by all lanes of the warp.
+// The windows of a warp are copied by the warp together: GL lanes per window, lane k of a group copies
+// pieces k, k + GL, ..., so that one instruction requests runs of 16 GL bytes (32 / GL windows at a time) instead of
+// 32 separate half-used sectors -- the memory side of K1 is bound by L2 requests, not by bytes.  Fewer lanes per
+// window mean fewer trips through the loop (its shuffles and address arithmetic are paid per trip) but shorter
+// runs per request; FSB_K1_GATHER_LANES picks the balance (measured: profiles/).  Must be called by all lanes of the warp.
+#ifndef FSB_K1_GATHER_LANES
+#define FSB_K1_GATHER_LANES 8
+#endif
 template <int NW>
 __device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece0, uint32_t npieces, const uint8_t* text)
 {
-    static_assert(win_pieces<NW>() <= 24, "three pieces per lane of a group cover a window");
-    const unsigned lane = threadIdx.x & 31, l8 = lane & 7u, grp = lane >> 3;
+    constexpr unsigned GL = FSB_K1_GATHER_LANES;                           // lanes per window
+    constexpr unsigned PPL = (win_pieces<NW>() + GL - 1) / GL;             // pieces per lane
+    static_assert(GL == 2 || GL == 4 || GL == 8 || GL == 16, "lanes per window: a power of two");
+    const unsigned lane = threadIdx.x & 31, lg = lane & (GL - 1u), grp = lane / GL;
     const unsigned long long my_src = (unsigned long long)(text + (piece0 << 4));
     // shared address of the first piece (below 2^24) and the number of pieces in one word
     const uint32_t my_dst = ((uint32_t)__cvta_generic_to_shared(my_window) + 16u) | (min(npieces, win_pieces<NW>()) << 24);
 #pragma unroll 1
-    for (uint32_t w0 = 0; w0 < 32u; w0 += 4)
+    for (uint32_t w0 = 0; w0 < 32u; w0 += 32u / GL)
     {
         const unsigned from = w0 + grp;
         const unsigned long long src = __shfl_sync(0xFFFFFFFFu, my_src, from);
         const uint32_t dn = __shfl_sync(0xFFFFFFFFu, my_dst, from);
-        const uint32_t np = dn >> 24, dst = (dn & 0xFFFFFFu) + 16u * l8;
-        const uint8_t* sp = reinterpret_cast<const uint8_t*>(src) + 16u * l8;
+        const uint32_t np = dn >> 24, dst = (dn & 0xFFFFFFu) + 16u * lg;
+        const uint8_t* sp = reinterpret_cast<const uint8_t*>(src) + 16u * lg;
 #ifndef FSB_EXP_NOGATHER
-        cp_async16_if(l8 < np, dst, sp);
-        cp_async16_if(l8 + 8u < np, dst + 128u, sp + 128u);
-        if (win_pieces<NW>() > 16) cp_async16_if(l8 + 16u < np, dst + 256u, sp + 256u);
+#pragma unroll
+        for (unsigned q = 0; q < PPL; ++q) cp_async16_if(lg + q * GL < np, dst + 16u * q * GL, sp + 16u * q * GL);
 #else
         (void)dst; (void)sp; (void)np;
 #endif
