@@ -161,7 +161,7 @@ inline IngestPlan make_ingest_plan(const DeviceParams& P, const SlotGeom& G, uin
 // window mean fewer trips through the loop (its shuffles and address arithmetic are paid per trip) but shorter
 // runs per request; FSB_K1_GATHER_LANES picks the balance (measured: profiles/).  Must be called by all lanes of the warp.
 #ifndef FSB_K1_GATHER_LANES
-#define FSB_K1_GATHER_LANES 8
+#define FSB_K1_GATHER_LANES 4
 #endif
 template <int NW>
 __device__ __forceinline__ void gather_window(uint8_t* my_window, uint64_t piece0, uint32_t npieces, const uint8_t* text)
