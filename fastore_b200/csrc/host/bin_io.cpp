@@ -16,6 +16,10 @@
 #include <thread>
 #include <vector>
 
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
 namespace {
 
 thread_local std::string g_err;
@@ -34,14 +38,50 @@ struct MultiFile                       // IMultiFileStreamReader::Read (FileStre
         if (f) std::setvbuf(f, nullptr, _IOFBF, 8u << 20);
         return f != nullptr;
     }
+    // A large request on a regular file is read as kSlices positioned reads side by side (one thread is bound by a single
+    // core's copy speed: ~4 GB/s from the page cache); anything else goes through fread.
+    int64_t read_current(uint8_t* mem, uint64_t size)
+    {
+        constexpr uint64_t kParallelFrom = 32ull << 20;
+        constexpr int kSlices = 4;
+        struct stat st;
+        const int fd = fileno(f);
+        const off_t at = ftello(f);
+        if (size >= kParallelFrom && fd >= 0 && at >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > at)
+        {
+            const uint64_t n = std::min<uint64_t>(size, (uint64_t)(st.st_size - at));
+            const uint64_t per = (n + kSlices - 1) / kSlices;
+            bool ok[kSlices];
+            auto slice = [&](int k)
+            {
+                uint64_t o = std::min<uint64_t>(n, (uint64_t)k * per), end = std::min<uint64_t>(n, o + per);
+                ok[k] = true;
+                while (o < end)
+                {
+                    const ssize_t g = pread(fd, mem + o, end - o, at + (off_t)o);
+                    if (g <= 0) { ok[k] = false; return; }
+                    o += (uint64_t)g;
+                }
+            };
+            std::thread th[kSlices - 1];
+            for (int k = 1; k < kSlices; ++k) th[k - 1] = std::thread(slice, k);
+            slice(0);
+            for (int k = 1; k < kSlices; ++k) th[k - 1].join();
+            bool all = true;
+            for (int k = 0; k < kSlices; ++k) all = all && ok[k];
+            if (all && fseeko(f, at + (off_t)n, SEEK_SET) == 0) return (int64_t)n;
+            fseeko(f, at, SEEK_SET);                                // fall back to the plain read
+        }
+        return (int64_t)std::fread(mem, 1, size, f);
+    }
     int64_t read(uint8_t* mem, uint64_t size)
     {
         if (!f) return 0;
-        int64_t n = (int64_t)std::fread(mem, 1, size, f);
+        int64_t n = read_current(mem, size);
         while (n < (int64_t)size && open_next())
         {
-            const size_t n2 = std::fread(mem + n, 1, size - n, f);
-            if (n2 > 0) n += (int64_t)n2;
+            const int64_t n2 = read_current(mem + n, size - (uint64_t)n);
+            if (n2 > 0) n += n2;
         }
         return n;
     }
