@@ -199,13 +199,53 @@ FSB_HD uint32_t key_zero_mix(uint32_t df, uint32_t dr, uint32_t plane)      // c
 {
     return (df & ~plane) | (dr & plane);
 }
+// a | b | c as one three-input logic op that the compiler will not fold into a longer chain
+FSB_HD uint32_t or3(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xFE;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return a | b | c;
+#endif
+}
+// The step's decision needs the OR over all words.  Written as a running `o |= ...` it becomes a chain of 2 NW dependent
+// logic ops per bit step -- the longest dependency of the kernel, 16 times per mate; as NW independent ops and a tree of
+// three-input ORs the chain is 1 + ceil(log3 NW) deep and two ops shorter.
 template <int NW>
 FSB_HD uint32_t descend_step_joint(BV<NW>& Df, BV<NW>& Dr, const BV<NW>& plane)
 {
+#ifdef FSB_K1_DESCENT_CHAIN                                          // (the running OR, for comparison)
     uint32_t o = 0;
 #pragma unroll
     for (int j = 0; j < NW; ++j) o |= key_zero_mix(Df.w[j], Dr.w[j], plane.w[j]);
-    const uint32_t am = mask_nonzero(o);
+    const uint32_t am0 = mask_nonzero(o);
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { Df.w[j] = drop_ones<false>(Df.w[j], am0, plane.w[j]); Dr.w[j] = drop_ones<true>(Dr.w[j], am0, plane.w[j]); }
+    return am0;
+#endif
+    uint32_t z[NW + 2];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) z[j] = key_zero_mix(Df.w[j], Dr.w[j], plane.w[j]);
+    z[NW] = 0; z[NW + 1] = 0;
+    int n = NW;
+#pragma unroll
+    for (int round = 0; round < 3; ++round)                      // 3 rounds reduce up to 27 words
+    {
+        if (n > 1)
+        {
+            const int m = (n + 2) / 3;
+#pragma unroll
+            for (int j = 0; j < m; ++j)
+            {
+                const uint32_t a = z[3 * j], b = (3 * j + 1 < n) ? z[3 * j + 1] : 0u, c = (3 * j + 2 < n) ? z[3 * j + 2] : 0u;
+                z[j] = (3 * j + 2 < n) ? or3(a, b, c) : (a | b);
+            }
+            n = m;
+        }
+    }
+    const uint32_t am = mask_nonzero(z[0]);
 #pragma unroll
     for (int j = 0; j < NW; ++j) { Df.w[j] = drop_ones<false>(Df.w[j], am, plane.w[j]); Dr.w[j] = drop_ones<true>(Dr.w[j], am, plane.w[j]); }
     return am;
@@ -215,10 +255,14 @@ FSB_HD void descend_joint(const BV<NW>& Cf, const BV<NW>& Cr, const BV<NW>& H, c
                           StrandMin& fwd, StrandMin& rev)
 {
     BV<NW> Df = Cf, Dr = bv_shl(Cr, P.k - 1);
-    uint32_t m = 0;
-    for (uint32_t d = 0; d < P.k; ++d)
+    uint32_t m = descend_step_joint<NW>(Df, Dr, H);               // symbol 0 in place, then k - 1 times: move on, two bit steps
+    m = 2 * m + descend_step_joint<NW>(Df, Dr, Lo);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+    for (uint32_t d = 1; d < P.k; ++d)
     {
-        if (d) { Df = bv_shl(Df, 1); Dr = bv_shr(Dr, 1); }
+        Df = bv_shl(Df, 1); Dr = bv_shr(Dr, 1);
         m = 2 * m + descend_step_joint<NW>(Df, Dr, H);
         m = 2 * m + descend_step_joint<NW>(Df, Dr, Lo);
     }
