@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -44,10 +45,11 @@ struct MultiFile                       // IMultiFileStreamReader::Read (FileStre
     {
         constexpr uint64_t kParallelFrom = 32ull << 20;
         constexpr int kSlices = 4;
+        static const bool sliced = []() { const char* e = std::getenv("FSH_READ_SLICES"); return !(e && std::atoi(e) <= 1); }();
         struct stat st;
         const int fd = fileno(f);
         const off_t at = ftello(f);
-        if (size >= kParallelFrom && fd >= 0 && at >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > at)
+        if (sliced && size >= kParallelFrom && fd >= 0 && at >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > at)
         {
             const uint64_t n = std::min<uint64_t>(size, (uint64_t)(st.st_size - at));
             const uint64_t per = (n + kSlices - 1) / kSlices;
