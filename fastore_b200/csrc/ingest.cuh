@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
         __syncwarp();
         if (live && roleB) seg_finish(ed, true);
         __syncwarp();
-        {   // the warp's slots leave as whole lines: 8 lanes per record, one 16-byte vector each per step
+        {   // the warp's slots leave as whole lines: 8 lanes per record, 16-byte vectors; a lane's (up to four) vectors of a record
+            // are loaded together and then stored, so that the stores do not each wait for a shared-memory load of their own
             const uint32_t nvec = (G.qw + G.tw + 3u) >> 2, sub = lane >> 3, l8 = lane & 7u;
             uint32_t sa = (uint32_t)__cvta_generic_to_shared(stg) + 16u * l8 + sub * pl.stg_stride * 4u;
             uint32_t* const batch_slots = slots + rec0 * G.words;
@@ -449,9 +450,16 @@ __global__ void __launch_bounds__(kIngestMaxWarps * 32, FSB_K1_MINBLOCKS) ingest
 #pragma unroll 1
             for (uint32_t r = sub; r < nrec; r += 4)
             {
-#pragma unroll 1
 #ifndef FSB_EXP_NOCOPYOUT
-                for (uint32_t v = l8; v < nvec; v += 8) *reinterpret_cast<uint4*>(batch_slots + di + 4u * (v - l8)) = lds128(sa + 16u * (v - l8));
+#pragma unroll 1
+                for (uint32_t v = l8; v < nvec; v += 32)
+                {
+                    uint4 t[4];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) if (v + 8u * u < nvec) t[u] = lds128(sa + 16u * (v + 8u * u - l8));
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) if (v + 8u * u < nvec) *reinterpret_cast<uint4*>(batch_slots + di + 4u * (v + 8u * u - l8)) = t[u];
+                }
 #endif
                 sa += 16u * pl.stg_stride; di += 4u * G.words;
             }
