@@ -117,3 +117,32 @@ def test_title_statistics_merged_per_chunk_equal_the_reference(tmp_path):
     BF.run_reference_bin(files, tmp_path / "ref", flags)
     BF.host_chain(files, tmp_path / "ours", flags, BF.oracle_producer, merge_titles=True)
     BF.assert_bin_files_equal(tmp_path / "ours", tmp_path / "ref", True)
+
+
+def test_large_requests_read_as_slices_reassemble_the_file(tmp_path):
+    """The chunk reader serves requests of 32 MB and more on regular files as four positioned reads side by side
+    (bin_io.cpp: MultiFile::read_current); smaller ones go through fread.  Either way the chunks, put back together with the
+    line ends the cutter drops between them, are the file -- also across the seam between two input files."""
+    lib = N.host_lib()
+    lib.fsh_reader_open.restype = C.c_void_p
+    lib.fsh_reader_open.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint64]
+    lib.fsh_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.fsh_reader_close.argtypes = [C.c_void_p]
+    cfg = synth.synth_config(330000, 100, seed=77)                    # 71 MB
+    text, _, _, _ = synth.generate(cfg, threads=4)
+    raw = text.tobytes()
+    cut = raw.find(b"\n@", len(raw) // 3) + 1                         # two input files, split at a record boundary
+    paths = [tmp_path / "a.fastq", tmp_path / "b.fastq"]
+    paths[0].write_bytes(raw[:cut]); paths[1].write_bytes(raw[cut:])
+    for block in (40 << 20, 12 << 20):                                # sliced reads / plain reads
+        files = (C.c_char_p * 2)(str(paths[0]).encode(), str(paths[1]).encode())
+        r = lib.fsh_reader_open(files, 2, None, 0, block)
+        assert r
+        buf = np.empty(block + 64, dtype=np.uint8)
+        size = C.c_uint64()
+        chunks = []
+        while lib.fsh_reader_next(r, buf.ctypes.data, C.byref(size), None, None) > 0 and size.value:
+            chunks.append(buf[: size.value].tobytes())
+        lib.fsh_reader_close(r)
+        assert len(chunks) >= 2
+        assert b"\n".join(chunks) + b"\n" == raw, f"block {block >> 20} MB"
