@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 
 #include "core.cuh"
+#include "parse_core.cuh"
 
 namespace fsb {
 
@@ -62,39 +63,6 @@ __device__ __forceinline__ uint32_t parse_seg_of_tile(const ParseSeg* __restrict
     return lo;
 }
 
-// 0x80 in every byte of w that equals the byte repeated in pattern4 (exact: no borrow crosses a byte)
-__device__ __forceinline__ uint32_t bytes_equal(uint32_t w, uint32_t pattern4)
-{
-    const uint32_t x = w ^ pattern4;
-    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
-}
-// The flags of two words (0x80 per byte) as eight mask bits, byte b of word j at bit 4 j + b: with c = f0 >> 7 | f1 >> 3 byte b
-// holds its two flags at bits 0 and 4, and one multiplication moves byte b down by 7 b places next to its neighbours (every
-// stray product term lands on a position of its own below bit 21 or above bit 28, so nothing carries into the result).
-__device__ __forceinline__ uint32_t gather_flags8(uint32_t f0, uint32_t f1)
-{
-    const uint32_t c = (f0 >> 7) | (f1 >> 3);
-    return ((c * ((1u << 21) | (1u << 14) | (1u << 7) | 1u)) >> 21) & 0xFFu;
-}
-// bit b of the result: byte b of the vector ends a line -- it is LF, or CR not followed by LF (FastqParser.cpp:46-68).
-// `next` = the byte behind the vector (0 if none); bytes from `valid_bytes` on do not belong to the text.
-__device__ __forceinline__ uint32_t line_end_mask(const uint4& v, uint32_t next, uint32_t valid_bytes)
-{
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t lf[5], e[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) lf[j] = bytes_equal(w[j], 0x0A0A0A0Au);
-    lf[4] = next == '\n' ? 0x80u : 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-    {
-        const uint32_t lf_behind = __funnelshift_r(lf[j], lf[j + 1], 8);           // the LF flag of the byte behind every byte
-        e[j] = lf[j] | (bytes_equal(w[j], 0x0D0D0D0Du) & ~lf_behind);
-    }
-    const uint32_t m = gather_flags8(e[0], e[1]) | (gather_flags8(e[2], e[3]) << 8);
-    return valid_bytes >= 16u ? m : (m & ((1u << valid_bytes) - 1u));
-}
-
 // vector `vec` (0 .. kParseTileVecs) of a tile, the byte behind it, and how many of its bytes belong to the segment; must be
 // called by whole warps with consecutive `vec` in consecutive lanes
 struct ParseVec { uint4 v; uint32_t next; uint32_t valid; unsigned long long off; };
@@ -128,7 +96,8 @@ __global__ void __launch_bounds__(kParseThreads) parse_count_kernel(const uint8_
     {
         const uint32_t vec = k * kParseThreads + threadIdx.x;
         const ParseVec pv = parse_load(text, s, tile, vec);
-        const uint32_t m = line_end_mask(pv.v, pv.next, pv.valid);
+        const uint32_t vw[4] = {pv.v.x, pv.v.y, pv.v.z, pv.v.w};
+        const uint32_t m = line_end_mask(vw, pv.next, pv.valid);
         end_mask[tile * kParseTileVecs + vec] = (uint16_t)m;
         cnt += __popc(m);
     }

@@ -434,3 +434,20 @@ extern "C" int emul_new_minimizers(const fsb_params* p, const uint8_t* text, uin
     }
     return FSB_OK;
 }
+
+// ---- device-side parse: the line-end mask of every 16-byte vector of a text (parse_core.cuh) -------------------------
+#include "../../fastore_b200/csrc/parse_core.cuh"
+
+extern "C" void emul_line_end_masks(const uint8_t* text, uint64_t size, uint16_t* masks /* ceil(size / 16) */)
+{
+    for (uint64_t off = 0; off < size; off += 16)
+    {
+        uint8_t v[16] = {0};
+        const uint32_t valid = (uint32_t)std::min<uint64_t>(16, size - off);
+        std::memcpy(v, text + off, valid);
+        uint32_t w[4];
+        std::memcpy(w, v, 16);
+        const uint32_t next = off + 16 < size ? text[off + 16] : 0u;           // parse_load: the byte behind the vector, 0 at the end of the text
+        masks[off / 16] = (uint16_t)fsb::line_end_mask(w, next, valid);
+    }
+}

@@ -74,3 +74,22 @@ def test_one_scan_layout_matches_the_sequential_walk(emul, name, per_thread, thr
     if bad == -1:
         pytest.skip("reads of different lengths")
     assert bad == 0, f"{name}: {bad} mismatches"
+
+
+def test_line_end_masks_follow_skipline(emul):
+    """parse_core.cuh finds line ends four bytes at a time; here against the byte-by-byte rule of SkipLine
+    (FastqParser.cpp:46-68): LF ends a line, CR ends a line unless an LF follows it."""
+    emul.emul_line_end_masks.restype = None
+    emul.emul_line_end_masks.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"\n\r\n\rACGTN@+I!~\x00\x0b\x0c\x0e\x8a\x8d\xff", dtype=np.uint8)      # line ends often, and their near misses
+    for size in (0, 1, 15, 16, 17, 31, 32, 33, 4096, 100003):
+        text = alphabet[rng.integers(0, alphabet.size, size)].copy()
+        masks = np.zeros((size + 15) // 16 + 1, dtype=np.uint16)
+        emul.emul_line_end_masks(N.np_ptr(text), size, N.np_ptr(masks))
+        nxt = np.append(text[1:], 0) if size else text
+        ends = (text == 10) | ((text == 13) & (nxt != 10))
+        padded = np.zeros(((size + 15) // 16) * 16, dtype=bool)
+        padded[:size] = ends
+        want = (padded.reshape(-1, 16) * (1 << np.arange(16))).sum(axis=1).astype(np.uint16) if size else np.zeros(0, np.uint16)
+        assert np.array_equal(masks[: want.size], want), f"size {size}"
