@@ -154,8 +154,6 @@ __global__ void __launch_bounds__(kParseThreads) parse_lines_kernel(const uint16
     }
 }
 
-enum { kStopNone = 0, kStopBadTitle = 1, kStopEmptyPlus = 2, kStopLenMismatch = 3 };     // FSH_STOP_* (host_api.h)
-
 // records: [mate] the record tables of the batch.  One thread per record candidate of a segment (blockIdx.y = segment).
 __global__ void __launch_bounds__(256) parse_records_kernel(const uint8_t* __restrict__ text0, const uint8_t* __restrict__ text1, const ParseSeg* __restrict__ segs,
                                                             const uint32_t* __restrict__ line_start, uint32_t keep_headers, uint32_t keep_comments,
@@ -165,42 +163,11 @@ __global__ void __launch_bounds__(256) parse_records_kernel(const uint8_t* __res
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= s.cap) return;
     const uint8_t* text = (s.mate ? text1 : text0) + s.text_base;
-    const uint32_t* ls = line_start + s.line0;
-    const uint32_t L = s.n_lines;
-    // what SkipLine returns for line j and where the line starts; lines past the last one are empty (the scan has hit the end of the memory)
-    auto line = [&](uint32_t j, uint32_t& start) -> uint32_t
-    {
-        if (j >= L) { start = (uint32_t)s.size; return 0u; }
-        start = ls[j];
-        if (j < s.n_ends)
-        {   // the line has a line end at ls[j + 1] - 1
-            const uint32_t term = ls[j + 1] - 1u;
-            const bool crlf = text[term] == '\n' && term > start && text[term - 1] == '\r';
-            return term - start - (crlf ? 1u : 0u);
-        }
-        return (uint32_t)s.size - start;                          // the last line of a text without a final line end
-    };
-    uint32_t title, seq, plus, qua;
-    const uint32_t titleLen = line(4u * r, title), seqLen = line(4u * r + 1u, seq), plusLen = line(4u * r + 2u, plus), quaLen = line(4u * r + 3u, qua);
-    uint32_t reason = kStopNone;
-    if (titleLen == 0 || text[title] != '@') reason = kStopBadTitle;                       // FastqParser.cpp:125
-    else if ((plusLen & 0xFFFFu) == 0) reason = kStopEmptyPlus;                            // :132-134 (uint16 plen)
-    else if ((quaLen & 0xFFFFu) != seqLen) reason = kStopLenMismatch;                      // :137-139 (uint16 qlen)
-    if (reason != kStopNone) { atomicMin(&results[blockIdx.y].first_bad, ((unsigned long long)r << 8) | reason); return; }
-    uint32_t headLen = 0;
-    if (keep_headers)
-    {
-        headLen = titleLen;
-        if (!keep_comments)                                        // :148-155: the title ends at the first space
-        {
-            const uint32_t lim = min(titleLen, 257u);             // beyond 255 the record is outside the contract anyway
-            for (uint32_t i = 0; i < lim; ++i) if (text[title + i] == ' ') { headLen = i; break; }
-        }
-    }
-    if (seqLen < 1 || seqLen > 255 || headLen > 255) atomicMin(&results[blockIdx.y].first_invalid, (unsigned long long)r);
     fsb_record o;
-    o.head_off = title; o.seq_off = seq; o.qua_off = qua;
-    o.seq_len = (uint16_t)seqLen; o.head_len = (uint8_t)headLen; o.reserved = 0;
+    bool invalid = false;
+    const uint32_t reason = parse_candidate(text, (uint32_t)s.size, line_start + s.line0, s.n_ends, s.n_lines, r, keep_headers != 0, keep_comments != 0, o, invalid);
+    if (reason != kStopNone) { atomicMin(&results[blockIdx.y].first_bad, ((unsigned long long)r << 8) | reason); return; }
+    if (invalid) atomicMin(&results[blockIdx.y].first_invalid, (unsigned long long)r);
     (s.mate ? rec1 : rec0)[s.rec0 + r] = o;
 }
 

@@ -451,3 +451,34 @@ extern "C" void emul_line_end_masks(const uint8_t* text, uint64_t size, uint16_t
         masks[off / 16] = (uint16_t)fsb::line_end_mask(w, next, valid);
     }
 }
+
+// The whole device-side parse of one text, pass by pass as the kernels do it (parse.cuh): masks -> line starts -> candidates.
+// Returns the number of records in front of the first rejected candidate; *first_invalid = first record outside the device
+// contract among them (~0: none).
+extern "C" uint64_t emul_parse_text(const uint8_t* text, uint64_t size, int keep_headers, int keep_comments, fsb_record* out, uint64_t capacity,
+                                    uint32_t* stop_reason, uint64_t* first_invalid)
+{
+    std::vector<uint16_t> masks((size + 15) / 16 + 1, 0);
+    emul_line_end_masks(text, size, masks.data());
+    std::vector<uint32_t> ls{0};
+    for (uint64_t v = 0; v * 16 < size; ++v)
+        for (uint32_t b = 0; b < 16; ++b)
+            if (masks[v] >> b & 1u) ls.push_back((uint32_t)(v * 16 + b + 1));
+    const uint32_t n_ends = (uint32_t)ls.size() - 1;
+    const uint8_t last = size ? text[size - 1] : (uint8_t)'\n';
+    const uint32_t n_lines = n_ends + ((size && last != '\n' && last != '\r') ? 1u : 0u);
+    const uint32_t cap = (n_lines + 3u) / 4u;
+    *stop_reason = 0; *first_invalid = ~0ull;
+    uint64_t n = 0;
+    for (uint32_t r = 0; r < cap; ++r)
+    {
+        fsb_record o{};
+        bool invalid = false;
+        const uint32_t reason = fsb::parse_candidate(text, (uint32_t)size, ls.data(), n_ends, n_lines, r, keep_headers != 0, keep_comments != 0, o, invalid);
+        if (reason != fsb::kStopNone) { *stop_reason = reason; break; }
+        if (invalid && *first_invalid == ~0ull) *first_invalid = r;
+        if (n < capacity) out[n] = o;
+        ++n;
+    }
+    return n;
+}

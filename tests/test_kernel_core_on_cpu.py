@@ -12,6 +12,7 @@ import pytest
 import oracle_helpers as O
 from cases import CASES, make_case
 from fastore_b200 import _native as N
+from fastore_b200 import synth
 
 ROOT = Path(__file__).resolve().parent.parent
 EMUL_SRC = ROOT / "tests" / "emul" / "emul.cpp"
@@ -93,3 +94,25 @@ def test_line_end_masks_follow_skipline(emul):
         padded[:size] = ends
         want = (padded.reshape(-1, 16) * (1 << np.arange(16))).sum(axis=1).astype(np.uint16) if size else np.zeros(0, np.uint16)
         assert np.array_equal(masks[: want.size], want), f"size {size}"
+
+
+@pytest.mark.parametrize("keep_comments", [True, False])
+def test_device_parse_rules_equal_the_host_parser(emul, keep_comments):
+    """The three passes of the device-side parse (parse_core.cuh, run here on the host) against the host parser -- itself
+    pinned to SingleFastqRecordParser::ReadNextRecord by the whole-file tests -- for every kind of line end and for texts
+    that stop short.  tests/test_gpu_parse.py repeats this through the kernels."""
+    from test_gpu_parse import variants
+    emul.emul_parse_text.restype = C.c_uint64
+    emul.emul_parse_text.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    cfg = synth.synth_config(1500, 100, seed=51, header_comments=True, nrich=0.03)
+    t1, _, _, _ = synth.generate(cfg, threads=2)
+    for name, txt in variants(t1.tobytes()).items():
+        text = np.frombuffer(txt, dtype=np.uint8).copy()
+        want, _ = synth.parse_chunk(text, keep_headers=True, keep_comments=keep_comments, strict=True)
+        got = np.zeros(max(1, len(txt) // 8), dtype=N.RECORD_DTYPE)
+        reason, bad = C.c_uint32(), C.c_uint64()
+        n = emul.emul_parse_text(N.np_ptr(text), text.size, 1, int(keep_comments), N.np_ptr(got), got.shape[0], C.byref(reason), C.byref(bad))
+        assert n == want.shape[0], f"{name}: {n} records vs {want.shape[0]}"
+        assert bad.value == 2**64 - 1, name
+        for f in N.RECORD_DTYPE.names:
+            assert np.array_equal(got[f][:n], want[f]), f"{name}: field {f}"
