@@ -280,13 +280,13 @@ struct fsb_ctx
         DevBuf d_keys[2], d_cards[2], d_slots, d_counts, d_counts_scan, d_scan_tmp;
         DevBuf d_flags, d_flags_excl, d_bin_of, d_bin_start, d_bin_min, d_bin_max, d_raw_dna, d_raw_head, d_tbase;
         DevBuf d_bits[4], d_P[4], d_bytes[4], d_BO[4];
-        DevBuf d_lay_states, d_lay_thread_states, d_chunk_start, d_nb;     // the one-scan layout (layout_fused.cuh)
+        DevBuf d_lay_states, d_chunk_start, d_nb;     // the one-scan layout (layout_fused.cuh)
         template <class F> void each(F f)
         {
             DevBuf* all[] = {&d_keys[0], &d_keys[1], &d_cards[0], &d_cards[1], &d_slots, &d_counts, &d_counts_scan, &d_scan_tmp, &d_flags, &d_flags_excl,
                              &d_bin_of, &d_bin_start, &d_bin_min, &d_bin_max, &d_raw_dna, &d_raw_head, &d_tbase, &d_bits[0], &d_bits[1], &d_bits[2], &d_bits[3],
                              &d_P[0], &d_P[1], &d_P[2], &d_P[3], &d_bytes[0], &d_bytes[1], &d_bytes[2], &d_bytes[3], &d_BO[0], &d_BO[1], &d_BO[2], &d_BO[3],
-                             &d_lay_states, &d_lay_thread_states, &d_chunk_start, &d_nb};
+                             &d_lay_states, &d_chunk_start, &d_nb};
             for (DevBuf* d : all) f(*d);
         }
     } lane[2];
@@ -295,7 +295,6 @@ struct fsb_ctx
     uint32_t k1_batches_per_warp = 32, k4_tiles_per_block = 64;   // block granularity of K1 / K4 when sub-batches share the GPU (0: persistent)
     bool block_grids_always = false;             // use that granularity for unsplit runs too (measurement only)
     bool fused_layout = true;                    // batches of one read length take the one-scan layout (FSB_OPT_FUSED_LAYOUT, measurement only)
-    bool lay_thread_states = true;               // lay_reduce hands every thread's state to lay_apply (FSB_LAY_THREAD_STATES=0: lay_apply walks twice; measurement only)
     bool fused_hist = false;                     // K1 / every scatter pass count the digits of the next radix pass (FSB_OPT_FUSED_HIST).  Measured SLOWER than the
                                                  // histogram kernels (sort 0.79 vs 0.44 ms per 10M pairs, r02l): 10M scattered L2 reductions cost more than re-reading the keys
     bool keep_records = false;                   // device-side parse inside fsb_bin_chunks: copy the record tables back too (FSB_OPT_KEEP_RECORDS)
@@ -882,7 +881,6 @@ int stage_complete(fsb_ctx* c, Batch& b)
         uint32_t lchunks = 0;
         for (size_t j = l; j < b.subs.size(); j += 2) lchunks = std::max(lchunks, b.subs[j].c1 - b.subs[j].c0);
         CUDA_TRY(c, ensure_shared(L.st, L.d_lay_states, ((ln + kLayBlock - 1) / kLayBlock + 2 + ((ln + kLayBlock - 1) / kLayBlock) / kLayScanThreads + 2) * sizeof(LayState)));      // block states, the total, the scan's group totals
-        if (c->lay_thread_states) CUDA_TRY(c, ensure_shared(L.st, L.d_lay_thread_states, ((ln + kLayBlock - 1) / kLayBlock + 1) * kLayThreads * sizeof(LayState)));
         CUDA_TRY(c, ensure_shared(L.st, L.d_chunk_start, ((size_t)lchunks + 2) * sizeof(ChunkStart)));
         CUDA_TRY(c, ensure_shared(L.st, L.d_nb, 64));
         CUDA_TRY(c, ensure_shared(L.st, L.d_flags, (ln + 4) * 4));
@@ -1026,12 +1024,11 @@ int run_sub(fsb_ctx* c, Batch& b, const Sub& sb, fsb_ctx::Lane& L, cudaEvent_t* 
         const unsigned nlay = (unsigned)((n + kLayBlock - 1) / kLayBlock);
         LayState* states = L.d_lay_states.as<LayState>();
         ChunkStart* cstart = L.d_chunk_start.as<ChunkStart>();
-        LayState* tstates = c->lay_thread_states ? L.d_lay_thread_states.as<LayState>() : nullptr;
-        lay_reduce_kernel<<<nlay, kLayThreads, 0, st>>>(n, P, S, b.min_len, states, tstates);
+        lay_reduce_kernel<<<nlay, kLayThreads, 0, st>>>(n, P, S, b.min_len, states);
         const unsigned ngroups = (nlay + kLayScanThreads - 1) / kLayScanThreads;
         lay_scan_groups_kernel<<<ngroups, kLayScanThreads, 0, st>>>(states, nlay, states + nlay + 1);
         lay_scan_finish_kernel<<<ngroups, kLayScanThreads, 0, st>>>(states, nlay, states + nlay + 1);
-        lay_apply_kernel<<<nlay, kLayThreads, 0, st>>>(n, sub_chunks, P, S, b.min_len, states, tstates, LayOut{pm, O, desc, cstart, L.d_nb.as<uint32_t>()});
+        lay_apply_kernel<<<nlay, kLayThreads, 0, st>>>(n, sub_chunks, P, S, b.min_len, states, LayOut{pm, O, desc, cstart, L.d_nb.as<uint32_t>()});
         chunk_summary_fused_kernel<<<sub_chunks, 128, 0, st>>>(B, cstart, desc, b.d_summary.as<ChunkSummary>() + sb.c0);
         launches += 5;
     }
@@ -1280,7 +1277,6 @@ extern "C" int fsb_create(const fsb_params* p, int device, void* cuda_stream, fs
     }
     // tuning knobs for experiments (the defaults are what the measurements in DESIGN.md chose)
     if (const char* e = std::getenv("FSB_RUN_SPLIT")) c->run_split = (uint32_t)std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("FSB_LAY_THREAD_STATES")) c->lay_thread_states = std::atoi(e) != 0;
     if (const char* e = std::getenv("FSB_K1_R")) c->k1_batches_per_warp = (uint32_t)std::max(0, std::atoi(e));
     if (const char* e = std::getenv("FSB_K4_R")) c->k4_tiles_per_block = (uint32_t)std::max(0, std::atoi(e));
     for (Batch& b : c->batch)

@@ -122,13 +122,10 @@ __device__ __forceinline__ LayState lay_run_state(const DeviceParams& P, const S
     return st;
 }
 
-// thread_states (optional): every thread's own state, for lay_apply to pick up instead of walking over its records twice
-__global__ void __launch_bounds__(kLayThreads) lay_reduce_kernel(uint64_t n, DeviceParams P, SortedView S, uint32_t uniform_len, LayState* __restrict__ tile_states,
-                                                                 LayState* __restrict__ thread_states)
+__global__ void __launch_bounds__(kLayThreads) lay_reduce_kernel(uint64_t n, DeviceParams P, SortedView S, uint32_t uniform_len, LayState* __restrict__ tile_states)
 {
     __shared__ LayState sm[kLayThreads / 32];
     const LayState mine = lay_run_state(P, S, lay_run(n), uniform_len);
-    if (thread_states) thread_states[(size_t)blockIdx.x * kLayThreads + threadIdx.x] = mine;
     LayState total;
     lay_block_scan(mine, total, sm);
     if (threadIdx.x == 0) tile_states[blockIdx.x] = total;
@@ -187,11 +184,11 @@ struct LayOut
 };
 
 __global__ void __launch_bounds__(kLayThreads) lay_apply_kernel(uint64_t n, uint32_t n_chunks, DeviceParams P, SortedView S, uint32_t uniform_len,
-                                                                const LayState* __restrict__ tile_prefix, const LayState* __restrict__ thread_states, LayOut out)
+                                                                const LayState* __restrict__ tile_prefix, LayOut out)
 {
     __shared__ LayState sm[kLayThreads / 32];
     const LayRun run = lay_run(n);
-    const LayState mine = thread_states ? thread_states[(size_t)blockIdx.x * kLayThreads + threadIdx.x] : lay_run_state(P, S, run, uniform_len);
+    const LayState mine = lay_run_state(P, S, run, uniform_len);
     LayState total;
     const LayState excl = lay_combine(tile_prefix[blockIdx.x], lay_block_scan(mine, total, sm));
     if (run.cnt == 0) return;
