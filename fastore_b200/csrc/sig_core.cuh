@@ -50,27 +50,6 @@ FSB_HD void ascii_to_planes(const uint32_t* w, uint32_t bshift, BV<NW>& H, BV<NW
 {
     uint32_t prev = w[0];
     const uint32_t* p = w + 1;
-#ifdef FSB_K1_PLANES_UNROLLED
-    // every plane word written in place: no register shuffling between rounds, and the loads of all rounds can be in flight at once
-#pragma unroll
-    for (int j = 0; j < NW; ++j)
-    {
-        uint32_t h = 0, b1 = 0, n = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-        {
-            const uint32_t a = p[8 * j + 2 * q], b = p[8 * j + 2 * q + 1];
-            const uint32_t w0 = funnel_r(prev, a, bshift);
-            const uint32_t w1 = funnel_r(a, b, bshift);
-            prev = b;
-            const uint32_t t = (w0 & 0x0E0E0E0Eu) | ((w1 * 16u) & 0xE0E0E0E0u);
-            h = byte_perm(h, (t & 0x44444444u) * kGatherBit2, 0x7321u);
-            b1 = byte_perm(b1, (t & 0x22222222u) * kGatherBit1, 0x7321u);
-            n = byte_perm(n, (t & 0x88888888u) * kGatherBit3, 0x7321u);
-        }
-        H.w[j] = h; Lo.w[j] = b1 ^ h; Nm.w[j] = n;
-    }
-#else
 #pragma unroll
     for (int i = 0; i < NW; ++i) { H.w[i] = 0; Lo.w[i] = 0; Nm.w[i] = 0; }
 #pragma unroll 1
@@ -96,7 +75,6 @@ FSB_HD void ascii_to_planes(const uint32_t* w, uint32_t bshift, BV<NW>& H, BV<NW
         for (int i = 0; i + 1 < NW; ++i) { H.w[i] = H.w[i + 1]; Lo.w[i] = Lo.w[i + 1]; Nm.w[i] = Nm.w[i + 1]; }
         H.w[NW - 1] = h; Lo.w[NW - 1] = b1 ^ h; Nm.w[NW - 1] = n;
     }
-#endif
 }
 
 // Candidate positions of both strands (forward coordinates): in the scan window, no 'N' in the
