@@ -149,7 +149,9 @@ typedef struct fsb_ctx fsb_ctx;
 /* options for fsb_set_option */
 enum {
     FSB_OPT_PER_READ = 1,    /* also return per-read signature/info arrays (parity Mode B)        */
-    FSB_OPT_PROFILE = 2,     /* record CUDA events around every pipeline stage of fsb_run         */
+    FSB_OPT_PROFILE = 2,     /* record CUDA events around every pipeline stage of fsb_run (runs with FSB_OPT_RUN_SPLIT 1 only: overlapped
+                                sub-batches have no per-stage duration; a batch of more than 32 chunks is then run as sub-batches one after
+                                the other and their stage times add up) */
     FSB_OPT_VALIDATE = 3,    /* device-side check of the bytes behind the record table in fsb_stage / fsb_bin_chunks: sequence
                                 symbols A C G T N, quality in [offset, offset + 64) (>= offset in the 1-bit mode), 7-bit title
                                 characters; default 1.  The record table itself (lengths, offsets, mate lengths) is always checked. */
